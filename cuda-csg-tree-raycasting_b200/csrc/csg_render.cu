@@ -1,0 +1,959 @@
+// csg_render.cu — frame kernel, launcher and the C ABI of libcsg_b200 (include/csg_b200.h).
+//
+// Replaces Raycaster::{ChangeSize,Raycast,CleanUp} (RayCasting/Raycaster.cu:3-45) and the two kernels it
+// launches (RayCasting/Kernels/RaycastingKernels.cu).  sm_100a only; there is no CPU path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/csg_b200.h"
+#include "csg_kernel.cuh"
+#include "csg_scene.h"
+
+using namespace csgb;
+
+// =========================================================================================== device code
+namespace csgb {
+
+constexpr int kThreads = 256;           // 8 warps per CTA
+constexpr int kWarpTileW = 8, kWarpTileH = 4;   // one warp = one 8x4 pixel tile (Raycaster.cuh:7-8 uses the same shape)
+constexpr int kMacroW = 64, kMacroH = 32;       // sharding unit: 8x8 warp tiles
+
+// Hit details + Phong (sphere/cylinder/cubeHitDetails :183-200/:338-372/:436-457 and LightningKernel :49-111).
+__device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const float4* __restrict__ prims, const FrameParams& p)
+{
+    if (is_miss(res)) return make_float4(0.08f, 0.08f, 0.11f, 1.0f);   // :109
+    const uint32_t id = (res.m & H_META_MASK) >> H_ID_SHIFT;
+    const uint32_t kind = (res.m >> H_KIND_SHIFT) & 7u;
+    const float4 col = __ldg(&prims[id * 5 + 0]);
+    const float4 pc = __ldg(&prims[id * 5 + 1]);
+    const float t = res.t;
+    const float px = __fmaf_rn(t, r.dx, r.ox), py = __fmaf_rn(t, r.dy, r.oy), pz = __fmaf_rn(t, r.dz, r.oz);
+    float nx, ny, nz;
+    if (kind == 3u) {                                   // sphereHitDetails :189-195
+        nx = px - pc.x; ny = py - pc.y; nz = pz - pc.z;
+    } else if (kind == 5u) {                            // cubeHitDetails :446-451
+        const float bias = 1.00001f;
+        nx = (float)__float2int_rz(__fmul_rn(__fdiv_rn(px - pc.x, pc.w), bias));
+        ny = (float)__float2int_rz(__fmul_rn(__fdiv_rn(py - pc.y, pc.w), bias));
+        nz = (float)__float2int_rz(__fmul_rn(__fdiv_rn(pz - pc.z, pc.w), bias));
+    } else {                                            // cylinderHitDetails :345-365
+        const float4 pb = __ldg(&prims[id * 5 + 2]);
+        const float4 pv = __ldg(&prims[id * 5 + 3]);
+        if (res.m & H_FLAG1) { nx = -pv.x; ny = -pv.y; nz = -pv.z; }
+        else if (res.m & H_FLAG2) { nx = pv.x; ny = pv.y; nz = pv.z; }
+        else {
+            const float ocx = r.ox - pb.x, ocy = r.oy - pb.y, ocz = r.oz - pb.z;
+            const float dV = dot_ref(pv.x, pv.y, pv.z, r.dx, r.dy, r.dz);
+            const float ocv = dot_ref(pv.x, pv.y, pv.z, ocx, ocy, ocz);
+            const float m = __fmaf_rn(t, dV, ocv);
+            nx = __fmaf_rn(-pv.x, m, px - pb.x);
+            ny = __fmaf_rn(-pv.y, m, py - pb.y);
+            nz = __fmaf_rn(-pv.z, m, pz - pb.z);
+        }
+    }
+    if (!((res.m & (H_FLAG1 | H_FLAG2)) && kind == 4u)) {   // caps carry the unit axis as is; everything else is normalised
+        const float inv = __frcp_rn(__fsqrt_rn(dot_ref(nx, ny, nz, nx, ny, nz)));
+        nx *= inv; ny *= inv; nz *= inv;
+    }
+    if (res.m & H_FLIP) { nx = -nx; ny = -ny; nz = -nz; }
+    if ((res.m & H_CLS) == H_EXIT) { nx = -nx; ny = -ny; nz = -nz; }
+
+    // LightningKernel :78-103
+    const float il = __frcp_rn(__fsqrt_rn(dot_ref(p.light[0], p.light[1], p.light[2], p.light[0], p.light[1], p.light[2])));
+    const float Lx = p.light[0] * il, Ly = p.light[1] * il, Lz = p.light[2] * il;
+    float vx = p.cam_pos[0] - px, vy = p.cam_pos[1] - py, vz = p.cam_pos[2] - pz;
+    const float iv = __frcp_rn(__fsqrt_rn(dot_ref(vx, vy, vz, vx, vy, vz)));
+    vx *= iv; vy *= iv; vz *= iv;
+    const float in = __frcp_rn(__fsqrt_rn(dot_ref(nx, ny, nz, nx, ny, nz)));   // reflect() re-normalises n
+    const float ux = nx * in, uy = ny * in, uz = nz * in;
+    const float dn = __fmaf_rn(-Lz, uz, __fmaf_rn(-Lx, ux, uy * -Ly));
+    const float two = dn + dn;
+    const float rx = __fmaf_rn(-ux, two, -Lx), ry = __fmaf_rn(-uy, two, -Ly), rz = __fmaf_rn(-uz, two, -Lz);
+    const float diff = fmaxf(dot_ref(nx, ny, nz, Lx, Ly, Lz), 0.0f);
+    const float sb = fmaxf(dot_ref(vx, vy, vz, rx, ry, rz), 0.0f);
+    const float spec = powf(sb, 30.0f);
+    const float k = __fmaf_rn(spec, 0.7f, __fmaf_rn(diff, 0.8f, 0.2f));
+    float4 o;
+    o.x = fminf(fmaxf(col.x * k, 0.0f), 1.0f);
+    o.y = fminf(fmaxf(col.y * k, 0.0f), 1.0f);
+    o.z = fminf(fmaxf(col.z * k, 0.0f), 1.0f);
+    o.w = 1.0f;
+    return o;
+}
+
+__device__ __forceinline__ uint32_t to_u8(float c)
+{  // Q12: (int)(clamp(c,0,1)*255 + 0.5)
+    return (uint32_t)__float2int_rz(__fadd_rn(__fmul_rn(fminf(fmaxf(c, 0.0f), 1.0f), 255.0f), 0.5f));
+}
+
+// CSGRayCast (RaycastingKernels.cu:459-512) re-expressed as an explicit-frame evaluation; equivalence with the
+// reference's GoTo/Compute/SaveLft action machine is argued in DESIGN.md §"State machine".
+//   frame (one per operator on the current path, in shared memory): word0 = saved tmin (F_SAVE_LFT) or saved hit t,
+//   word1 = saved hit meta | return state.
+__device__ __forceinline__ Hit traverse(const uint4* __restrict__ nodes, const float4* __restrict__ prims,
+                                        const uint32_t* __restrict__ table, uint2* __restrict__ stack,
+                                        const int stack_stride, const Ray& r, const bool root_is_leaf)
+{
+    enum { ST_ENTER = 0, ST_LOOPL = 1, ST_LOOPR = 2, ST_COMPUTE = 3, ST_RETURN = 4, ST_DONE = 5 };
+    Hit L = make_miss(), R = make_miss();
+    float tmin = 0.0f;                        // :466
+    if (root_is_leaf) {                        // GoTo's leaf branch on the virtual root: no box test (:582-594, Q7)
+        bool go;
+        eval_child(nodes, prims, 0, r, tmin, false, L, go);
+        return L;
+    }
+    int n = 0, sp = 0, st = ST_ENTER;
+    while (st != ST_DONE) {
+        if (st <= ST_LOOPR) {
+            const uint4 nb = nodes[2 * n + 1];
+            const uint32_t meta = nb.w;
+            const uint32_t op = meta & 7u;
+            const int cl = n + 1, cr = (int)(meta >> 8);
+            bool goL = false, goR = false;
+            if (st != ST_LOOPR) eval_child(nodes, prims, cl, r, tmin, st == ST_ENTER, L, goL);
+            if (st == ST_ENTER && op != 0u && !goL && is_miss(L)) {
+                // left operand of a Difference/Intersection already missed: the node's result is Miss whatever the right
+                // operand does (all M* cells of both tables, :670-677) — skip the right subtree (Q8)
+                R = L = make_miss();
+                st = ST_RETURN;
+            } else {
+                if (st != ST_LOOPL) eval_child(nodes, prims, cr, r, tmin, st == ST_ENTER, R, goR);
+                if (st != ST_ENTER) {
+                    st = ST_COMPUTE;
+                } else if (!goL && !goR) {
+                    st = ST_COMPUTE;                                                   // :578
+                } else if (!goL) {                                                     // :556-561
+                    stack[sp * stack_stride] = make_uint2(__float_as_uint(L.t), L.m | F_LOAD_LFT);
+                    ++sp; n = cr;
+                } else if (!goR) {                                                     // :562-567
+                    stack[sp * stack_stride] = make_uint2(__float_as_uint(R.t), R.m | F_LOAD_RGH);
+                    ++sp; n = cl;
+                } else {                                                               // :568-574
+                    stack[sp * stack_stride] = make_uint2(__float_as_uint(tmin), F_SAVE_LFT);
+                    ++sp; n = cl;
+                }
+            }
+        }
+        if (st == ST_COMPUTE) {                                                        // Compute :597-661
+            const uint32_t meta = nodes[2 * n + 1].w;
+            const uint32_t op = meta & 7u;
+            const uint32_t e = table[op * 9u + (L.m & H_CLS) * 3u + (R.m & H_CLS)];
+            const uint32_t o = (L.t < R.t) ? (e & 7u) : (L.t > R.t) ? ((e >> 3) & 7u) : ((e >> 6) & 7u);
+            if (o == O_RETL) { R = L; st = ST_RETURN; }
+            else if (o == O_RETR || o == O_RETR_FLIP) {
+                if (o == O_RETR_FLIP) R.m ^= (H_FLIP | 1u);                            // :629-635 toggles Flip and Enter<->Exit
+                L = R; st = ST_RETURN;
+            } else if (o == O_LOOPL) {                                                 // :640-646
+                tmin = L.t;
+                if (meta & kMetaLeftLeaf) st = ST_LOOPL;
+                else { stack[sp * stack_stride] = make_uint2(__float_as_uint(R.t), R.m | F_LOAD_RGH); ++sp; n = n + 1; st = ST_ENTER; }
+            } else if (o == O_LOOPR) {                                                 // :647-653
+                tmin = R.t;
+                if (meta & kMetaRightLeaf) st = ST_LOOPR;
+                else { stack[sp * stack_stride] = make_uint2(__float_as_uint(L.t), L.m | F_LOAD_LFT); ++sp; n = (int)(meta >> 8); st = ST_ENTER; }
+            } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
+        }
+        if (st == ST_RETURN) {                  // action = actionStack.pop(); node = GetParent() (:624-625 etc.)
+            if (sp == 0) { st = ST_DONE; }
+            else {
+                --sp;
+                const uint2 f = stack[sp * stack_stride];
+                n = (int)nodes[2 * n + 1].z;    // parent
+                const uint32_t ret = f.y & F_RET_MASK;
+                if (ret == F_SAVE_LFT) {        // SaveLft :476-481: restore tmin, keep the left result, go right
+                    tmin = __uint_as_float(f.x);
+                    const uint32_t pm = nodes[2 * n + 1].w;
+                    if ((pm & 7u) != 0u && is_miss(L)) {
+                        R = L = make_miss();    // same short-circuit as above; stay in ST_RETURN
+                    } else {
+                        stack[sp * stack_stride] = make_uint2(__float_as_uint(L.t), L.m | F_LOAD_LFT);
+                        ++sp; n = (int)(pm >> 8); st = ST_ENTER;
+                    }
+                } else if (ret == F_LOAD_LFT) { // :611-614
+                    R = L; L.t = __uint_as_float(f.x); L.m = f.y & H_META_MASK; st = ST_COMPUTE;
+                } else {                        // F_LOAD_RGH :615-618
+                    L = R; R.t = __uint_as_float(f.x); R.m = f.y & H_META_MASK; st = ST_COMPUTE;
+                }
+            }
+        }
+    }
+    return L;                                   // :511
+}
+
+template <int MODE, bool TREE_SMEM>
+__global__ void __launch_bounds__(kThreads, 2) csg_frame_kernel(const __grid_constant__ FrameParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* s_nodes = reinterpret_cast<uint4*>(smem_raw);
+    const int n_staged = TREE_SMEM ? p.n_nodes : 0;
+    uint2* s_stack = reinterpret_cast<uint2*>(s_nodes + 2 * n_staged);
+    uint32_t* s_table = reinterpret_cast<uint32_t*>(s_stack + (size_t)p.stack_levels * kThreads);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const float ox = p.cam_pos[0], oy = p.cam_pos[1], oz = p.cam_pos[2];
+
+    if (tid < 27) s_table[tid] = kOutcomeTable[tid];
+    if (TREE_SMEM) {
+        // Stage the tree once per CTA, origin-relative: every primary ray shares the camera position, so the
+        // (bound - origin) / (origin - centre) subtractions of isBVHNodeHit :724-729, cubeHit :389-394 and
+        // sphereHit :139-143 are done here once per node instead of once per ray (same single FADD, same bits).
+        for (int i = tid; i < p.n_nodes; i += kThreads) {
+            uint4 ua = p.nodes[2 * i], ub = p.nodes[2 * i + 1];
+            float4 a = as_float4(ua), b = as_float4(ub);
+            if ((ub.w & 7u) == 3u) {
+                a.x = __fsub_rn(ox, a.x); a.y = __fsub_rn(oy, a.y); a.z = __fsub_rn(oz, a.z);
+            } else {
+                a.x = __fsub_rn(a.x, ox); a.y = __fsub_rn(a.y, oy); a.z = __fsub_rn(a.z, oz);
+                a.w = __fsub_rn(a.w, ox); b.x = __fsub_rn(b.x, oy); b.y = __fsub_rn(b.y, oz);
+            }
+            s_nodes[2 * i] = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+            s_nodes[2 * i + 1] = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), ub.z, ub.w);
+        }
+    }
+    __syncthreads();
+    const uint4* nodes = TREE_SMEM ? s_nodes : p.nodes;   // !TREE_SMEM: p.nodes was staged by csg_stage_kernel
+    uint2* my_stack = s_stack + tid;
+
+    // per-frame constants of ray generation, RaycastKernel :11-16
+    const float wf = (float)p.width, hf = (float)p.height;
+    const float wm1 = __fsub_rn(wf, 1.0f), hm1 = __fsub_rn(hf, 1.0f);
+    const float aspect = __fdiv_rn(wf, hf);
+    const float th = p.tan_half_fov;   // tan(cam.fov / 2.0f), :15-16
+
+    for (;;) {
+        unsigned long long ticket = 0;
+        if (lane == 0) ticket = atomicAdd(p.tile_counter, 1ull) - p.counter_base;
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= (unsigned long long)p.n_local_warp_tiles) break;
+        const int k = (int)(ticket & 63ull);
+        const int macro = (int)(ticket >> 6) * p.shard_count + p.shard_rank;
+        const int mx = macro % p.macro_x, my = macro / p.macro_x;
+        const int kx = (k & 1) | ((k >> 1) & 2) | ((k >> 2) & 4);        // Morton order inside the macro tile
+        const int ky = ((k >> 1) & 1) | ((k >> 2) & 2) | ((k >> 3) & 4);
+        const int x = mx * kMacroW + kx * kWarpTileW + (lane & 7);
+        const int y = my * kMacroH + ky * kWarpTileH + (lane >> 3);
+        const bool active = x < p.width && y < p.height;
+        if (__ballot_sync(0xffffffffu, active) == 0u) continue;
+
+        Hit res = make_miss();
+        Ray r;
+        r.ox = ox; r.oy = oy; r.oz = oz;
+        if (active) {
+            // RaycastKernel :11-27 + Ray ctor (Ray.cuh:12-18)
+            const float u = __fdiv_rn(__fadd_rn((float)x, 0.5f), wm1);
+            const float v = __fdiv_rn(__fadd_rn((float)y, 0.5f), hm1);
+            const float nx = __fmul_rn(__fmul_rn(aspect, __fmaf_rn(u, 2.0f, -1.0f)), th);
+            const float ny = __fmul_rn(__fsub_rn(1.0f, __fadd_rn(v, v)), th);
+            float cx = __fadd_rn(p.forward[0], __fmaf_rn(p.right[0], nx, __fmul_rn(p.up[0], ny)));
+            float cy = __fadd_rn(p.forward[1], __fmaf_rn(p.right[1], nx, __fmul_rn(p.up[1], ny)));
+            float cz = __fadd_rn(p.forward[2], __fmaf_rn(p.right[2], nx, __fmul_rn(p.up[2], ny)));
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {   // normalize() then the Ray ctor normalises again (Q3)
+                const float inv = __frcp_rn(__fsqrt_rn(dot_ref(cx, cy, cz, cx, cy, cz)));
+                cx = __fmul_rn(inv, cx); cy = __fmul_rn(inv, cy); cz = __fmul_rn(inv, cz);
+            }
+            r.dx = cx; r.dy = cy; r.dz = cz;
+            r.ix = __frcp_rn(cx); r.iy = __frcp_rn(cy); r.iz = __frcp_rn(cz);
+            res = traverse(nodes, p.prims, s_table, my_stack, kThreads, r, p.root_is_leaf != 0);
+        }
+
+        const size_t pix = (size_t)y * p.width + x;   // :33
+        if (MODE == OUT_AOV) {
+            if (active) {
+                const bool hit = !is_miss(res);
+                if (p.aov_hit) p.aov_hit[pix] = hit ? 1 : 0;
+                if (p.aov_prim) p.aov_prim[pix] = hit ? (int32_t)((res.m & H_META_MASK) >> H_ID_SHIFT) : -1;
+                if (p.aov_t) p.aov_t[pix] = hit ? res.t : -1.0f;
+            }
+        } else {
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) c = shade_pixel(res, r, p.prims, p);
+            if (MODE == OUT_F32) {
+                if (active) reinterpret_cast<float4*>(p.out)[pix] = c;
+            } else {
+                const uint32_t px8 = to_u8(c.x) | (to_u8(c.y) << 8) | (to_u8(c.z) << 16) | 0xFF000000u;
+                // four horizontally adjacent pixels -> one 16-byte store
+                const uint32_t p1 = __shfl_down_sync(0xffffffffu, px8, 1);
+                const uint32_t p2 = __shfl_down_sync(0xffffffffu, px8, 2);
+                const uint32_t p3 = __shfl_down_sync(0xffffffffu, px8, 3);
+                if ((p.width & 3) == 0) {
+                    if (active && (lane & 3) == 0) reinterpret_cast<uint4*>(p.out)[pix >> 2] = make_uint4(px8, p1, p2, p3);
+                } else if (active) {
+                    reinterpret_cast<uint32_t*>(p.out)[pix] = px8;
+                }
+            }
+        }
+    }
+}
+
+// tan(cam.fov / 2.0f) of RaycastKernel :15-16, evaluated with the device tanf once per field of view (kept out of
+// the frame kernel: tanf's large-argument path needs a local-memory scratch array).
+__global__ void csg_tan_kernel(float fov, float* out) { *out = tanf(__fmul_rn(fov, 0.5f)); }
+
+// Pre-stages an origin-relative copy of the tree in global memory for trees that do not fit in shared memory.
+__global__ void csg_stage_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n_nodes, float ox, float oy, float oz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    uint4 ua = src[2 * i], ub = src[2 * i + 1];
+    float4 a = as_float4(ua), b = as_float4(ub);
+    if ((ub.w & 7u) == 3u) {
+        a.x = __fsub_rn(ox, a.x); a.y = __fsub_rn(oy, a.y); a.z = __fsub_rn(oz, a.z);
+    } else {
+        a.x = __fsub_rn(a.x, ox); a.y = __fsub_rn(a.y, oy); a.z = __fsub_rn(a.z, oz);
+        a.w = __fsub_rn(a.w, ox); b.x = __fsub_rn(b.x, oy); b.y = __fsub_rn(b.y, oz);
+    }
+    dst[2 * i] = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+    dst[2 * i + 1] = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), ub.z, ub.w);
+}
+
+}  // namespace csgb
+
+// =========================================================================================== host side
+struct csg_scene {
+    Scene scene;
+};
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                     \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) return fail(CSG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct Shard {  // one GPU's share of the frame
+    int device = 0;
+    int rank = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+    uint4* d_nodes = nullptr;
+    uint4* d_staged = nullptr;   // only when the tree does not fit in shared memory
+    float4* d_prims = nullptr;
+    unsigned long long* d_counter = nullptr;
+    unsigned long long counter_base = 0;
+    float* d_tan = nullptr;
+    int grid = 0;
+    int n_local_warp_tiles = 0;
+    uint8_t* target = nullptr;   // where this shard writes RGBA8 (root framebuffer, possibly a peer pointer)
+    void* ipc_mapped = nullptr;
+};
+
+}  // namespace
+
+struct csg_context {
+    int width = 0, height = 0;
+    int macro_x = 0, macro_y = 0;
+    int shard_count = 1;
+    bool multi_process = false;
+    FlatTree tree;
+    bool tree_in_smem = true;
+    size_t smem_bytes = 0;
+    int stack_levels = 1;
+    std::vector<Shard> shards;   // in-process: one per device; multi-process: exactly one
+    uint8_t* d_fb = nullptr;     // RGBA8 framebuffer on the root device (or this rank's device)
+    float* d_f32 = nullptr;      // lazily allocated
+    uint8_t* d_aov_hit = nullptr;
+    int32_t* d_aov_prim = nullptr;
+    float* d_aov_t = nullptr;
+    uint64_t launches = 0;
+    float cached_fov = -1.f, cached_tan = 0.f;   // device tanf(fov/2) of the last field of view seen
+    float last_ms = 0.f;
+    bool frame_pending = false;
+    std::string info;
+};
+
+namespace {
+
+template <int MODE>
+int launch_mode(csg_context* c, Shard& s, const FrameParams& fp)
+{
+    cudaError_t e;
+    if (c->tree_in_smem) {
+        csg_frame_kernel<MODE, true><<<s.grid, kThreads, c->smem_bytes, s.stream>>>(fp);
+    } else {
+        csg_frame_kernel<MODE, false><<<s.grid, kThreads, c->smem_bytes, s.stream>>>(fp);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    return CSG_OK;
+}
+
+template <int MODE, bool SM>
+int configure_kernel(size_t smem, int* blocks_per_sm)
+{
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, SM>, kThreads, smem));
+    return CSG_OK;
+}
+
+void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, const float light[3], FrameParams& fp)
+{
+    std::memset(&fp, 0, sizeof fp);
+    for (int i = 0; i < 3; ++i) {
+        fp.cam_pos[i] = cam->pos[i];
+        fp.forward[i] = cam->forward[i];
+        fp.right[i] = cam->right[i];
+        fp.up[i] = cam->up[i];
+        fp.light[i] = light ? light[i] : 0.f;
+    }
+    fp.fov = cam->fov;
+    fp.tan_half_fov = c->cached_tan;
+    fp.width = c->width;
+    fp.height = c->height;
+    fp.macro_x = c->macro_x;
+    fp.macro_y = c->macro_y;
+    fp.shard_rank = s.rank;
+    fp.shard_count = c->shard_count;
+    fp.n_local_warp_tiles = s.n_local_warp_tiles;
+    fp.counter_base = s.counter_base;
+    fp.tile_counter = s.d_counter;
+    fp.nodes = c->tree_in_smem ? s.d_nodes : s.d_staged;
+    fp.prims = s.d_prims;
+    fp.n_nodes = (int)c->tree.nodes.size();
+    fp.root_is_leaf = c->tree.root_is_leaf ? 1 : 0;
+    fp.stack_levels = c->stack_levels;
+}
+
+// Enqueue one frame on every shard.  mode: OUT_RGBA8 -> out = rgba8 target (NULL: each shard's own target),
+// OUT_F32 / OUT_AOV only on single-shard contexts.
+int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], int mode, void* out)
+{
+    if (!c || !cam) return fail(CSG_ERR_ARG, "null argument");
+    if (mode != OUT_RGBA8 && c->shards.size() != 1) return fail(CSG_ERR_ARG, "f32/aov output needs a single-shard context");
+    Shard& root = c->shards[0];
+    CU(cudaSetDevice(root.device));
+    if (!(cam->fov == c->cached_fov)) {   // new field of view: one tiny launch + 4-byte readback, then cached
+        csg_tan_kernel<<<1, 1, 0, root.stream>>>(cam->fov, root.d_tan);
+        CU(cudaMemcpyAsync(&c->cached_tan, root.d_tan, sizeof(float), cudaMemcpyDeviceToHost, root.stream));
+        CU(cudaStreamSynchronize(root.stream));
+        c->cached_fov = cam->fov;
+        c->launches++;
+    }
+    CU(cudaEventRecord(root.ev_start, root.stream));
+    for (size_t i = 1; i < c->shards.size(); ++i) {   // peers start after the root's start mark
+        CU(cudaSetDevice(c->shards[i].device));
+        CU(cudaStreamWaitEvent(c->shards[i].stream, root.ev_start, 0));
+    }
+    const int total_warps_per_cta = kThreads / 32;
+    for (Shard& s : c->shards) {
+        CU(cudaSetDevice(s.device));
+        FrameParams fp;
+        fill_params(c, s, cam, light, fp);
+        if (!c->tree_in_smem) {
+            const int n = (int)c->tree.nodes.size();
+            csg_stage_kernel<<<(n + 255) / 256, 256, 0, s.stream>>>(s.d_nodes, s.d_staged, n, cam->pos[0], cam->pos[1], cam->pos[2]);
+            c->launches++;
+        }
+        int rc = CSG_OK;
+        if (mode == OUT_RGBA8) {
+            fp.out = out ? out : (void*)s.target;
+            if (!fp.out) return fail(CSG_ERR_ARG, "no output target");
+            rc = launch_mode<OUT_RGBA8>(c, s, fp);
+        } else if (mode == OUT_F32) {
+            fp.out = out;
+            rc = launch_mode<OUT_F32>(c, s, fp);
+        } else {
+            fp.aov_hit = c->d_aov_hit;
+            fp.aov_prim = c->d_aov_prim;
+            fp.aov_t = c->d_aov_t;
+            rc = launch_mode<OUT_AOV>(c, s, fp);
+        }
+        if (rc) return rc;
+        c->launches++;
+        // every warp of the grid draws exactly one ticket past the end
+        s.counter_base += (unsigned long long)s.n_local_warp_tiles + (unsigned long long)s.grid * total_warps_per_cta;
+        if (&s != &root) CU(cudaEventRecord(s.ev_done, s.stream));
+    }
+    CU(cudaSetDevice(root.device));
+    for (size_t i = 1; i < c->shards.size(); ++i) CU(cudaStreamWaitEvent(root.stream, c->shards[i].ev_done, 0));
+    CU(cudaEventRecord(root.ev_done, root.stream));
+    c->frame_pending = true;
+    return CSG_OK;
+}
+
+int sync_frame(csg_context* c)
+{
+    Shard& root = c->shards[0];
+    CU(cudaSetDevice(root.device));
+    CU(cudaEventSynchronize(root.ev_done));
+    if (c->frame_pending) {
+        CU(cudaEventElapsedTime(&c->last_ms, root.ev_start, root.ev_done));
+        c->frame_pending = false;
+    }
+    CU(cudaGetLastError());
+    return CSG_OK;
+}
+
+bool is_device_pointer(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int create_context(const csg_scene* scene, int width, int height, const std::vector<int>& devices, int shard_rank0,
+                   int shard_count, bool multi_process, csg_context** out)
+{
+    if (!scene || !out) return fail(CSG_ERR_ARG, "null argument");
+    if (width < 2 || height < 2) return fail(CSG_ERR_ARG, "width and height must be >= 2");  // (w-1),(h-1) divisors, Q1
+    if (scene->scene.nodes.empty()) return fail(CSG_ERR_ARG, "empty scene");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CSG_ERR_NO_DEVICE, "no CUDA device available (libcsg_b200 has no CPU fallback)");
+    }
+    for (int d : devices)
+        if (d < 0 || d >= ndev) return fail(CSG_ERR_NO_DEVICE, "requested CUDA device " + std::to_string(d) + " of " + std::to_string(ndev));
+
+    csg_context* c = new csg_context();
+    c->width = width;
+    c->height = height;
+    c->macro_x = (width + kMacroW - 1) / kMacroW;
+    c->macro_y = (height + kMacroH - 1) / kMacroH;
+    c->shard_count = shard_count;
+    c->multi_process = multi_process;
+    flatten(scene->scene, scene->scene.optimize, c->tree);
+    c->stack_levels = std::max(1, c->tree.depth);
+
+    auto cleanup_fail = [&](int code) { csg_free_context(c); return code; };
+
+    // shared memory plan: [tree 32 B/node][stack 8 B x levels x threads][table 27 x 4 B]
+    CU(cudaSetDevice(devices[0]));
+    int max_optin = 0, sms = 0;
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, devices[0]));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devices[0]));
+    const size_t tree_bytes = c->tree.nodes.size() * sizeof(NodeRec);
+    const size_t stack_bytes = (size_t)c->stack_levels * kThreads * sizeof(uint2);
+    const size_t table_bytes = 32 * sizeof(uint32_t);
+    // keep at least two CTAs per SM when the tree is staged in shared memory
+    c->tree_in_smem = tree_bytes + stack_bytes + table_bytes <= (size_t)max_optin / 2 - 1024;
+    c->smem_bytes = (c->tree_in_smem ? tree_bytes : 0) + stack_bytes + table_bytes;
+    if (c->smem_bytes > (size_t)max_optin) {
+        g_err = "tree depth " + std::to_string(c->tree.depth) + " needs " + std::to_string(c->smem_bytes) +
+                " bytes of traversal stack per CTA; limit is " + std::to_string(max_optin) +
+                " (the reference's own stacks hold 32 entries, RaycastingKernels.cuh:19)";
+        return cleanup_fail(CSG_ERR_LIMIT);
+    }
+
+    const int total_macros = c->macro_x * c->macro_y;
+    c->shards.resize(devices.size());
+    for (size_t i = 0; i < devices.size(); ++i) {
+        Shard& s = c->shards[i];
+        s.device = devices[i];
+        s.rank = shard_rank0 + (int)i;
+        CU(cudaSetDevice(s.device));
+        int bps = 0, rc;
+        if (c->tree_in_smem) {
+            if ((rc = configure_kernel<OUT_RGBA8, true>(c->smem_bytes, &bps))) return cleanup_fail(rc);
+            if ((rc = configure_kernel<OUT_F32, true>(c->smem_bytes, &bps))) return cleanup_fail(rc);
+            if ((rc = configure_kernel<OUT_AOV, true>(c->smem_bytes, &bps))) return cleanup_fail(rc);
+            if ((rc = configure_kernel<OUT_RGBA8, true>(c->smem_bytes, &bps))) return cleanup_fail(rc);
+        } else {
+            if ((rc = configure_kernel<OUT_F32, false>(c->smem_bytes, &bps))) return cleanup_fail(rc);
+            if ((rc = configure_kernel<OUT_AOV, false>(c->smem_bytes, &bps))) return cleanup_fail(rc);
+            if ((rc = configure_kernel<OUT_RGBA8, false>(c->smem_bytes, &bps))) return cleanup_fail(rc);
+        }
+        if (bps < 1) { g_err = "kernel does not fit on an SM"; return cleanup_fail(CSG_ERR_LIMIT); }
+        int dev_sms = 0;
+        CU(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s.device));
+        const int my_macros = (total_macros - s.rank + shard_count - 1) / shard_count;
+        s.n_local_warp_tiles = my_macros * 64;
+        const int want = (s.n_local_warp_tiles + (kThreads / 32) - 1) / (kThreads / 32);
+        s.grid = std::max(1, std::min(dev_sms * bps, want));   // persistent CTAs: a multiple of the SM count
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&s.ev_start));
+        CU(cudaEventCreate(&s.ev_done));
+        CU(cudaMalloc(&s.d_nodes, std::max<size_t>(tree_bytes, 32)));
+        CU(cudaMemcpy(s.d_nodes, c->tree.nodes.data(), tree_bytes, cudaMemcpyHostToDevice));
+        if (!c->tree_in_smem) CU(cudaMalloc(&s.d_staged, tree_bytes));
+        const size_t prim_bytes = c->tree.prims.size() * sizeof(PrimRec);
+        CU(cudaMalloc(&s.d_prims, std::max<size_t>(prim_bytes, 80)));
+        CU(cudaMemcpy(s.d_prims, c->tree.prims.data(), prim_bytes, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&s.d_tan, sizeof(float)));
+        CU(cudaMalloc(&s.d_counter, sizeof(unsigned long long)));
+        CU(cudaMemset(s.d_counter, 0, sizeof(unsigned long long)));
+        if (i == 0) {
+            CU(cudaMalloc(&c->d_fb, (size_t)width * height * 4));
+            CU(cudaMemset(c->d_fb, 0, (size_t)width * height * 4));
+        } else {
+            // NVLink peer stores into the root framebuffer
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, s.device, devices[0]));
+            if (!can) { g_err = "device " + std::to_string(s.device) + " cannot access device " + std::to_string(devices[0]) + " (P2P)"; return cleanup_fail(CSG_ERR_CUDA); }
+            cudaError_t pe = cudaDeviceEnablePeerAccess(devices[0], 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { g_err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe); return cleanup_fail(CSG_ERR_CUDA); }
+            cudaGetLastError();
+        }
+        s.target = c->d_fb;
+    }
+    char buf[512];
+    std::snprintf(buf, sizeof buf,
+                  "{\"threads_per_cta\": %d, \"ctas\": %d, \"sms\": %d, \"smem_bytes_per_cta\": %zu, \"tree_bytes\": %zu, "
+                  "\"tree_in_smem\": %s, \"stack_levels\": %d, \"n_nodes\": %zu, \"n_prims\": %zu, \"shards\": %d, "
+                  "\"macro_tiles\": %d, \"optimize\": %d}",
+                  kThreads, c->shards[0].grid, sms, c->smem_bytes, tree_bytes, c->tree_in_smem ? "true" : "false",
+                  c->stack_levels, c->tree.nodes.size(), c->tree.prims.size(), shard_count, total_macros, scene->scene.optimize);
+    c->info = buf;
+    *out = c;
+    return CSG_OK;
+}
+
+}  // namespace
+
+// =========================================================================================== C ABI
+extern "C" {
+
+const char* csg_last_error(void) { return g_err.c_str(); }
+const char* csg_version(void) { return "csg_b200 0.1 (sm_100a)"; }
+
+int csg_parse_scene(const char* text, size_t len, csg_scene** out)
+{
+    if (!text || !out) return fail(CSG_ERR_ARG, "null argument");
+    csg_scene* s = new csg_scene();
+    std::string err = parse_scene(text, len, s->scene);
+    if (!err.empty()) {
+        delete s;
+        return fail(CSG_ERR_PARSE, err);
+    }
+    s->scene.optimize = 1;
+    *out = s;
+    return CSG_OK;
+}
+
+int csg_load_scene(const char* path, csg_scene** out)
+{
+    if (!path || !out) return fail(CSG_ERR_ARG, "null argument");
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return fail(CSG_ERR_IO, std::string("cannot open ") + path);
+    std::stringstream ss;
+    ss << f.rdbuf();   // Application::LoadCSGTree reads the whole file, Application.cpp:59-75
+    const std::string text = ss.str();
+    return csg_parse_scene(text.data(), text.size(), out);
+}
+
+void csg_free_scene(csg_scene* scene) { delete scene; }
+
+int csg_scene_counts(const csg_scene* scene, int* n_nodes, int* n_prims, int* depth)
+{
+    if (!scene) return fail(CSG_ERR_ARG, "null scene");
+    if (n_nodes) *n_nodes = (int)scene->scene.nodes.size();
+    if (n_prims) *n_prims = (int)scene->scene.prims.size();
+    if (depth) *depth = scene->scene.depth();
+    return CSG_OK;
+}
+
+int csg_scene_dump(const csg_scene* scene, void* nodes44, void* prims48)
+{
+    if (!scene) return fail(CSG_ERR_ARG, "null scene");
+    if (nodes44) std::memcpy(nodes44, scene->scene.nodes.data(), scene->scene.nodes.size() * sizeof(RefNode));
+    if (prims48) std::memcpy(prims48, scene->scene.prims.data(), scene->scene.prims.size() * sizeof(RefPrim));
+    return CSG_OK;
+}
+
+size_t csg_scene_write(const csg_scene* scene, char* buf, size_t buflen)
+{
+    if (!scene) return 0;
+    const std::string s = write_scene(scene->scene);
+    if (buf && buflen) {
+        const size_t n = std::min(buflen - 1, s.size());
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return s.size();
+}
+
+size_t csg_generate_scene(int n_primitives, uint64_t seed, char* buf, size_t buflen)
+{
+    const std::string s = generate_scene(n_primitives, seed);
+    if (buf && buflen) {
+        const size_t n = std::min(buflen - 1, s.size());
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return s.size();
+}
+
+int csg_scene_set_optimize(csg_scene* scene, int level)
+{
+    if (!scene) return fail(CSG_ERR_ARG, "null scene");
+    scene->scene.optimize = level < 0 ? 0 : level;
+    return CSG_OK;
+}
+
+// ---- camera / light (host math mirrors Camera.cpp:4-36 and DirectionalLight.h:8-18 operation for operation)
+static void cam_normalize(float* v)
+{
+    float length = (float)std::sqrt((double)(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
+    if (length > 0) {
+        v[0] /= length;
+        v[1] /= length;
+        v[2] /= length;
+    }
+}
+static void cam_update(csg_camera* c)
+{
+    const double rx = c->pitch, ry = c->yaw;
+    c->forward[0] = (float)(-std::sin(ry) * std::cos(rx));
+    c->forward[1] = (float)std::sin(rx);
+    c->forward[2] = (float)(-std::cos(ry) * std::cos(rx));
+    cam_normalize(c->forward);
+    c->right[0] = (float)std::cos(ry);
+    c->right[1] = 0;
+    c->right[2] = (float)-std::sin(ry);
+    cam_normalize(c->right);
+    c->up[0] = c->forward[1] * c->right[2] - c->forward[2] * c->right[1];
+    c->up[1] = c->forward[2] * c->right[0] - c->forward[0] * c->right[2];
+    c->up[2] = c->forward[0] * c->right[1] - c->forward[1] * c->right[0];
+    cam_normalize(c->up);
+}
+
+void csg_camera_default(csg_camera* cam)
+{
+    if (!cam) return;
+    cam->pos[0] = 0; cam->pos[1] = 0; cam->pos[2] = 5;
+    cam->pitch = 0; cam->yaw = 0;
+    cam->fov = 90.0f * 3.14159f / 180.0f;
+    cam_update(cam);
+}
+
+void csg_camera_set(csg_camera* cam, float x, float y, float z, float pitch, float yaw)
+{
+    if (!cam) return;
+    cam->pos[0] = x; cam->pos[1] = y; cam->pos[2] = z;
+    cam->pitch = std::fmax(-89.0f * 3.14159f / 180.0f, std::fmin(89.0f * 3.14159f / 180.0f, pitch));
+    cam->yaw = yaw;
+    cam_update(cam);
+}
+
+void csg_camera_set_fov_degrees(csg_camera* cam, float degrees)
+{
+    if (cam) cam->fov = degrees * 3.14159f / 180.0f;
+}
+
+void csg_light_default(csg_light* l)
+{
+    if (!l) return;
+    l->polar = -60.f * 3.14159f / 180.f;
+    l->azimuth = -45.f * 3.14159f / 180.f;
+}
+
+void csg_light_direction(const csg_light* l, float out3[3])
+{
+    out3[0] = sinf(l->polar) * cosf(l->azimuth);
+    out3[1] = cosf(l->polar);
+    out3[2] = sinf(l->polar) * sinf(l->azimuth);
+}
+
+// ---- contexts
+int csg_upload(const csg_scene* scene, int width, int height, int n_gpus, csg_context** out)
+{
+    if (n_gpus < 1) return fail(CSG_ERR_ARG, "n_gpus must be >= 1");
+    std::vector<int> devs;
+    for (int i = 0; i < n_gpus; ++i) devs.push_back(i);
+    return create_context(scene, width, height, devs, 0, n_gpus, false, out);
+}
+
+int csg_upload_shard(const csg_scene* scene, int width, int height, int device, int shard_rank, int shard_count, csg_context** out)
+{
+    if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return fail(CSG_ERR_ARG, "bad shard rank/count");
+    std::vector<int> devs{device};
+    return create_context(scene, width, height, devs, shard_rank, shard_count, true, out);
+}
+
+void csg_free_context(csg_context* c)
+{
+    if (!c) return;
+    for (Shard& s : c->shards) {
+        cudaSetDevice(s.device);
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.ipc_mapped) cudaIpcCloseMemHandle(s.ipc_mapped);
+        cudaFree(s.d_nodes);
+        cudaFree(s.d_staged);
+        cudaFree(s.d_prims);
+        cudaFree(s.d_counter);
+        cudaFree(s.d_tan);
+        if (s.ev_start) cudaEventDestroy(s.ev_start);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (!c->shards.empty()) cudaSetDevice(c->shards[0].device);
+    cudaFree(c->d_fb);
+    cudaFree(c->d_f32);
+    cudaFree(c->d_aov_hit);
+    cudaFree(c->d_aov_prim);
+    cudaFree(c->d_aov_t);
+    cudaGetLastError();
+    delete c;
+}
+
+int csg_render_enqueue(csg_context* ctx, const csg_camera* cam, const csg_light* light, uint8_t* rgba8_dev)
+{
+    if (!ctx || !cam || !light) return fail(CSG_ERR_ARG, "null argument");
+    float ld[3];
+    csg_light_direction(light, ld);
+    return enqueue_frame(ctx, cam, ld, OUT_RGBA8, rgba8_dev);
+}
+
+int csg_sync(csg_context* ctx)
+{
+    if (!ctx) return fail(CSG_ERR_ARG, "null context");
+    return sync_frame(ctx);
+}
+
+int csg_last_frame_ms(csg_context* ctx, float* ms)
+{
+    if (!ctx || !ms) return fail(CSG_ERR_ARG, "null argument");
+    if (ctx->frame_pending) {
+        int rc = sync_frame(ctx);
+        if (rc) return rc;
+    }
+    *ms = ctx->last_ms;
+    return CSG_OK;
+}
+
+uint64_t csg_launch_count(const csg_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int csg_framebuffer(csg_context* ctx, uint8_t** rgba8_dev)
+{
+    if (!ctx || !rgba8_dev) return fail(CSG_ERR_ARG, "null argument");
+    *rgba8_dev = ctx->d_fb;
+    return CSG_OK;
+}
+
+int csg_framebuffer_ipc_handle(csg_context* ctx, void* handle64)
+{
+    if (!ctx || !handle64) return fail(CSG_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    CU(cudaSetDevice(ctx->shards[0].device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_fb));
+    std::memcpy(handle64, &h, 64);
+    return CSG_OK;
+}
+
+int csg_set_gather_target_ipc(csg_context* ctx, const void* handle64)
+{
+    if (!ctx || !handle64) return fail(CSG_ERR_ARG, "null argument");
+    Shard& s = ctx->shards[0];
+    CU(cudaSetDevice(s.device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    if (s.ipc_mapped) cudaIpcCloseMemHandle(s.ipc_mapped);
+    s.ipc_mapped = p;
+    s.target = static_cast<uint8_t*>(p);
+    return CSG_OK;
+}
+
+int csg_set_gather_target(csg_context* ctx, uint8_t* rgba8_dev)
+{
+    if (!ctx) return fail(CSG_ERR_ARG, "null context");
+    for (Shard& s : ctx->shards) s.target = rgba8_dev ? rgba8_dev : ctx->d_fb;
+    return CSG_OK;
+}
+
+int csg_read_framebuffer(csg_context* ctx, uint8_t* rgba8_host)
+{
+    if (!ctx || !rgba8_host) return fail(CSG_ERR_ARG, "null argument");
+    int rc = sync_frame(ctx);
+    if (rc) return rc;
+    CU(cudaMemcpy(rgba8_host, ctx->d_fb, (size_t)ctx->width * ctx->height * 4, cudaMemcpyDeviceToHost));
+    return CSG_OK;
+}
+
+int csg_render(csg_context* ctx, const csg_camera* cam, const csg_light* light, uint8_t* rgba8_out)
+{
+    if (!ctx || !cam || !light || !rgba8_out) return fail(CSG_ERR_ARG, "null argument");
+    const bool dev = is_device_pointer(rgba8_out);
+    float ld[3];
+    csg_light_direction(light, ld);
+    // multi-shard contexts always gather into the root framebuffer first
+    const bool direct = dev && ctx->shards.size() == 1;
+    int rc = enqueue_frame(ctx, cam, ld, OUT_RGBA8, direct ? (void*)rgba8_out : nullptr);
+    if (rc) return rc;
+    Shard& root = ctx->shards[0];
+    const size_t bytes = (size_t)ctx->width * ctx->height * 4;
+    if (!direct) {
+        CU(cudaSetDevice(root.device));
+        CU(cudaMemcpyAsync(rgba8_out, root.target, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, root.stream));
+        CU(cudaStreamSynchronize(root.stream));
+    }
+    return sync_frame(ctx);
+}
+
+int csg_render_f32(csg_context* ctx, const csg_camera* cam, const csg_light* light, float* rgba_f32_out)
+{
+    if (!ctx || !cam || !light || !rgba_f32_out) return fail(CSG_ERR_ARG, "null argument");
+    if (ctx->shards.size() != 1) return fail(CSG_ERR_ARG, "csg_render_f32 needs a single-GPU context");
+    Shard& root = ctx->shards[0];
+    CU(cudaSetDevice(root.device));
+    const bool dev = is_device_pointer(rgba_f32_out);
+    const size_t bytes = (size_t)ctx->width * ctx->height * 16;
+    float ld[3];
+    csg_light_direction(light, ld);
+    if (!dev && !ctx->d_f32) CU(cudaMalloc(&ctx->d_f32, bytes));
+    int rc = enqueue_frame(ctx, cam, ld, OUT_F32, dev ? rgba_f32_out : ctx->d_f32);
+    if (rc) return rc;
+    if (!dev) {
+        CU(cudaMemcpyAsync(rgba_f32_out, ctx->d_f32, bytes, cudaMemcpyDeviceToHost, root.stream));
+        CU(cudaStreamSynchronize(root.stream));
+    }
+    return sync_frame(ctx);
+}
+
+int csg_render_aov(csg_context* ctx, const csg_camera* cam, uint8_t* hit, int32_t* prim_id, float* t)
+{
+    if (!ctx || !cam) return fail(CSG_ERR_ARG, "null argument");
+    if (ctx->shards.size() != 1) return fail(CSG_ERR_ARG, "csg_render_aov needs a single-GPU context");
+    Shard& root = ctx->shards[0];
+    CU(cudaSetDevice(root.device));
+    const size_t n = (size_t)ctx->width * ctx->height;
+    if (!ctx->d_aov_hit) {
+        CU(cudaMalloc(&ctx->d_aov_hit, n));
+        CU(cudaMalloc(&ctx->d_aov_prim, n * 4));
+        CU(cudaMalloc(&ctx->d_aov_t, n * 4));
+    }
+    int rc = enqueue_frame(ctx, cam, nullptr, OUT_AOV, nullptr);
+    if (rc) return rc;
+    rc = sync_frame(ctx);
+    if (rc) return rc;
+    if (hit) CU(cudaMemcpy(hit, ctx->d_aov_hit, n, cudaMemcpyDeviceToHost));
+    if (prim_id) CU(cudaMemcpy(prim_id, ctx->d_aov_prim, n * 4, cudaMemcpyDeviceToHost));
+    if (t) CU(cudaMemcpy(t, ctx->d_aov_t, n * 4, cudaMemcpyDeviceToHost));
+    return CSG_OK;
+}
+
+int csg_device_tan_half_fov(csg_context* ctx, float fov, float* out)
+{
+    if (!ctx || !out) return fail(CSG_ERR_ARG, "null argument");
+    Shard& root = ctx->shards[0];
+    CU(cudaSetDevice(root.device));
+    csg_tan_kernel<<<1, 1, 0, root.stream>>>(fov, root.d_tan);
+    CU(cudaMemcpyAsync(out, root.d_tan, sizeof(float), cudaMemcpyDeviceToHost, root.stream));
+    CU(cudaStreamSynchronize(root.stream));
+    ctx->launches++;
+    return CSG_OK;
+}
+
+const char* csg_context_info(csg_context* ctx) { return ctx ? ctx->info.c_str() : ""; }
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// Host-side scene model of libcsg_b200: parsed CSG tree + the flattened GPU layout.
+//
+// Replaces CSGTree / CSGNode / Primitive / BVHNode of the reference
+// (RayCasting/CSGTree/CSGTree.cuh, CSGTree.cu, BVH/BVHNode.cuh, Primitives/Primitives.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace csgb {
+
+enum NodeType : int { kUnion = 0, kDifference = 1, kIntersection = 2, kSphere = 3, kCylinder = 4, kCube = 5 };
+
+// Same 44-byte / 48-byte layouts as the reference's CSGNode / Primitive so csg_scene_dump can hand
+// them to a reference-side caller unchanged.
+struct RefNode {
+    int32_t type, prim, left, right, parent;
+    float bmin[3], bmax[3];
+};
+struct RefPrim {
+    int32_t id;
+    float x, y, z;
+    float r, g, b;
+    float p[5];  // p[0] radius|size, p[1] height, p[2..4] axis
+};
+static_assert(sizeof(RefNode) == 44 && sizeof(RefPrim) == 48, "reference layouts");
+
+// ---- flattened GPU tree -------------------------------------------------------------------
+// One 32-byte record per node, preorder (left child of operator n is n+1):
+//   word 7 (all kinds)   kind | leftIsLeaf<<3 | rightIsLeaf<<4 | idx<<8   idx = right child (operator) / primitive id (leaf)
+//   operator   w0..5 = culling box (min xyz, max xyz),  w6 = parent node (-1 at the root)
+//   sphere     w0..2 = centre, w3 = radius, w4..6 = centre again (the kernel turns w0..2 into origin-centre while staging)
+//   cube       w0..5 = lb, rt  (centre -/+ size/2, rounded like the reference rounds them)
+//   cylinder   w0..5 = the reference's own leaf box (centre -/+ max(h/2, r)), which gates the primitive (Q6)
+struct NodeRec {
+    float f[7];
+    uint32_t meta;
+};
+static_assert(sizeof(NodeRec) == 32, "record");
+constexpr uint32_t kMetaLeftLeaf = 1u << 3, kMetaRightLeaf = 1u << 4;
+
+// Per-primitive data kept in global memory (read on accepted hits / cylinder + cube tests / shading): 5 x float4.
+struct PrimRec {
+    float color[4];   // r g b, kind
+    float centre[4];  // x y z, p0 (radius | half size)
+    float base[4];    // cylinder: C = centre - (h/2)V, height
+    float axis[4];    // cylinder: V, radius
+    float haxis[4];   // cylinder: (h/2)V
+};
+static_assert(sizeof(PrimRec) == 80, "prim record");
+
+struct FlatTree {
+    std::vector<NodeRec> nodes;
+    std::vector<PrimRec> prims;
+    int depth = 0;        // operator levels on the longest path = stack slots the kernel needs
+    bool root_is_leaf = false;
+};
+
+struct Scene {
+    std::vector<RefNode> nodes;  // as parsed: the reference's tree, reference AABBs
+    std::vector<RefPrim> prims;
+    int optimize = 1;
+    int depth() const;
+};
+
+// CSGTree::Parse.  Returns "" on success, else the reference's error text.
+std::string parse_scene(const char* text, size_t len, Scene& out);
+std::string write_scene(const Scene& s);
+std::string generate_scene(int n_primitives, uint64_t seed);
+
+// Builds the GPU layout.  optimize >= 1 re-balances Union-only subtrees spatially.
+void flatten(const Scene& s, int optimize, FlatTree& out);
+
+}  // namespace csgb

@@ -1,0 +1,141 @@
+/* csg_b200 — C ABI of the B200-native CSG ray caster (libcsg_b200.so).
+ *
+ * Drop-in boundary for the per-pixel raycast + Phong path of
+ * Zumi002/CUDA-CSG-Tree-Raycasting.  The reference has no FFI; its seam is the C++ class
+ * `Raycaster` plus `CSGTree::Parse`.  Each entry point below names the
+ * reference interface it replaces (paths relative to CSGRayCasting/Graphics/).
+ *
+ * Conventions: plain C, opaque handles, int status codes (0 = CSG_OK), no exceptions and no
+ * exit() across the boundary (the reference's gpuErrchk exits the process,
+ * RayCasting/Kernels/RaycastingKernels.cuh:22-31).  A handle may be used by one thread at a
+ * time.  csg_last_error() is thread-local.  There is no CPU fallback: every render entry
+ * point fails with CSG_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Image convention (same as the reference): pixel index = y*width + x, row 0 is the BOTTOM
+ * scanline; RGBA8 byte = (int)(clamp(c,0,1)*255 + 0.5), alpha = 255 (Q12).
+ */
+#ifndef CSG_B200_H
+#define CSG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct csg_scene csg_scene;     /* host: parsed + flattened CSG tree */
+typedef struct csg_context csg_context; /* device(s): uploaded tree, framebuffers, streams */
+
+enum csg_status {
+    CSG_OK = 0,
+    CSG_ERR_PARSE = 1,     /* scene text rejected; csg_last_error() carries the reference's message */
+    CSG_ERR_IO = 2,        /* file could not be read */
+    CSG_ERR_CUDA = 3,      /* a CUDA call failed; message = cudaGetErrorString */
+    CSG_ERR_ARG = 4,       /* bad argument */
+    CSG_ERR_NO_DEVICE = 5, /* no usable CUDA device (there is no CPU fallback) */
+    CSG_ERR_LIMIT = 6      /* tree too deep / too large for the kernel's bounded stack */
+};
+
+/* Mirrors `Camera` (RenderManager/Camera/Camera.h:9-16): same field order, 60 bytes.
+ * forward/right/up are the cached basis Camera::updateVectors computes (Camera.cpp:4-27);
+ * fill them with csg_camera_set(), or copy them from an existing reference Camera. */
+typedef struct csg_camera {
+    float pos[3];
+    float pitch, yaw; /* rotX, rotY in radians */
+    float fov;        /* radians */
+    float forward[3], right[3], up[3];
+} csg_camera;
+
+/* Mirrors `DirectionalLight` (RenderManager/DirectionalLight.h:8-18). */
+typedef struct csg_light {
+    float polar, azimuth; /* radians */
+} csg_light;
+
+/* ---- scene: replaces CSGTree::Parse (RayCasting/CSGTree/CSGTree.cuh:53, CSGTree.cu:5-152) and
+ *      Application::LoadCSGTree (Application.cpp:59-83).  Grammar, keywords, argument counts,
+ *      rotation range checks and error texts are the reference's; truncated input (undefined
+ *      behaviour in the reference) is reported as CSG_ERR_PARSE. */
+int csg_load_scene(const char* path, csg_scene** out);
+int csg_parse_scene(const char* text, size_t len, csg_scene** out);
+void csg_free_scene(csg_scene* scene);
+/* n_nodes / n_prims as CSGTree::nodes.size() / primitives.size(); depth = operator levels on the longest path */
+int csg_scene_counts(const csg_scene* scene, int* n_nodes, int* n_prims, int* depth);
+/* Copies the tree in the reference's own layouts: n_nodes*44 bytes of CSGNode (CSGTree.cuh:15-34,
+ * with the reference's AABBs of BVHNode.cuh:17-77) and n_prims*48 bytes of Primitive (Primitives.h:29-41). */
+int csg_scene_dump(const csg_scene* scene, void* nodes44, void* prims48);
+/* Writes the scene back out in the text format. Returns bytes needed (excluding NUL). */
+size_t csg_scene_write(const csg_scene* scene, char* buf, size_t buflen);
+/* Synthetic balanced tree in the scene text format (BASELINE.json configs[4]).
+ * Returns bytes needed (excluding NUL); call with buf=NULL to size. */
+size_t csg_generate_scene(int n_primitives, uint64_t seed, char* buf, size_t buflen);
+
+/* ---- camera / light: replace Camera (Camera.h:18-52, Camera.cpp) and DirectionalLight */
+void csg_camera_default(csg_camera* cam);                                        /* Camera(): pos (0,0,5), fov 90*3.14159/180 */
+void csg_camera_set(csg_camera* cam, float x, float y, float z, float pitch, float yaw); /* setPosition + setRotation */
+void csg_camera_set_fov_degrees(csg_camera* cam, float degrees);                 /* setFOV */
+void csg_light_default(csg_light* light);                                        /* polar -60 deg, azimuth -45 deg */
+void csg_light_direction(const csg_light* light, float out3[3]);                 /* getLightDir */
+
+/* ---- upload: replaces Raycaster::ChangeSize(int w,int h,CSGTree) (RayCasting/Raycaster.cu:3-21).
+ * In-process form: the frame is sharded in 64x32-pixel tiles over devices 0..n_gpus-1, every shard
+ * writes its tiles straight into device 0's framebuffer over NVLink (peer stores). */
+int csg_upload(const csg_scene* scene, int width, int height, int n_gpus, csg_context** out);
+/* One-process-per-GPU form (torchrun): this process renders shard `shard_rank` of `shard_count` on
+ * CUDA device `device`.  The gather target is set with csg_set_gather_target(). */
+int csg_upload_shard(const csg_scene* scene, int width, int height, int device, int shard_rank,
+                     int shard_count, csg_context** out);
+void csg_free_context(csg_context* ctx); /* replaces Raycaster::CleanUp (Raycaster.cu:36-45) */
+
+/* Load-time tree optimisation.  0 = keep the parsed tree shape; 1 (default) =
+ * spatially re-balance maximal Union-only subtrees and tighten culling boxes.  Results are
+ * identical except on exact-tie pixels; must be called before csg_upload. */
+int csg_scene_set_optimize(csg_scene* scene, int level);
+
+/* ---- render: replaces Raycaster::Raycast(float4* devPBO, Camera, DirectionalLight) (Raycaster.cu:23-34).
+ * All three are synchronous (return when the output is complete), like the reference. */
+/* rgba8_out: width*height*4 bytes; host OR device pointer (detected with cudaPointerGetAttributes). */
+int csg_render(csg_context* ctx, const csg_camera* cam, const csg_light* light, uint8_t* rgba8_out);
+/* rgba_f32_out: width*height float4, linear colour exactly as the reference's LightningKernel writes its
+ * PBO (RaycastingKernels.cu:49-111); host or device pointer.  This is the literal PBO drop-in. */
+int csg_render_f32(csg_context* ctx, const csg_camera* cam, const csg_light* light, float* rgba_f32_out);
+/* Parity / debug outputs = RayHit.hit, RayHit.primitiveIdx (-1 on miss), RayHit.t (-1 on miss)
+ * (RayCasting/Utils/Ray.cuh:24-34).  Host pointers; any may be NULL. */
+int csg_render_aov(csg_context* ctx, const csg_camera* cam, uint8_t* hit, int32_t* prim_id, float* t);
+
+/* ---- asynchronous / device-resident form (benchmarks, interop viewers, multi-process gather) */
+/* Enqueues one frame on the context's stream(s); rgba8_dev NULL = the context's own framebuffer
+ * (or the gather target).  Returns without waiting. */
+int csg_render_enqueue(csg_context* ctx, const csg_camera* cam, const csg_light* light, uint8_t* rgba8_dev);
+int csg_sync(csg_context* ctx);
+/* CUDA-event time (ms) of the last completed csg_render_enqueue / csg_render* call: first kernel start to
+ * framebuffer complete on the root device. */
+int csg_last_frame_ms(csg_context* ctx, float* ms);
+/* Kernel launches issued by this context so far (bench.py's gpu_launches). */
+uint64_t csg_launch_count(const csg_context* ctx);
+/* Device pointer of the context's own RGBA8 framebuffer (valid until csg_free_context). */
+int csg_framebuffer(csg_context* ctx, uint8_t** rgba8_dev);
+/* Multi-process gather: 64-byte cudaIpcMemHandle_t of this context's framebuffer (root rank) ... */
+int csg_framebuffer_ipc_handle(csg_context* ctx, void* handle64);
+/* ... and on the other ranks: open the root's handle and make it the target of csg_render_enqueue(NULL). */
+int csg_set_gather_target_ipc(csg_context* ctx, const void* handle64);
+/* Same, for a pointer that is already addressable from this context's device. */
+int csg_set_gather_target(csg_context* ctx, uint8_t* rgba8_dev);
+
+/* Copies `bytes` from the framebuffer to a host buffer (synchronous). */
+int csg_read_framebuffer(csg_context* ctx, uint8_t* rgba8_host);
+
+/* tanf(fov/2) as the CUDA device evaluates it (RaycastingKernels.cu:15-16 runs tan() on the device); lets a host-side
+ * checker reproduce ray generation bit for bit. */
+int csg_device_tan_half_fov(csg_context* ctx, float fov, float* out);
+
+/* Description of the launch configuration chosen at upload, as JSON (threads, CTAs, smem, tree bytes...). */
+const char* csg_context_info(csg_context* ctx);
+
+const char* csg_last_error(void);
+const char* csg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
