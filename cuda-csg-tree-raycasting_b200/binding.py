@@ -25,7 +25,7 @@ EXPORTS = [
     "csg_light_direction", "csg_upload", "csg_upload_shard", "csg_free_context", "csg_scene_set_optimize",
     "csg_render", "csg_render_f32", "csg_render_aov", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
     "csg_launch_count", "csg_framebuffer", "csg_framebuffer_ipc_handle", "csg_set_gather_target_ipc",
-    "csg_set_gather_target", "csg_read_framebuffer", "csg_device_tan_half_fov", "csg_context_info",
+    "csg_set_gather_target", "csg_read_framebuffer", "csg_device_tan_half_fov", "csg_fp32_peak_tflops", "csg_context_info",
     "csg_last_error", "csg_version",
 ]
 
@@ -83,6 +83,7 @@ def _load():
         "csg_set_gather_target": (i, [vp, vp]),
         "csg_read_framebuffer": (i, [vp, vp]),
         "csg_device_tan_half_fov": (i, [vp, f, C.POINTER(f)]),
+        "csg_fp32_peak_tflops": (i, [i, C.POINTER(f)]),
         "csg_context_info": (C.c_char_p, [vp]),
         "csg_last_error": (C.c_char_p, []),
         "csg_version": (C.c_char_p, []),
@@ -112,6 +113,12 @@ def _ptr(a):
 
 def version():
     return lib.csg_version().decode()
+
+
+def fp32_peak_tflops(device=0):
+    out = C.c_float()
+    _check(lib.csg_fp32_peak_tflops(device, C.byref(out)))
+    return out.value
 
 
 class Camera:

@@ -315,6 +315,21 @@ __global__ void csg_stage_kernel(const uint4* __restrict__ src, uint4* __restric
     dst[2 * i + 1] = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), ub.z, ub.w);
 }
 
+// FP32 roofline probe: 8 independent FFMA chains per thread, nothing else.
+__global__ void __launch_bounds__(256) csg_ffma_probe_kernel(float* out, int iters, float a, float b)
+{
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+            x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 }  // namespace csgb
 
 // =========================================================================================== host side
@@ -951,6 +966,41 @@ int csg_device_tan_half_fov(csg_context* ctx, float fov, float* out)
     CU(cudaMemcpyAsync(out, root.d_tan, sizeof(float), cudaMemcpyDeviceToHost, root.stream));
     CU(cudaStreamSynchronize(root.stream));
     ctx->launches++;
+    return CSG_OK;
+}
+
+int csg_fp32_peak_tflops(int device, float* tflops)
+{
+    if (!tflops) return fail(CSG_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(CSG_ERR_NO_DEVICE, "no such CUDA device");
+    }
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    float* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 0.f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0));
+        csg_ffma_probe_kernel<<<blocks, threads>>>(d, iters, 1.0000001f, 1e-7f);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 64.0 * iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, (float)(flop / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
     return CSG_OK;
 }
 

@@ -129,6 +129,9 @@ int csg_read_framebuffer(csg_context* ctx, uint8_t* rgba8_host);
  * checker reproduce ray generation bit for bit. */
 int csg_device_tan_half_fov(csg_context* ctx, float fov, float* out);
 
+/* Measured FP32 roofline of `device`: an FFMA-only kernel (8 independent chains per thread), best of 4, in TFLOP/s. */
+int csg_fp32_peak_tflops(int device, float* tflops);
+
 /* Description of the launch configuration chosen at upload, as JSON (threads, CTAs, smem, tree bytes...). */
 const char* csg_context_info(csg_context* ctx);
 

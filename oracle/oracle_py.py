@@ -219,14 +219,14 @@ class RefCPU(_Ref):
 
     def __init__(self, path=None):
         super().__init__(path or os.path.join(HERE, "_ref", "libref_cpu.so"))
-        self.lib.refcpu_render.argtypes = [C.c_char_p, C.POINTER(RefView), C.c_int, C.c_int, C.c_int] + \
+        self.lib.refcpu_render.argtypes = [C.c_char_p, C.POINTER(RefView), C.c_int, C.c_int, C.c_int, C.c_int] + \
             [C.c_void_p] * 4 + [C.POINTER(C.c_double), C.c_char_p, C.c_int]
         self.lib.refcpu_max_threads.restype = C.c_int
 
     def max_threads(self):
         return self.lib.refcpu_max_threads()
 
-    def render(self, text, view, rows=None, nthreads=0, outputs=True):
+    def render(self, text, view, rows=None, nthreads=0, outputs=True, row_step=1):
         if isinstance(text, str):
             text = text.encode()
         w, h = view.width, view.height
@@ -235,7 +235,7 @@ class RefCPU(_Ref):
         sec = C.c_double()
         err = C.create_string_buffer(512)
         rv = view.ref()
-        rc = self.lib.refcpu_render(text, C.byref(rv), y0, y1, nthreads,
+        rc = self.lib.refcpu_render(text, C.byref(rv), y0, y1, row_step, nthreads,
                                     _p(fr.hit) if fr else None, _p(fr.prim) if fr else None,
                                     _p(fr.t) if fr else None, _p(fr.rgba) if fr else None,
                                     C.byref(sec), err, 512)

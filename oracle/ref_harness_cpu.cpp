@@ -106,10 +106,10 @@ void refcpu_light_dir(const ref_view* v, float* out3)
 
 int refcpu_max_threads(void) { return omp_get_max_threads(); }
 
-// Renders rows [y0,y1) of the frame (row 0 = bottom scanline, as the reference).
+// Renders rows y0, y0+row_step, ... < y1 of the frame (row 0 = bottom scanline, as the reference).
 // Output arrays are full-frame (w*h), only the rendered rows are written; any may be NULL.
 // rgba = 4 floats per pixel exactly as LightningKernel writes them.
-int refcpu_render(const char* text, const ref_view* v, int y0, int y1, int nthreads,
+int refcpu_render(const char* text, const ref_view* v, int y0, int y1, int row_step, int nthreads,
                   uint8_t* hit, int32_t* prim, float* t, float* rgba,
                   double* seconds, char* err, int errlen)
 {
@@ -130,10 +130,13 @@ int refcpu_render(const char* text, const ref_view* v, int y0, int y1, int nthre
     if (y0 < 0) y0 = 0;
     if (y1 > h) y1 = h;
     if (nthreads <= 0) nthreads = omp_get_max_threads();
+    if (row_step < 1) row_step = 1;
+    const int nrows = (y1 - y0 + row_step - 1) / row_step;
 
     auto t0 = std::chrono::steady_clock::now();
 #pragma omp parallel for schedule(dynamic, 8) num_threads(nthreads)
-    for (int y = y0; y < y1; ++y) {
+    for (int yi = 0; yi < nrows; ++yi) {
+        const int y = y0 + yi * row_step;
         blockDim = dim3(1, 1, 1);
         blockIdx = uint3{0, 0, 0};
         for (int x = 0; x < w; ++x) {

@@ -1,0 +1,202 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle, the golden fixtures of the reference CUDA kernel and,
+where oracle/_ref/libref_gpu.so travelled to the box, the reference CUDA kernel itself.
+
+Bars (BASELINE.json north_star): hit mask + primitive id equal on >= 99.99 % of pixels, t within 1e-4 relative,
+RGBA8 within 1 LSB.  In practice the kernel is bit-identical; the tests assert the contract, and report exactness."""
+import numpy as np
+import pytest
+
+import scenes
+from oracle_py import View, oblique_view, orbit_view
+
+pytestmark = pytest.mark.gpu
+
+W, H = 256, 144
+
+
+def cam_of(csg, v):
+    return csg.Camera(pos=v.pos, pitch=v.pitch, yaw=v.yaw, fov=v.fov)
+
+
+def light_of(csg, v):
+    return csg.Light() if v.polar > 1e9 else csg.Light(v.polar, v.azimuth)
+
+
+def views(scene_id, w=W, h=H):
+    if "Cheese" in scene_id:
+        return [View(w, h), oblique_view(w, h), View(w, h, pos=(0.5, 1.0, -19.0), pitch=0.3, yaw=2.0)]  # last: camera inside the solid
+    return [View(w, h), orbit_view(w, h, 5), orbit_view(w, h, 41, pitch_deg=30.0, radius=4.0),
+            View(w, h, pos=(0.2, 0.1, 0.3), pitch=0.4, yaw=1.0),          # camera inside / very near the solids
+            View(w, h, pos=(0, 0, 6), fov=30 * 3.14159 / 180, polar=0.7, azimuth=2.0)]
+
+
+def check(csg, a_hit, a_prim, a_t, a_rgba8, b, what, exact=False):
+    n = a_hit.size
+    bad = (a_hit != b.hit) | ((a_hit == 1) & (a_prim != b.prim))
+    assert bad.sum() <= (0 if exact else max(1, int(1e-4 * n))), f"{what}: {bad.sum()} of {n} pixels differ in hit/id"
+    ok = (a_hit == 1) & ~bad
+    rel = np.abs(a_t[ok] - b.t[ok]) / np.maximum(np.abs(b.t[ok]), 1e-30)
+    assert rel.size == 0 or rel.max() <= (0 if exact else 1e-4), f"{what}: t rel err {rel.max()}"
+    d = np.abs(a_rgba8.reshape(-1, 4).astype(int) - b.rgba8().reshape(-1, 4).astype(int)).max(axis=1)
+    assert (d[~bad] <= 1).all(), f"{what}: RGBA8 differs by {d[~bad].max()} LSB"
+
+
+@pytest.mark.parametrize("optimize", [0, 1])
+@pytest.mark.parametrize("scene_id", scenes.all_scene_ids())
+def test_cuda_matches_oracle(scene_id, optimize, csg, oracle):
+    txt = scenes.text_of(scene_id)
+    sc = csg.Scene.parse(txt, optimize=optimize)
+    ctx = sc.upload(W, H)
+    for v in views(scene_id):
+        cam, light = cam_of(csg, v), light_of(csg, v)
+        hit, prim, t = ctx.render_aov(cam)
+        rgba8 = ctx.render(cam, light)
+        f32 = ctx.render_f32(cam, light).reshape(-1)
+        ref = oracle.render(txt, v, tan_half_fov=ctx.device_tan_half_fov(cam.c.fov))
+        check(csg, hit, prim, t, rgba8, ref, f"{scene_id} opt={optimize}")
+        q = (np.clip(f32, 0, 1) * np.float32(255) + np.float32(0.5)).astype(np.uint8)
+        assert np.abs(q.astype(int) - rgba8.reshape(-1).astype(int)).max() <= 1   # f32 and RGBA8 outputs agree
+    ctx.close()
+
+
+def test_cuda_matches_reference_cuda_golden(csg, golden):
+    """Committed outputs of the reference's own CUDA kernels (tests/golden/make_golden.py)."""
+    keys = sorted({k.rsplit("/", 1)[0] for k in golden.files})
+    names = set(scenes.corpus_names())
+    done = 0
+    for key in keys:
+        name = key.split("/")[0]
+        if name not in names:
+            continue
+        p = golden[key + "/view"]
+        v = View(int(p[0]), int(p[1]), pos=p[2:5], pitch=p[5], yaw=p[6], fov=p[7], polar=p[8], azimuth=p[9])
+        sc = csg.Scene.parse(scenes.text_of("corpus:" + name))
+        ctx = sc.upload(v.width, v.height)
+        cam, light = cam_of(csg, v), light_of(csg, v)
+        hit, prim, t = ctx.render_aov(cam)
+        rgba8 = ctx.render(cam, light).reshape(-1)
+        n = hit.size
+
+        class G:
+            pass
+        g = G()
+        g.hit = np.unpackbits(golden[key + "/hit"])[:n]
+        g.prim = golden[key + "/prim"].astype(np.int32)
+        g.t = golden[key + "/t"]
+        g.rgba8 = lambda k=key: golden[k + "/rgba8"]
+        check(csg, hit, prim, t, rgba8, g, key)
+        ctx.close()
+        done += 1
+    if not done:
+        pytest.skip("scene corpus not staged")
+
+
+@pytest.mark.parametrize("name,view,optimize", [
+    ("testWikipedia", View(1920, 1080), 1),
+    ("testSphereCutByCubesAndCylinder", orbit_view(3840, 2160, 9), 1),
+    ("testCheese256", View(3840, 2160), 1),
+    ("testCheese512", View(3840, 2160), 1),
+    ("testCheese512", View(3840, 2160), 0),
+    ("testCheese512", oblique_view(3840, 2160), 1),
+])
+def test_full_size_against_reference_cuda_kernel(name, view, optimize, csg, ref_gpu):
+    """BASELINE.json configs at their full sizes against the reference's own kernels run live on this GPU."""
+    if name not in scenes.corpus_names():
+        pytest.skip("scene corpus not staged")
+    txt = scenes.text_of("corpus:" + name)
+    ref = ref_gpu.render(txt, view)
+    sc = csg.Scene.parse(txt, optimize=optimize)
+    ctx = sc.upload(view.width, view.height)
+    cam, light = cam_of(csg, view), light_of(csg, view)
+    hit, prim, t = ctx.render_aov(cam)
+    rgba8 = ctx.render(cam, light)
+    check(csg, hit, prim, t, rgba8, ref, f"{name} {view.width}x{view.height}")
+    ctx.close()
+
+
+def test_synthetic_4096_against_reference_cuda_kernel(csg, ref_gpu):
+    """BASELINE.json configs[4] scene (balanced tree, 4096 primitives, all operator and primitive kinds)."""
+    txt = csg.Scene.generate_text(4096, seed=1234)
+    v = View(1920, 1080)
+    ref = ref_gpu.render(txt, v)
+    for optimize in (0, 1):
+        sc = csg.Scene.parse(txt, optimize=optimize)
+        ctx = sc.upload(v.width, v.height)
+        cam, light = cam_of(csg, v), light_of(csg, v)
+        hit, prim, t = ctx.render_aov(cam)
+        rgba8 = ctx.render(cam, light)
+        check(csg, hit, prim, t, rgba8, ref, f"synthetic4096 opt={optimize}")
+        ctx.close()
+
+
+def test_size_independent_properties(csg):
+    """At BASELINE's full size: determinism, optimisation-invariance, host/device output paths agree, miss colour."""
+    if "testCheese512" not in scenes.corpus_names():
+        pytest.skip("scene corpus not staged")
+    import torch
+    txt = scenes.text_of("corpus:testCheese512")
+    cam, light = csg.Camera(), csg.Light()
+    frames = []
+    for optimize in (0, 1):
+        sc = csg.Scene.parse(txt, optimize=optimize)
+        ctx = sc.upload(3840, 2160)
+        a = ctx.render(cam, light).copy()
+        b = ctx.render(cam, light).copy()
+        assert np.array_equal(a, b)                        # deterministic despite dynamic tile scheduling
+        dev = torch.empty(3840 * 2160 * 4, dtype=torch.uint8, device="cuda")
+        ctx.render(cam, light, dev.data_ptr())             # device-pointer output path
+        assert np.array_equal(dev.cpu().numpy().reshape(a.shape), a)
+        ctx.enqueue(cam, light)
+        assert np.array_equal(ctx.read_framebuffer(), a)   # async path
+        assert ctx.last_frame_ms() > 0
+        frames.append(a)
+        ctx.close()
+    assert np.array_equal(frames[0], frames[1])            # tree re-balancing does not change a single byte
+    img = frames[0].reshape(2160, 3840, 4)
+    assert (img[..., 3] == 255).all()
+    assert tuple(img[0, 0]) == (20, 20, 28, 255)           # miss colour (0.08,0.08,0.11,1) quantised per Q12
+
+
+def test_odd_sizes_and_partial_tiles(csg, oracle):
+    txt = scenes.INLINE["nested"]
+    for (w, h) in [(2, 2), (7, 5), (65, 33), (130, 70), (257, 129)]:
+        v = orbit_view(w, h, 3, radius=4.0)
+        sc = csg.Scene.parse(txt)
+        ctx = sc.upload(w, h)
+        cam, light = cam_of(csg, v), light_of(csg, v)
+        hit, prim, t = ctx.render_aov(cam)
+        rgba8 = ctx.render(cam, light)
+        ref = oracle.render(txt, v, tan_half_fov=ctx.device_tan_half_fov(cam.c.fov))
+        check(csg, hit, prim, t, rgba8, ref, f"{w}x{h}")
+        ctx.close()
+
+
+def test_multi_gpu_in_process_equals_single_gpu(csg):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    if "testCheese512" not in scenes.corpus_names():
+        pytest.skip("scene corpus not staged")
+    txt = scenes.text_of("corpus:testCheese512")
+    cam, light = csg.Camera(), csg.Light()
+    sc = csg.Scene.parse(txt)
+    one = sc.upload(1920, 1080, 1)
+    a = one.render(cam, light).copy()
+    one.close()
+    n = min(torch.cuda.device_count(), 8)
+    for k in sorted({2, n}):
+        many = sc.upload(1920, 1080, k)
+        b = many.render(cam, light).copy()
+        assert np.array_equal(a, b), f"{k}-GPU frame differs from the 1-GPU frame"
+        many.close()
+
+
+def test_deep_tree_limit_is_an_error_not_a_crash(csg):
+    depth = 400
+    txt = "Union\n" * depth + "Sphere 0 0 0 FF0000 1\n" + "".join(f"Sphere {i * 0.01} 0 0 00FF00 1\n" for i in range(depth))
+    sc = csg.Scene.parse(txt, optimize=0)
+    with pytest.raises(csg.CsgError) as e:
+        sc.upload(64, 36)
+    assert e.value.code == csg.CSG_ERR_LIMIT
+    ok = csg.Scene.parse(txt, optimize=1).upload(64, 36)   # re-balancing brings the union chain back to log depth
+    ok.close()

@@ -1,0 +1,195 @@
+"""Host-side logic of libcsg_b200 (no GPU needed): C-ABI exports, parser parity with the oracle, error behaviour,
+camera/light math, writer/generator, multi-rank tile sharding logic (gloo, world_size 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import scenes
+from oracle_py import View, ParseError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(csg):
+    header = open(os.path.join(ROOT, "include", "csg_b200.h")).read()
+    declared = set(re.findall(r"\b(csg_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = C.CDLL(csg.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/csg_b200.h but not exported"
+    assert declared == set(csg.EXPORTS)
+
+
+def test_library_does_not_link_the_oracle(csg):
+    out = subprocess.run(["ldd", csg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "ref_cpu" not in out and "ref_gpu" not in out
+    syms = subprocess.run(["nm", "-D", "--defined-only", csg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "orc_" not in syms and "refcpu_" not in syms
+
+
+@pytest.mark.parametrize("scene_id", scenes.all_scene_ids())
+def test_parser_matches_oracle(scene_id, csg, oracle):
+    """csg_parse_scene == CSGTree::Parse: reference-layout node and primitive arrays byte-identical to the oracle's
+    (which tests/test_oracle_vs_reference.py pins to the reference parser itself)."""
+    txt = scenes.text_of(scene_id)
+    s = csg.Scene.parse(txt)
+    n1, p1 = s.dump()
+    sc = oracle.parse(txt)
+    n2, p2 = oracle.tree_arrays(sc)
+    oracle.free(sc)
+    assert np.array_equal(n1, n2)
+    types = n1.view(np.int32)[:, 0]
+    prim = n1.view(np.int32)[:, 1]
+    for t, pi in zip(types, prim):
+        if pi >= 0:
+            nb = 48 if t == 4 else 32
+            assert np.array_equal(p1[pi, :nb], p2[pi, :nb])
+    nn, npr, depth = s.counts()
+    assert nn == 2 * npr - 1 and depth >= (0 if npr == 1 else 1)
+
+
+BAD_INPUTS = [
+    ("", "Cannot parse - number of primitives do not match number of nodes"),
+    ("Union Sphere 0 0 0 FF00FF 1", "Cannot parse - number of primitives do not match number of nodes"),
+    ("Sphere 0 0 0 FF00FF 1 Sphere 0 0 0 FF00FF 1", "Cannot parse"),
+    ("Blob 0 0 0", "Cannot parse - Unrecognized keyword: Blob"),
+    ("Sphere 0 0 0 FF00F 1", "Cannot parse color FF00F"),
+    ("Sphere x 0 0 FF00FF 1", "stof"),
+    ("Sphere 0 0 0 GG00FF 1", "stoi"),
+    ("Cylinder 0 0 0 FF00FF 1 2 361 0 0", "Invalid roation rotX should be in range [0, 360] deg"),
+    ("Cylinder 0 0 0 FF00FF 1 2 0 -1 0", "Invalid roation rotY should be in range [0, 360] deg"),
+    ("Cylinder 0 0 0 FF00FF 1 2 0 0 400", "Invalid roation rotZ should be in range [0, 360] deg"),
+    ("Cylinder 0 0 0 FF00FF 1 2 0 0 q", "stod"),
+    ("Union Sphere 0 0 0 FF00FF", "Cannot parse - unexpected end of input"),  # reference: out-of-range read (UB)
+]
+
+
+@pytest.mark.parametrize("text,message", BAD_INPUTS)
+def test_parse_errors(text, message, csg, oracle):
+    with pytest.raises(csg.CsgError) as e:
+        csg.Scene.parse(text)
+    assert e.value.code == csg.CSG_ERR_PARSE and e.value.message == message
+    with pytest.raises(ParseError) as e2:
+        oracle.parse(text)
+    assert str(e2.value) == message
+
+
+def test_load_scene_io_error(csg):
+    with pytest.raises(csg.CsgError) as e:
+        csg.Scene.load("/nonexistent/scene.txt")
+    assert e.value.code == csg.CSG_ERR_IO
+
+
+def test_camera_and_light_match_oracle(csg, oracle):
+    rng = np.random.default_rng(11)
+    for i in range(500):
+        v = View(64, 36, pos=rng.uniform(-10, 10, 3), pitch=rng.uniform(-2, 2), yaw=rng.uniform(-7, 7),
+                 fov=rng.uniform(0.2, 2.5) if i % 2 else -1, polar=rng.uniform(-3, 3), azimuth=rng.uniform(-3, 3))
+        cam = csg.Camera(pos=v.pos, pitch=v.pitch, yaw=v.yaw, fov=v.fov)
+        assert np.array_equal(cam.as_array().view(np.uint32), oracle.camera(v).as_array().view(np.uint32))
+        li = csg.Light(v.polar, v.azimuth)
+        assert np.array_equal(li.direction().view(np.uint32), np.array(oracle.light_dir(v), np.float32).view(np.uint32))
+    d = View(8, 8)
+    assert np.array_equal(csg.Camera().as_array().view(np.uint32), oracle.camera(d).as_array().view(np.uint32))
+    assert np.array_equal(csg.Light().direction().view(np.uint32), np.array(oracle.light_dir(d), np.float32).view(np.uint32))
+
+
+def test_generator_and_writer_roundtrip(csg):
+    txt = csg.Scene.generate_text(4096, seed=1234)
+    s = csg.Scene.parse(txt)
+    nn, npr, depth = s.counts()
+    assert (nn, npr, depth) == (8191, 4096, 12)
+    assert csg.Scene.generate_text(4096, seed=1234) == txt          # deterministic
+    assert csg.Scene.generate_text(4096, seed=1235) != txt
+    small = csg.Scene.parse(csg.Scene.generate_text(37, seed=5))
+    out = small.write()
+    again = csg.Scene.parse(out)
+    n1, p1 = small.dump()
+    n2, p2 = again.dump()
+    assert np.array_equal(n1.view(np.int32)[:, :5], n2.view(np.int32)[:, :5])   # same tree shape
+    a = p1.view(np.float32).reshape(len(p1), 12)
+    b = p2.view(np.float32).reshape(len(p2), 12)
+    types = {pi: t for t, pi in zip(n1.view(np.int32)[:, 0], n1.view(np.int32)[:, 1]) if pi >= 0}
+    for i in range(len(a)):
+        assert np.allclose(a[i, 1:4], b[i, 1:4], rtol=0, atol=0)   # positions exact (%.9g)
+        assert a[i, 7] == b[i, 7]
+        if types[i] == 4:
+            assert np.allclose(a[i, 9:12], b[i, 9:12], atol=2e-6)    # axis re-derived from Euler angles
+
+
+def test_no_gpu_means_error_not_fallback(csg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    s = csg.Scene.parse(scenes.INLINE["nested"])
+    with pytest.raises(csg.CsgError) as e:
+        s.upload(64, 36)
+    assert e.value.code == csg.CSG_ERR_NO_DEVICE
+
+
+def test_tile_sharding_covers_frame_once():
+    """The kernel renders macro tile m on shard m % S; local ticket i maps to macro (i>>6)*S + rank.  Check the host-side
+    arithmetic the launcher uses (number of local warp tiles per shard) covers every macro tile exactly once."""
+    for (w, h) in [(3840, 2160), (1920, 1080), (7680, 4320), (100, 50), (64, 32), (65, 33)]:
+        mx, my = (w + 63) // 64, (h + 31) // 32
+        total = mx * my
+        for S in (1, 2, 3, 4, 8):
+            seen = np.zeros(total, int)
+            for r in range(S):
+                mine = (total - r + S - 1) // S
+                for j in range(mine):
+                    seen[j * S + r] += 1
+            assert (seen == 1).all()
+
+
+GLOO_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
+from oracle_py import Oracle, View
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# Host-side model of the multi-rank frame: each rank renders only the 64x32 macro tiles it owns (with the oracle
+# standing in for the kernel), "stores" them into rank 0's framebuffer (gloo gather), and the result must equal
+# the single-rank frame bit for bit.
+W, H = 200, 100
+txt = "Difference\n Cube 0 0 0 FF0000 2\n Union\n  Sphere 1 1 1 00FF00 0.8\n  Cylinder 0 0 0 0000FF 0.5 3 0 0 0\n"
+orc = Oracle()
+full = orc.render(txt, View(W, H, pos=(1.5, 1.0, 4.0), pitch=-0.2, yaw=0.3))
+rgba = full.rgba8().reshape(H, W, 4)
+mx, my = (W + 63) // 64, (H + 31) // 32
+mine = np.zeros((H, W, 4), np.uint8)
+mask = np.zeros((H, W), np.uint8)
+for m in range(rank, mx * my, world):
+    x0, y0 = (m % mx) * 64, (m // mx) * 32
+    mine[y0:y0 + 32, x0:x0 + 64] = rgba[y0:y0 + 32, x0:x0 + 64]
+    mask[y0:y0 + 32, x0:x0 + 64] += 1
+parts = [torch.zeros(H, W, 4, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
+masks = [torch.zeros(H, W, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
+dist.gather(torch.from_numpy(mine), parts, dst=0)
+dist.gather(torch.from_numpy(mask), masks, dst=0)
+if rank == 0:
+    cover = sum(m.numpy().astype(int) for m in masks)
+    assert (cover == 1).all(), "tiles must partition the frame"
+    fb = sum(p.numpy().astype(int) for p in parts).astype(np.uint8)
+    assert np.array_equal(fb, rgba)
+    print("GLOO_OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    """world_size-2 CPU run of the N>1 host logic (gloo backend)."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(script), ROOT],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GLOO_OK" in r.stdout
