@@ -96,10 +96,18 @@ __device__ __forceinline__ uint32_t to_u8(float c)
 
 // CSGRayCast (RaycastingKernels.cu:459-512) re-expressed as an explicit-frame evaluation; equivalence with the
 // reference's GoTo/Compute/SaveLft action machine is argued in DESIGN.md §"State machine".
-//   frame (one per operator on the current path, in shared memory): word0 = saved tmin (F_SAVE_LFT) or saved hit t,
-//   word1 = saved hit meta | return state.
-__device__ __forceinline__ Hit traverse(const uint4* __restrict__ nodes, const float4* __restrict__ prims,
-                                        const uint32_t* __restrict__ table, uint2* __restrict__ stack,
+//
+// One 16-byte frame per operator on the current path, in shared memory ([level][thread]):
+//   x = saved tmin (F_FIRST_*) or saved hit t (F_LOAD_*),  y = saved hit meta | return state,
+//   z = F_FIRST_*: lower bound of the pending sibling's hits (prune test),  w = byte offset of the operator's record.
+//
+// Two additions over the reference's traversal order, both result-preserving (DESIGN.md §"Culling contract"):
+//   * a Union evaluates the child whose box the ray enters first; Difference/Intersection keep left-first;
+//   * when the first child returns a hit at t and the pending sibling's box starts beyond t, the sibling cannot change
+//     the outcome (Union: every cell with a farther Enter or a Miss on the other side returns this hit; Difference: same
+//     for the right operand) and is skipped.
+__device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, const float4* __restrict__ prims,
+                                        const uint32_t* __restrict__ table, uint4* __restrict__ stack,
                                         const int stack_stride, const Ray& r, const bool root_is_leaf)
 {
     enum { ST_ENTER = 0, ST_LOOPL = 1, ST_LOOPR = 2, ST_COMPUTE = 3, ST_RETURN = 4, ST_DONE = 5 };
@@ -107,43 +115,55 @@ __device__ __forceinline__ Hit traverse(const uint4* __restrict__ nodes, const f
     float tmin = 0.0f;                        // :466
     if (root_is_leaf) {                        // GoTo's leaf branch on the virtual root: no box test (:582-594, Q7)
         bool go;
-        eval_child(nodes, prims, 0, r, tmin, false, L, go);
+        float tn;
+        eval_child(tree, prims, 0u, r, tmin, false, L, go, tn);
         return L;
     }
-    int n = 0, sp = 0, st = ST_ENTER;
+    uint32_t n = 0u;                           // byte offset of the current operator's record
+    uint4* sp = stack;                         // next free frame
+    int st = ST_ENTER;
     while (st != ST_DONE) {
         if (st <= ST_LOOPR) {
-            const uint4 nb = nodes[2 * n + 1];
-            const uint32_t meta = nb.w;
+            const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
             const uint32_t op = meta & 7u;
-            const int cl = n + 1, cr = (int)(meta >> 8);
+            const uint32_t cl = n + 32u, cr = (meta >> 8) << 5;
             bool goL = false, goR = false;
-            if (st != ST_LOOPR) eval_child(nodes, prims, cl, r, tmin, st == ST_ENTER, L, goL);
+            float tnL = -INFINITY, tnR = -INFINITY;
+            if (st != ST_LOOPR) eval_child(tree, prims, cl, r, tmin, st == ST_ENTER, L, goL, tnL);
             if (st == ST_ENTER && op != 0u && !goL && is_miss(L)) {
                 // left operand of a Difference/Intersection already missed: the node's result is Miss whatever the right
                 // operand does (all M* cells of both tables, :670-677) — skip the right subtree (Q8)
-                R = L = make_miss();
+                R = L;
                 st = ST_RETURN;
             } else {
-                if (st != ST_LOOPL) eval_child(nodes, prims, cr, r, tmin, st == ST_ENTER, R, goR);
+                if (st != ST_LOOPL) eval_child(tree, prims, cr, r, tmin, st == ST_ENTER, R, goR, tnR);
                 if (st != ST_ENTER) {
                     st = ST_COMPUTE;
-                } else if (!goL && !goR) {
-                    st = ST_COMPUTE;                                                   // :578
-                } else if (!goL) {                                                     // :556-561
-                    stack[sp * stack_stride] = make_uint2(__float_as_uint(L.t), L.m | F_LOAD_LFT);
-                    ++sp; n = cr;
-                } else if (!goR) {                                                     // :562-567
-                    stack[sp * stack_stride] = make_uint2(__float_as_uint(R.t), R.m | F_LOAD_RGH);
-                    ++sp; n = cl;
-                } else {                                                               // :568-574
-                    stack[sp * stack_stride] = make_uint2(__float_as_uint(tmin), F_SAVE_LFT);
-                    ++sp; n = cl;
+                } else {
+                    // sibling pruning against a leaf hit that is already known
+                    if (op != 2u) {
+                        if (goR && !goL && !is_miss(L) && tnR > L.t) { goR = false; R = make_miss(); }
+                        if (op == 0u && goL && !goR && !is_miss(R) && tnL > R.t) { goL = false; L = make_miss(); }
+                    }
+                    if (!goL && !goR) {
+                        st = ST_COMPUTE;                                                   // :578
+                    } else if (!goL) {                                                     // :556-561
+                        *sp = make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n);
+                        sp += stack_stride; n = cr;
+                    } else if (!goR) {                                                     // :562-567
+                        *sp = make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n);
+                        sp += stack_stride; n = cl;
+                    } else {                                                               // :568-574
+                        const bool right_first = (op == 0u) && (tnR < tnL);
+                        const float bound = (op == 2u) ? -INFINITY : (right_first ? tnL : tnR);
+                        *sp = make_uint4(__float_as_uint(tmin), right_first ? F_FIRST_RGH : F_FIRST_LFT, __float_as_uint(bound), n);
+                        sp += stack_stride; n = right_first ? cr : cl;
+                    }
                 }
             }
         }
         if (st == ST_COMPUTE) {                                                        // Compute :597-661
-            const uint32_t meta = nodes[2 * n + 1].w;
+            const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
             const uint32_t op = meta & 7u;
             const uint32_t e = table[op * 9u + (L.m & H_CLS) * 3u + (R.m & H_CLS)];
             const uint32_t o = (L.t < R.t) ? (e & 7u) : (L.t > R.t) ? ((e >> 3) & 7u) : ((e >> 6) & 7u);
@@ -154,33 +174,38 @@ __device__ __forceinline__ Hit traverse(const uint4* __restrict__ nodes, const f
             } else if (o == O_LOOPL) {                                                 // :640-646
                 tmin = L.t;
                 if (meta & kMetaLeftLeaf) st = ST_LOOPL;
-                else { stack[sp * stack_stride] = make_uint2(__float_as_uint(R.t), R.m | F_LOAD_RGH); ++sp; n = n + 1; st = ST_ENTER; }
+                else { *sp = make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n); sp += stack_stride; n = n + 32u; st = ST_ENTER; }
             } else if (o == O_LOOPR) {                                                 // :647-653
                 tmin = R.t;
                 if (meta & kMetaRightLeaf) st = ST_LOOPR;
-                else { stack[sp * stack_stride] = make_uint2(__float_as_uint(L.t), L.m | F_LOAD_LFT); ++sp; n = (int)(meta >> 8); st = ST_ENTER; }
+                else { *sp = make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n); sp += stack_stride; n = (meta >> 8) << 5; st = ST_ENTER; }
             } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
         }
-        if (st == ST_RETURN) {                  // action = actionStack.pop(); node = GetParent() (:624-625 etc.)
-            if (sp == 0) { st = ST_DONE; }
+        if (st == ST_RETURN) {                  // action = actionStack.pop(); node = GetParent() (:624-625 etc.); L == R == result
+            if (sp == stack) { st = ST_DONE; }
             else {
-                --sp;
-                const uint2 f = stack[sp * stack_stride];
-                n = (int)nodes[2 * n + 1].z;    // parent
+                sp -= stack_stride;
+                const uint4 f = *sp;
+                n = f.w;
                 const uint32_t ret = f.y & F_RET_MASK;
-                if (ret == F_SAVE_LFT) {        // SaveLft :476-481: restore tmin, keep the left result, go right
+                if (ret == F_LOAD_LFT) {        // :611-614
+                    L.t = __uint_as_float(f.x); L.m = f.y & H_META_MASK; st = ST_COMPUTE;
+                } else if (ret == F_LOAD_RGH) { // :615-618
+                    R.t = __uint_as_float(f.x); R.m = f.y & H_META_MASK; st = ST_COMPUTE;
+                } else {                        // SaveLft :476-481: restore tmin, keep the first result, evaluate the sibling
                     tmin = __uint_as_float(f.x);
-                    const uint32_t pm = nodes[2 * n + 1].w;
-                    if ((pm & 7u) != 0u && is_miss(L)) {
-                        R = L = make_miss();    // same short-circuit as above; stay in ST_RETURN
+                    const uint32_t pm = *reinterpret_cast<const uint32_t*>(tree + n + 28);
+                    const bool miss = is_miss(L);
+                    if (miss ? ((pm & 7u) != 0u) : (__uint_as_float(f.z) > L.t)) {
+                        // Difference/Intersection whose left operand missed -> Miss; or the sibling lies beyond this hit -> this hit.
+                        // Either way the node's result is what L == R already hold; stay in ST_RETURN.
+                    } else if (ret == F_FIRST_LFT) {
+                        *sp = make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n);
+                        sp += stack_stride; n = (pm >> 8) << 5; st = ST_ENTER;
                     } else {
-                        stack[sp * stack_stride] = make_uint2(__float_as_uint(L.t), L.m | F_LOAD_LFT);
-                        ++sp; n = (int)(pm >> 8); st = ST_ENTER;
+                        *sp = make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n);
+                        sp += stack_stride; n = n + 32u; st = ST_ENTER;
                     }
-                } else if (ret == F_LOAD_LFT) { // :611-614
-                    R = L; L.t = __uint_as_float(f.x); L.m = f.y & H_META_MASK; st = ST_COMPUTE;
-                } else {                        // F_LOAD_RGH :615-618
-                    L = R; R.t = __uint_as_float(f.x); R.m = f.y & H_META_MASK; st = ST_COMPUTE;
                 }
             }
         }
@@ -194,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 2) csg_frame_kernel(const __grid_con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* s_nodes = reinterpret_cast<uint4*>(smem_raw);
     const int n_staged = TREE_SMEM ? p.n_nodes : 0;
-    uint2* s_stack = reinterpret_cast<uint2*>(s_nodes + 2 * n_staged);
+    uint4* s_stack = s_nodes + 2 * n_staged;
     uint32_t* s_table = reinterpret_cast<uint32_t*>(s_stack + (size_t)p.stack_levels * kThreads);
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -219,8 +244,8 @@ __global__ void __launch_bounds__(kThreads, 2) csg_frame_kernel(const __grid_con
         }
     }
     __syncthreads();
-    const uint4* nodes = TREE_SMEM ? s_nodes : p.nodes;   // !TREE_SMEM: p.nodes was staged by csg_stage_kernel
-    uint2* my_stack = s_stack + tid;
+    const unsigned char* tree = reinterpret_cast<const unsigned char*>(TREE_SMEM ? s_nodes : p.nodes);   // !TREE_SMEM: staged by csg_stage_kernel
+    uint4* my_stack = s_stack + tid;
 
     // per-frame constants of ray generation, RaycastKernel :11-16
     const float wf = (float)p.width, hf = (float)p.height;
@@ -262,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 2) csg_frame_kernel(const __grid_con
             }
             r.dx = cx; r.dy = cy; r.dz = cz;
             r.ix = __frcp_rn(cx); r.iy = __frcp_rn(cy); r.iz = __frcp_rn(cz);
-            res = traverse(nodes, p.prims, s_table, my_stack, kThreads, r, p.root_is_leaf != 0);
+            res = traverse(tree, p.prims, s_table, my_stack, kThreads, r, p.root_is_leaf != 0);
         }
 
         const size_t pix = (size_t)y * p.width + x;   // :33
@@ -550,13 +575,13 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
 
     auto cleanup_fail = [&](int code) { csg_free_context(c); return code; };
 
-    // shared memory plan: [tree 32 B/node][stack 8 B x levels x threads][table 27 x 4 B]
+    // shared memory plan: [tree 32 B/node][stack 16 B x levels x threads][table 27 x 4 B]
     CU(cudaSetDevice(devices[0]));
     int max_optin = 0, sms = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, devices[0]));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devices[0]));
     const size_t tree_bytes = c->tree.nodes.size() * sizeof(NodeRec);
-    const size_t stack_bytes = (size_t)c->stack_levels * kThreads * sizeof(uint2);
+    const size_t stack_bytes = (size_t)c->stack_levels * kThreads * sizeof(uint4);
     const size_t table_bytes = 32 * sizeof(uint32_t);
     // keep at least two CTAs per SM when the tree is staged in shared memory
     c->tree_in_smem = tree_bytes + stack_bytes + table_bytes <= (size_t)max_optin / 2 - 1024;

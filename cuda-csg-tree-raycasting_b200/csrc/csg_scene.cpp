@@ -301,6 +301,7 @@ struct Box {
 struct Work {  // working tree node
     int type, prim, left, right;
     Box box;
+    bool has_cylinder = false;  // some cylinder below: the box only GATES (Q6), it does not bound the hits
 };
 
 // Culling box of a leaf.  Culling boxes only decide whether a subtree is skipped; the proof that any box
@@ -331,7 +332,13 @@ struct Builder {
     std::vector<Work> w;
     explicit Builder(const Scene& sc) : s(sc) {}
 
-    int add(int type, int prim, int l, int r) { w.push_back(Work{type, prim, l, r, Box{}}); return (int)w.size() - 1; }
+    int add(int type, int prim, int l, int r)
+    {
+        Work n{type, prim, l, r, Box{}, false};
+        n.has_cylinder = prim != -1 ? type == kCylinder : (w[l].has_cylinder || w[r].has_cylinder);
+        w.push_back(n);
+        return (int)w.size() - 1;
+    }
 
     // Copies the parsed tree shape.
     int copy(int id)
@@ -487,6 +494,7 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
         uint32_t meta = (uint32_t)n.type | ((uint32_t)right << 8);
         if (b.w[n.left].prim != -1) meta |= kMetaLeftLeaf;
         if (b.w[n.right].prim != -1) meta |= kMetaRightLeaf;
+        if (!n.has_cylinder) meta |= kMetaBounded;
         out.nodes[me].meta = meta;
     };
     emit(root, -1, 0);

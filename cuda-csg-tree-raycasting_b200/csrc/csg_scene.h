@@ -27,7 +27,8 @@ static_assert(sizeof(RefNode) == 44 && sizeof(RefPrim) == 48, "reference layouts
 
 // ---- flattened GPU tree -------------------------------------------------------------------
 // One 32-byte record per node, preorder (left child of operator n is n+1):
-//   word 7 (all kinds)   kind | leftIsLeaf<<3 | rightIsLeaf<<4 | idx<<8   idx = right child (operator) / primitive id (leaf)
+//   word 7 (all kinds)   kind | leftIsLeaf<<3 | rightIsLeaf<<4 | bounded<<5 | idx<<8   idx = right child (operator) / primitive id (leaf)
+//                        bounded = no cylinder below: the culling box really bounds every hit of the subtree (allows pruning)
 //   operator   w0..5 = culling box (min xyz, max xyz),  w6 = parent node (-1 at the root)
 //   sphere     w0..2 = centre, w3 = radius, w4..6 = centre again (the kernel turns w0..2 into origin-centre while staging)
 //   cube       w0..5 = lb, rt  (centre -/+ size/2, rounded like the reference rounds them)
@@ -37,7 +38,7 @@ struct NodeRec {
     uint32_t meta;
 };
 static_assert(sizeof(NodeRec) == 32, "record");
-constexpr uint32_t kMetaLeftLeaf = 1u << 3, kMetaRightLeaf = 1u << 4;
+constexpr uint32_t kMetaLeftLeaf = 1u << 3, kMetaRightLeaf = 1u << 4, kMetaBounded = 1u << 5;
 
 // Per-primitive data kept in global memory (read on accepted hits / cylinder + cube tests / shading): 5 x float4.
 struct PrimRec {
