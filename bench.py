@@ -56,7 +56,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -146,7 +146,11 @@ def bench_ours(args):
         ctx.sync()
         return ctx.last_frame_ms()
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here: nvidia-smi needs a few hundred ms before its first sample)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
     for _ in range(max(3, args.warmup)):
         flush.zero_()
         barrier()
@@ -154,9 +158,6 @@ def bench_ours(args):
     barrier()
 
     # ---- timed: exactly K steps; per-step device time from CUDA events on the launching stream, L2 flushed between steps
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launch_count()
     step_ms = []
     barrier()
@@ -341,7 +342,7 @@ def bench_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--optimize", type=int, default=1, help="load-time tree optimisation level (csg_scene_set_optimize)")

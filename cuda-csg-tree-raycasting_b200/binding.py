@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcsg_b200.so")
+LIB_PATH = os.environ.get("CSG_B200_LIB") or os.path.join(_HERE, "libcsg_b200.so")   # override = tuning sweeps only
 
 CSG_OK, CSG_ERR_PARSE, CSG_ERR_IO, CSG_ERR_CUDA, CSG_ERR_ARG, CSG_ERR_NO_DEVICE, CSG_ERR_LIMIT = range(7)
 
@@ -23,7 +23,7 @@ EXPORTS = [
     "csg_load_scene", "csg_parse_scene", "csg_free_scene", "csg_scene_counts", "csg_scene_dump", "csg_scene_write",
     "csg_generate_scene", "csg_camera_default", "csg_camera_set", "csg_camera_set_fov_degrees", "csg_light_default",
     "csg_light_direction", "csg_upload", "csg_upload_shard", "csg_free_context", "csg_scene_set_optimize",
-    "csg_render", "csg_render_f32", "csg_render_aov", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
+    "csg_render", "csg_render_f32", "csg_render_aov", "csg_render_stats", "csg_set_supersampling", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
     "csg_launch_count", "csg_framebuffer", "csg_framebuffer_ipc_handle", "csg_set_gather_target_ipc",
     "csg_set_gather_target", "csg_read_framebuffer", "csg_device_tan_half_fov", "csg_fp32_peak_tflops", "csg_context_info",
     "csg_last_error", "csg_version",
@@ -73,6 +73,8 @@ def _load():
         "csg_render": (i, [vp, C.POINTER(CCamera), C.POINTER(CLight), vp]),
         "csg_render_f32": (i, [vp, C.POINTER(CCamera), C.POINTER(CLight), vp]),
         "csg_render_aov": (i, [vp, C.POINTER(CCamera), vp, vp, vp]),
+        "csg_render_stats": (i, [vp, C.POINTER(CCamera), vp]),
+        "csg_set_supersampling": (i, [vp, i]),
         "csg_render_enqueue": (i, [vp, C.POINTER(CCamera), C.POINTER(CLight), vp]),
         "csg_sync": (i, [vp]),
         "csg_last_frame_ms": (i, [vp, C.POINTER(f)]),
@@ -261,6 +263,15 @@ class Context:
         t = np.empty(n, np.float32)
         _check(lib.csg_render_aov(self.h, C.byref(cam.c), _ptr(hit), _ptr(prim), _ptr(t)))
         return hit, prim, t
+
+    def set_supersampling(self, samples_per_axis):
+        _check(lib.csg_set_supersampling(self.h, int(samples_per_axis)))
+        return self
+
+    def render_stats(self, cam):
+        it = np.empty(self.width * self.height, np.int32)
+        _check(lib.csg_render_stats(self.h, C.byref(cam.c), _ptr(it)))
+        return it
 
     def enqueue(self, cam, light, out_dev=None):
         _check(lib.csg_render_enqueue(self.h, C.byref(cam.c), C.byref(light.c), _ptr(out_dev)))

@@ -22,7 +22,13 @@ using namespace csgb;
 // =========================================================================================== device code
 namespace csgb {
 
-constexpr int kThreads = 256;           // 8 warps per CTA
+// CTA shapes the frame kernel is compiled for.  All three keep 24 warps per SM at <= 80 registers/thread
+// (768 threads x 80 registers x 1 CTA, 384 x 2, 256 x 3 all fill the 64K-register file); they differ in how many copies
+// of the staged tree and how much stack an SM holds.  The launcher picks the shape with the most resident warps for the
+// scene at hand, the largest CTA on ties (one tree copy per SM).
+constexpr int kShapes = 3;
+constexpr int kShapeThreads[kShapes] = {768, 384, 256};
+constexpr int min_blocks_for(int threads) { return threads >= 768 ? 1 : threads >= 384 ? 2 : 3; }
 constexpr int kWarpTileW = 8, kWarpTileH = 4;   // one warp = one 8x4 pixel tile (Raycaster.cuh:7-8 uses the same shape)
 constexpr int kMacroW = 64, kMacroH = 32;       // sharding unit: 8x8 warp tiles
 
@@ -106,9 +112,10 @@ __device__ __forceinline__ uint32_t to_u8(float c)
 //   * when the first child returns a hit at t and the pending sibling's box starts beyond t, the sibling cannot change
 //     the outcome (Union: every cell with a farther Enter or a Miss on the other side returns this hit; Difference: same
 //     for the right operand) and is skipped.
+template <bool COUNT>
 __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, const float4* __restrict__ prims,
                                         const uint32_t* __restrict__ table, uint4* __restrict__ stack,
-                                        const int stack_stride, const Ray& r, const bool root_is_leaf)
+                                        const int stack_stride, const Ray& r, const bool root_is_leaf, int& iters)
 {
     enum { ST_ENTER = 0, ST_LOOPL = 1, ST_LOOPR = 2, ST_COMPUTE = 3, ST_RETURN = 4, ST_DONE = 5 };
     Hit L = make_miss(), R = make_miss();
@@ -121,8 +128,11 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     }
     uint32_t n = 0u;                           // byte offset of the current operator's record
     uint4* sp = stack;                         // next free frame
+    *sp = make_uint4(0u, 0u, 0u, 0xffffffffu); // sentinel frame: popping it ends the traversal (no base pointer to keep)
+    sp += stack_stride;
     int st = ST_ENTER;
     while (st != ST_DONE) {
+        if (COUNT) ++iters;
         if (st <= ST_LOOPR) {
             const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
             const uint32_t op = meta & 7u;
@@ -182,10 +192,10 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
             } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
         }
         if (st == ST_RETURN) {                  // action = actionStack.pop(); node = GetParent() (:624-625 etc.); L == R == result
-            if (sp == stack) { st = ST_DONE; }
+            sp -= stack_stride;
+            const uint4 f = *sp;
+            if (f.w == 0xffffffffu) { st = ST_DONE; }
             else {
-                sp -= stack_stride;
-                const uint4 f = *sp;
                 n = f.w;
                 const uint32_t ret = f.y & F_RET_MASK;
                 if (ret == F_LOAD_LFT) {        // :611-614
@@ -213,14 +223,14 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     return L;                                   // :511
 }
 
-template <int MODE, bool TREE_SMEM>
-__global__ void __launch_bounds__(kThreads, 2) csg_frame_kernel(const __grid_constant__ FrameParams p)
+template <int MODE, bool TREE_SMEM, int kThreads>
+__global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_kernel(const __grid_constant__ FrameParams p)
 {
+    // shared memory: [outcome table 128 B][stack: (levels+1) x kThreads x 16 B][staged tree 32 B/node]
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4* s_nodes = reinterpret_cast<uint4*>(smem_raw);
-    const int n_staged = TREE_SMEM ? p.n_nodes : 0;
-    uint4* s_stack = s_nodes + 2 * n_staged;
-    uint32_t* s_table = reinterpret_cast<uint32_t*>(s_stack + (size_t)p.stack_levels * kThreads);
+    uint32_t* s_table = reinterpret_cast<uint32_t*>(smem_raw);
+    uint4* s_stack = reinterpret_cast<uint4*>(smem_raw + 128);
+    uint4* s_nodes = s_stack + (size_t)(p.stack_levels + 1) * kThreads;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const float ox = p.cam_pos[0], oy = p.cam_pos[1], oz = p.cam_pos[2];
@@ -248,46 +258,112 @@ __global__ void __launch_bounds__(kThreads, 2) csg_frame_kernel(const __grid_con
     uint4* my_stack = s_stack + tid;
 
     // per-frame constants of ray generation, RaycastKernel :11-16
-    const float wf = (float)p.width, hf = (float)p.height;
-    const float wm1 = __fsub_rn(wf, 1.0f), hm1 = __fsub_rn(hf, 1.0f);
-    const float aspect = __fdiv_rn(wf, hf);
-    const float th = p.tan_half_fov;   // tan(cam.fov / 2.0f), :15-16
+    // Per-frame constants of ray generation (RaycastKernel :11-16) arrive precomputed in the parameter block (wm1 = w-1,
+    // hm1 = h-1, aspect = w/h: single IEEE operations, identical on the host; tan(fov/2) from the device, see csg_tan_kernel).
+    // With supersampling (ss samples per axis) they describe the virtual (width*ss) x (height*ss) grid: sub-sample (sx,sy)
+    // of pixel (x,y) is virtual pixel (x*ss+sx, y*ss+sy), SURVEY.md §8(d) row 5.
+    const int ss = p.ss;
 
-    for (;;) {
-        unsigned long long ticket = 0;
-        if (lane == 0) ticket = atomicAdd(p.tile_counter, 1ull) - p.counter_base;
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        if (ticket >= (unsigned long long)p.n_local_warp_tiles) break;
-        const int k = (int)(ticket & 63ull);
-        const int macro = (int)(ticket >> 6) * p.shard_count + p.shard_rank;
-        const int mx = macro % p.macro_x, my = macro / p.macro_x;
+    // ---- phase 1: macro tiles entirely outside the screen-space bound of the scene are Miss everywhere (:109): fill them
+    // with the background, statically partitioned over the warps of this shard (no traversal, no tickets).
+    {
+        const int warps_per_cta = kThreads / 32;
+        const int gw = blockIdx.x * warps_per_cta + (tid >> 5), GW = gridDim.x * warps_per_cta;
+        const int total_macros = p.macro_x * p.macro_y;
+        for (int m = gw * p.shard_count + p.shard_rank; m < total_macros; m += GW * p.shard_count) {
+            const int my = p.div_magic ? (int)__umulhi((unsigned int)m, p.div_magic) : m / p.macro_x;
+            const int mx = m - my * p.macro_x;
+            if (mx >= p.rm_x0 && mx < p.rm_x0 + p.rm_w && my >= p.rm_y0 && my < p.rm_y0 + p.rm_h) continue;   // traced in phase 2
+            const int x0 = mx * kMacroW, y0 = my * kMacroH;
+            if (MODE == OUT_RGBA8 && (p.width & 3) == 0) {
+                const uint32_t bg = 20u | (20u << 8) | (28u << 16) | 0xFF000000u;   // (0.08,0.08,0.11,1) quantised per Q12
+                const int x = x0 + (lane & 15) * 4;
+#pragma unroll 4
+                for (int r = lane >> 4; r < kMacroH; r += 2) {
+                    const int y = y0 + r;
+                    if (x < p.width && y < p.height) reinterpret_cast<uint4*>(p.out)[((size_t)y * p.width + x) >> 2] = make_uint4(bg, bg, bg, bg);
+                }
+            } else {
+                for (int r = 0; r < kMacroH; ++r) {
+                    const int y = y0 + r;
+                    if (y >= p.height) break;
+                    for (int cx = lane; cx < kMacroW; cx += 32) {
+                        const int x = x0 + cx;
+                        if (x >= p.width) continue;
+                        const size_t pix = (size_t)y * p.width + x;
+                        if (MODE == OUT_RGBA8) reinterpret_cast<uint32_t*>(p.out)[pix] = 20u | (20u << 8) | (28u << 16) | 0xFF000000u;
+                        else if (MODE == OUT_F32) reinterpret_cast<float4*>(p.out)[pix] = make_float4(0.08f, 0.08f, 0.11f, 1.0f);
+                        else {
+                            if (p.aov_hit) p.aov_hit[pix] = 0;
+                            if (p.aov_prim) p.aov_prim[pix] = -1;
+                            if (p.aov_t) p.aov_t[pix] = -1.0f;
+                            if (p.aov_iters) p.aov_iters[pix] = 0;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- phase 2: dynamic tile scheduling over the macro tiles that touch the bound: one ticket per warp tile; the next
+    // ticket is requested before the current tile is rendered so the atomic's round trip hides behind the traversal.
+    // Ticket t -> macro tile number (t >> 6) * shard_count + shard_rank of the rm_w x rm_h macro rectangle, warp tile t & 63.
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    while (ticket < (unsigned int)p.n_local_warp_tiles) {
+        const unsigned int cur = ticket;
+        unsigned int next = 0;
+        if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+        const int k = (int)(cur & 63u);
+        const int j = (int)(cur >> 6) * p.shard_count + p.shard_rank;
+        // j / rm_w by multiply-high with a host-computed reciprocal (exact for the ranges the host enables it for)
+        const int jy = p.rm_magic ? (int)__umulhi((unsigned int)j, p.rm_magic) : j / p.rm_w;
+        const int mx = p.rm_x0 + (j - jy * p.rm_w), my = p.rm_y0 + jy;
         const int kx = (k & 1) | ((k >> 1) & 2) | ((k >> 2) & 4);        // Morton order inside the macro tile
         const int ky = ((k >> 1) & 1) | ((k >> 2) & 2) | ((k >> 3) & 4);
         const int x = mx * kMacroW + kx * kWarpTileW + (lane & 7);
         const int y = my * kMacroH + ky * kWarpTileH + (lane >> 3);
         const bool active = x < p.width && y < p.height;
-        if (__ballot_sync(0xffffffffu, active) == 0u) continue;
+        ticket = 0xffffffffu;   // placeholder; the real value is broadcast at the end of the iteration
+        if (__ballot_sync(0xffffffffu, active) == 0u) { ticket = __shfl_sync(0xffffffffu, next, 0); continue; }
 
         Hit res = make_miss();
+        int iters = 0;
         Ray r;
         r.ox = ox; r.oy = oy; r.oz = oz;
-        if (active) {
-            // RaycastKernel :11-27 + Ray ctor (Ray.cuh:12-18)
-            const float u = __fdiv_rn(__fadd_rn((float)x, 0.5f), wm1);
-            const float v = __fdiv_rn(__fadd_rn((float)y, 0.5f), hm1);
-            const float nx = __fmul_rn(__fmul_rn(aspect, __fmaf_rn(u, 2.0f, -1.0f)), th);
-            const float ny = __fmul_rn(__fsub_rn(1.0f, __fadd_rn(v, v)), th);
-            float cx = __fadd_rn(p.forward[0], __fmaf_rn(p.right[0], nx, __fmul_rn(p.up[0], ny)));
-            float cy = __fadd_rn(p.forward[1], __fmaf_rn(p.right[1], nx, __fmul_rn(p.up[1], ny)));
-            float cz = __fadd_rn(p.forward[2], __fmaf_rn(p.right[2], nx, __fmul_rn(p.up[2], ny)));
+        float accx = 0.f, accy = 0.f, accz = 0.f;
+        // whole warp tile outside the screen-space bound of the root box: every ray is a Miss (:109 background colour)
+        const int tx0 = x - (lane & 7), ty0 = y - (lane >> 3);
+        const bool tile_empty = tx0 > p.rect_x1 || tx0 + (kWarpTileW - 1) < p.rect_x0 || ty0 > p.rect_y1 || ty0 + (kWarpTileH - 1) < p.rect_y0;
+        if (tile_empty) {
+            const float w = (float)(ss * ss);
+            accx = 0.08f * w; accy = 0.08f * w; accz = 0.11f * w;
+        } else if (active) {
+#pragma unroll 1
+            for (int s = 0; s < ss * ss; ++s) {
+                const int vx = x * ss + (s % ss), vy = y * ss + (s / ss);
+                // RaycastKernel :11-27 + Ray ctor (Ray.cuh:12-18)
+                const float u = __fdiv_rn(__fadd_rn((float)vx, 0.5f), p.wm1);
+                const float v = __fdiv_rn(__fadd_rn((float)vy, 0.5f), p.hm1);
+                const float nx = __fmul_rn(__fmul_rn(p.aspect, __fmaf_rn(u, 2.0f, -1.0f)), p.tan_half_fov);
+                const float ny = __fmul_rn(__fsub_rn(1.0f, __fadd_rn(v, v)), p.tan_half_fov);
+                float cx = __fadd_rn(p.forward[0], __fmaf_rn(p.right[0], nx, __fmul_rn(p.up[0], ny)));
+                float cy = __fadd_rn(p.forward[1], __fmaf_rn(p.right[1], nx, __fmul_rn(p.up[1], ny)));
+                float cz = __fadd_rn(p.forward[2], __fmaf_rn(p.right[2], nx, __fmul_rn(p.up[2], ny)));
 #pragma unroll
-            for (int rep = 0; rep < 2; ++rep) {   // normalize() then the Ray ctor normalises again (Q3)
-                const float inv = __frcp_rn(__fsqrt_rn(dot_ref(cx, cy, cz, cx, cy, cz)));
-                cx = __fmul_rn(inv, cx); cy = __fmul_rn(inv, cy); cz = __fmul_rn(inv, cz);
+                for (int rep = 0; rep < 2; ++rep) {   // normalize() then the Ray ctor normalises again (Q3)
+                    const float inv = __frcp_rn(__fsqrt_rn(dot_ref(cx, cy, cz, cx, cy, cz)));
+                    cx = __fmul_rn(inv, cx); cy = __fmul_rn(inv, cy); cz = __fmul_rn(inv, cz);
+                }
+                r.dx = cx; r.dy = cy; r.dz = cz;
+                r.ix = __frcp_rn(cx); r.iy = __frcp_rn(cy); r.iz = __frcp_rn(cz);
+                res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, kThreads, r, p.root_is_leaf != 0, iters);
+                if (MODE != OUT_AOV) {
+                    const float4 c = shade_pixel(res, r, p.prims, p);
+                    accx += c.x; accy += c.y; accz += c.z;
+                }
             }
-            r.dx = cx; r.dy = cy; r.dz = cz;
-            r.ix = __frcp_rn(cx); r.iy = __frcp_rn(cy); r.iz = __frcp_rn(cz);
-            res = traverse(tree, p.prims, s_table, my_stack, kThreads, r, p.root_is_leaf != 0);
         }
 
         const size_t pix = (size_t)y * p.width + x;   // :33
@@ -297,10 +373,14 @@ __global__ void __launch_bounds__(kThreads, 2) csg_frame_kernel(const __grid_con
                 if (p.aov_hit) p.aov_hit[pix] = hit ? 1 : 0;
                 if (p.aov_prim) p.aov_prim[pix] = hit ? (int32_t)((res.m & H_META_MASK) >> H_ID_SHIFT) : -1;
                 if (p.aov_t) p.aov_t[pix] = hit ? res.t : -1.0f;
+                if (p.aov_iters) p.aov_iters[pix] = iters;
             }
         } else {
-            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) c = shade_pixel(res, r, p.prims, p);
+            float4 c = make_float4(accx, accy, accz, 1.0f);
+            if (ss > 1) {   // box filter of the linear colour
+                const float w = __frcp_rn((float)(ss * ss));
+                c.x *= w; c.y *= w; c.z *= w;
+            }
             if (MODE == OUT_F32) {
                 if (active) reinterpret_cast<float4*>(p.out)[pix] = c;
             } else {
@@ -316,6 +396,7 @@ __global__ void __launch_bounds__(kThreads, 2) csg_frame_kernel(const __grid_con
                 }
             }
         }
+        ticket = __shfl_sync(0xffffffffu, next, 0);
     }
 }
 
@@ -384,8 +465,8 @@ struct Shard {  // one GPU's share of the frame
     uint4* d_nodes = nullptr;
     uint4* d_staged = nullptr;   // only when the tree does not fit in shared memory
     float4* d_prims = nullptr;
-    unsigned long long* d_counter = nullptr;
-    unsigned long long counter_base = 0;
+    unsigned int* d_counter = nullptr;
+    unsigned int counter_base = 0;
     float* d_tan = nullptr;
     int grid = 0;
     int n_local_warp_tiles = 0;
@@ -404,12 +485,17 @@ struct csg_context {
     bool tree_in_smem = true;
     size_t smem_bytes = 0;
     int stack_levels = 1;
+    int threads = 256;           // CTA shape chosen at upload (one of kShapeThreads)
+    bool root_box_valid = false; // root_box = culling box of the whole scene (min xyz, max xyz), for the screen-space bound
+    float root_box[6] = {0, 0, 0, 0, 0, 0};
     std::vector<Shard> shards;   // in-process: one per device; multi-process: exactly one
     uint8_t* d_fb = nullptr;     // RGBA8 framebuffer on the root device (or this rank's device)
     float* d_f32 = nullptr;      // lazily allocated
     uint8_t* d_aov_hit = nullptr;
     int32_t* d_aov_prim = nullptr;
     float* d_aov_t = nullptr;
+    int32_t* d_aov_iters = nullptr;
+    int ss = 1;                  // supersampling: samples per axis
     uint64_t launches = 0;
     float cached_fov = -1.f, cached_tan = 0.f;   // device tanf(fov/2) of the last field of view seen
     float last_ms = 0.f;
@@ -419,26 +505,87 @@ struct csg_context {
 
 namespace {
 
-template <int MODE>
-int launch_mode(csg_context* c, Shard& s, const FrameParams& fp)
+template <int MODE, bool SM, int T>
+int launch_one(csg_context* c, Shard& s, const FrameParams& fp)
 {
-    cudaError_t e;
-    if (c->tree_in_smem) {
-        csg_frame_kernel<MODE, true><<<s.grid, kThreads, c->smem_bytes, s.stream>>>(fp);
-    } else {
-        csg_frame_kernel<MODE, false><<<s.grid, kThreads, c->smem_bytes, s.stream>>>(fp);
-    }
-    e = cudaGetLastError();
+    csg_frame_kernel<MODE, SM, T><<<s.grid, T, c->smem_bytes, s.stream>>>(fp);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return CSG_OK;
 }
 
 template <int MODE, bool SM>
-int configure_kernel(size_t smem, int* blocks_per_sm)
+int launch_shape(csg_context* c, Shard& s, const FrameParams& fp)
 {
-    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, SM>, kThreads, smem));
+    switch (c->threads) {
+        case 768: return launch_one<MODE, SM, 768>(c, s, fp);
+        case 384: return launch_one<MODE, SM, 384>(c, s, fp);
+        default: return launch_one<MODE, SM, 256>(c, s, fp);
+    }
+}
+
+template <int MODE>
+int launch_mode(csg_context* c, Shard& s, const FrameParams& fp)
+{
+    return c->tree_in_smem ? launch_shape<MODE, true>(c, s, fp) : launch_shape<MODE, false>(c, s, fp);
+}
+
+template <int MODE, bool SM, int T>
+int configure_one(size_t smem, int* blocks_per_sm)
+{
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, SM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, SM, T>, T, smem));
     return CSG_OK;
+}
+
+template <bool SM, int T>
+int configure_modes(size_t smem, int* bps)
+{
+    int rc;
+    if ((rc = configure_one<OUT_F32, SM, T>(smem, bps))) return rc;
+    if ((rc = configure_one<OUT_AOV, SM, T>(smem, bps))) return rc;
+    return configure_one<OUT_RGBA8, SM, T>(smem, bps);
+}
+
+template <bool SM>
+int configure_shape(int threads, size_t smem, int* bps)
+{
+    switch (threads) {
+        case 768: return configure_modes<SM, 768>(smem, bps);
+        case 384: return configure_modes<SM, 384>(smem, bps);
+        default: return configure_modes<SM, 256>(smem, bps);
+    }
+}
+
+// Pixel rectangle that contains the projection of the root's culling box (padded by 2 pixels); full frame when any corner
+// of the box is not safely in front of the camera.
+void screen_bound(const csg_context* c, const csg_camera* cam, FrameParams& fp)
+{
+    fp.rect_x0 = 0; fp.rect_y0 = 0; fp.rect_x1 = c->width - 1; fp.rect_y1 = c->height - 1;
+    if (!c->root_box_valid) return;
+    const double W = (double)c->width * c->ss, H = (double)c->height * c->ss;
+    const double th = std::tan((double)cam->fov * 0.5), aspect = W / H;
+    if (!(th > 1e-6) || !std::isfinite(th)) return;
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int k = 0; k < 8; ++k) {
+        double v[3];
+        for (int a = 0; a < 3; ++a) v[a] = (double)((k >> a) & 1 ? c->root_box[3 + a] : c->root_box[a]) - (double)cam->pos[a];
+        const double z = v[0] * cam->forward[0] + v[1] * cam->forward[1] + v[2] * cam->forward[2];
+        const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (!(z > 1e-3 * len) || !(z > 1e-9)) return;   // corner beside/behind the camera: no useful bound
+        const double nx = (v[0] * cam->right[0] + v[1] * cam->right[1] + v[2] * cam->right[2]) / z;
+        const double ny = (v[0] * cam->up[0] + v[1] * cam->up[1] + v[2] * cam->up[2]) / z;
+        const double px = (nx / (aspect * th) + 1.0) * 0.5 * (W - 1.0) - 0.5;    // inverse of RaycastKernel :11-16
+        const double py = (1.0 - ny / th) * 0.5 * (H - 1.0) - 0.5;
+        if (!std::isfinite(px) || !std::isfinite(py)) return;
+        xmin = std::min(xmin, px); xmax = std::max(xmax, px);
+        ymin = std::min(ymin, py); ymax = std::max(ymax, py);
+    }
+    const double pad = 2.0 * c->ss, big = 1e9;
+    xmin = std::max(-big, xmin - pad); ymin = std::max(-big, ymin - pad);
+    xmax = std::min(big, xmax + pad);  ymax = std::min(big, ymax + pad);
+    fp.rect_x0 = (int)std::floor(xmin / c->ss); fp.rect_y0 = (int)std::floor(ymin / c->ss);
+    fp.rect_x1 = (int)std::ceil(xmax / c->ss);  fp.rect_y1 = (int)std::ceil(ymax / c->ss);
 }
 
 void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, const float light[3], FrameParams& fp)
@@ -457,9 +604,11 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
     fp.height = c->height;
     fp.macro_x = c->macro_x;
     fp.macro_y = c->macro_y;
+    // floor(n / d) == umulhi(n, floor(2^32 / d) + 1) whenever n < 2^20 and 1 < d < 2^12
+    fp.div_magic = (c->macro_x > 1 && c->macro_x < 4096 && (long long)c->macro_x * c->macro_y < (1ll << 20))
+                       ? (unsigned int)((1ull << 32) / (unsigned long long)c->macro_x + 1ull) : 0u;
     fp.shard_rank = s.rank;
     fp.shard_count = c->shard_count;
-    fp.n_local_warp_tiles = s.n_local_warp_tiles;
     fp.counter_base = s.counter_base;
     fp.tile_counter = s.d_counter;
     fp.nodes = c->tree_in_smem ? s.d_nodes : s.d_staged;
@@ -467,6 +616,26 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
     fp.n_nodes = (int)c->tree.nodes.size();
     fp.root_is_leaf = c->tree.root_is_leaf ? 1 : 0;
     fp.stack_levels = c->stack_levels;
+    fp.ss = c->ss;
+    const float wf = (float)(c->width * c->ss), hf = (float)(c->height * c->ss);
+    fp.wm1 = wf - 1.0f;       // (width - 1), :11
+    fp.hm1 = hf - 1.0f;       // (height - 1), :12
+    fp.aspect = wf / hf;      // (width / height), :15
+    screen_bound(c, cam, fp);
+    // macro-tile rectangle touched by the bound; the ticket space of this frame covers only these
+    const int ax0 = std::max(fp.rect_x0, 0), ay0 = std::max(fp.rect_y0, 0);
+    const int ax1 = std::min(fp.rect_x1, c->width - 1), ay1 = std::min(fp.rect_y1, c->height - 1);
+    if (ax0 > ax1 || ay0 > ay1) {
+        fp.rm_x0 = fp.rm_y0 = 0; fp.rm_w = fp.rm_h = 0;
+    } else {
+        fp.rm_x0 = ax0 / kMacroW; fp.rm_y0 = ay0 / kMacroH;
+        fp.rm_w = ax1 / kMacroW - fp.rm_x0 + 1; fp.rm_h = ay1 / kMacroH - fp.rm_y0 + 1;
+    }
+    const long long traced = (long long)fp.rm_w * fp.rm_h;
+    const long long mine = traced > s.rank ? (traced - s.rank + c->shard_count - 1) / c->shard_count : 0;
+    fp.n_local_warp_tiles = (int)(mine * 64);
+    fp.rm_magic = (fp.rm_w > 1 && fp.rm_w < 4096 && traced < (1ll << 20)) ? (unsigned int)((1ull << 32) / (unsigned long long)fp.rm_w + 1ull) : 0u;
+    if (fp.rm_w == 0) fp.rm_w = 1;   // never divide by zero; n_local_warp_tiles is 0 anyway
 }
 
 // Enqueue one frame on every shard.  mode: OUT_RGBA8 -> out = rgba8 target (NULL: each shard's own target),
@@ -475,6 +644,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
 {
     if (!c || !cam) return fail(CSG_ERR_ARG, "null argument");
     if (mode != OUT_RGBA8 && c->shards.size() != 1) return fail(CSG_ERR_ARG, "f32/aov output needs a single-shard context");
+    if (mode == OUT_AOV && c->ss != 1) return fail(CSG_ERR_ARG, "AOV output is per primary ray: set supersampling to 1");
     Shard& root = c->shards[0];
     CU(cudaSetDevice(root.device));
     if (!(cam->fov == c->cached_fov)) {   // new field of view: one tiny launch + 4-byte readback, then cached
@@ -489,7 +659,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
         CU(cudaSetDevice(c->shards[i].device));
         CU(cudaStreamWaitEvent(c->shards[i].stream, root.ev_start, 0));
     }
-    const int total_warps_per_cta = kThreads / 32;
+    const int total_warps_per_cta = c->threads / 32;
     for (Shard& s : c->shards) {
         CU(cudaSetDevice(s.device));
         FrameParams fp;
@@ -511,12 +681,13 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             fp.aov_hit = c->d_aov_hit;
             fp.aov_prim = c->d_aov_prim;
             fp.aov_t = c->d_aov_t;
+            fp.aov_iters = c->d_aov_iters;
             rc = launch_mode<OUT_AOV>(c, s, fp);
         }
         if (rc) return rc;
         c->launches++;
         // every warp of the grid draws exactly one ticket past the end
-        s.counter_base += (unsigned long long)s.n_local_warp_tiles + (unsigned long long)s.grid * total_warps_per_cta;
+        s.counter_base += (unsigned int)fp.n_local_warp_tiles + (unsigned int)(s.grid * total_warps_per_cta);   // wraps mod 2^32 like the device counter
         if (&s != &root) CU(cudaEventRecord(s.ev_done, s.stream));
     }
     CU(cudaSetDevice(root.device));
@@ -572,25 +743,39 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     c->multi_process = multi_process;
     flatten(scene->scene, scene->scene.optimize, c->tree);
     c->stack_levels = std::max(1, c->tree.depth);
+    c->root_box_valid = c->tree.root_box_valid;
+    for (int i = 0; i < 6; ++i) c->root_box[i] = c->tree.root_box[i];
 
     auto cleanup_fail = [&](int code) { csg_free_context(c); return code; };
 
-    // shared memory plan: [tree 32 B/node][stack 16 B x levels x threads][table 27 x 4 B]
+    // shared memory plan: [table 128 B][stack 16 B x (levels+1) x threads][tree 32 B/node]
     CU(cudaSetDevice(devices[0]));
     int max_optin = 0, sms = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, devices[0]));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devices[0]));
     const size_t tree_bytes = c->tree.nodes.size() * sizeof(NodeRec);
-    const size_t stack_bytes = (size_t)c->stack_levels * kThreads * sizeof(uint4);
     const size_t table_bytes = 32 * sizeof(uint32_t);
-    // keep at least two CTAs per SM when the tree is staged in shared memory
-    c->tree_in_smem = tree_bytes + stack_bytes + table_bytes <= (size_t)max_optin / 2 - 1024;
-    c->smem_bytes = (c->tree_in_smem ? tree_bytes : 0) + stack_bytes + table_bytes;
-    if (c->smem_bytes > (size_t)max_optin) {
-        g_err = "tree depth " + std::to_string(c->tree.depth) + " needs " + std::to_string(c->smem_bytes) +
-                " bytes of traversal stack per CTA; limit is " + std::to_string(max_optin) +
-                " (the reference's own stacks hold 32 entries, RaycastingKernels.cuh:19)";
-        return cleanup_fail(CSG_ERR_LIMIT);
+    {
+        // resident warps per SM for every (shape, tree placement); +1 KB per CTA is what the driver reserves
+        const size_t sm_total = (size_t)max_optin + 1024;
+        int best_warps = -1;
+        for (int pass = 0; pass < 2 && best_warps < 16; ++pass) {   // pass 0: tree in shared memory, pass 1: tree in global memory / L1
+            const bool in_smem = pass == 0;
+            for (int i = 0; i < kShapes; ++i) {
+                const int T = kShapeThreads[i];
+                const size_t stack_bytes = (size_t)(c->stack_levels + 1) * T * sizeof(uint4);   // +1: sentinel frame
+                const size_t need = (in_smem ? tree_bytes : 0) + stack_bytes + table_bytes;
+                if (need > (size_t)max_optin) continue;
+                const int ctas = (int)std::min<size_t>(min_blocks_for(T), sm_total / (need + 1024));
+                const int warps = ctas * T / 32;
+                if (warps > best_warps) { best_warps = warps; c->threads = T; c->tree_in_smem = in_smem; c->smem_bytes = need; }
+            }
+        }
+        if (best_warps <= 0) {
+            g_err = "tree depth " + std::to_string(c->tree.depth) + " needs more traversal stack than one SM's shared memory (" +
+                    std::to_string(max_optin) + " bytes) holds (the reference's own stacks hold 32 entries, RaycastingKernels.cuh:19)";
+            return cleanup_fail(CSG_ERR_LIMIT);
+        }
     }
 
     const int total_macros = c->macro_x * c->macro_y;
@@ -601,22 +786,14 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         s.rank = shard_rank0 + (int)i;
         CU(cudaSetDevice(s.device));
         int bps = 0, rc;
-        if (c->tree_in_smem) {
-            if ((rc = configure_kernel<OUT_RGBA8, true>(c->smem_bytes, &bps))) return cleanup_fail(rc);
-            if ((rc = configure_kernel<OUT_F32, true>(c->smem_bytes, &bps))) return cleanup_fail(rc);
-            if ((rc = configure_kernel<OUT_AOV, true>(c->smem_bytes, &bps))) return cleanup_fail(rc);
-            if ((rc = configure_kernel<OUT_RGBA8, true>(c->smem_bytes, &bps))) return cleanup_fail(rc);
-        } else {
-            if ((rc = configure_kernel<OUT_F32, false>(c->smem_bytes, &bps))) return cleanup_fail(rc);
-            if ((rc = configure_kernel<OUT_AOV, false>(c->smem_bytes, &bps))) return cleanup_fail(rc);
-            if ((rc = configure_kernel<OUT_RGBA8, false>(c->smem_bytes, &bps))) return cleanup_fail(rc);
-        }
+        rc = c->tree_in_smem ? configure_shape<true>(c->threads, c->smem_bytes, &bps) : configure_shape<false>(c->threads, c->smem_bytes, &bps);
+        if (rc) return cleanup_fail(rc);
         if (bps < 1) { g_err = "kernel does not fit on an SM"; return cleanup_fail(CSG_ERR_LIMIT); }
         int dev_sms = 0;
         CU(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s.device));
         const int my_macros = (total_macros - s.rank + shard_count - 1) / shard_count;
         s.n_local_warp_tiles = my_macros * 64;
-        const int want = (s.n_local_warp_tiles + (kThreads / 32) - 1) / (kThreads / 32);
+        const int want = (s.n_local_warp_tiles + (c->threads / 32) - 1) / (c->threads / 32);
         s.grid = std::max(1, std::min(dev_sms * bps, want));   // persistent CTAs: a multiple of the SM count
         CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&s.ev_start));
@@ -628,8 +805,8 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         CU(cudaMalloc(&s.d_prims, std::max<size_t>(prim_bytes, 80)));
         CU(cudaMemcpy(s.d_prims, c->tree.prims.data(), prim_bytes, cudaMemcpyHostToDevice));
         CU(cudaMalloc(&s.d_tan, sizeof(float)));
-        CU(cudaMalloc(&s.d_counter, sizeof(unsigned long long)));
-        CU(cudaMemset(s.d_counter, 0, sizeof(unsigned long long)));
+        CU(cudaMalloc(&s.d_counter, sizeof(unsigned int)));
+        CU(cudaMemset(s.d_counter, 0, sizeof(unsigned int)));
         if (i == 0) {
             CU(cudaMalloc(&c->d_fb, (size_t)width * height * 4));
             CU(cudaMemset(c->d_fb, 0, (size_t)width * height * 4));
@@ -649,7 +826,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
                   "{\"threads_per_cta\": %d, \"ctas\": %d, \"sms\": %d, \"smem_bytes_per_cta\": %zu, \"tree_bytes\": %zu, "
                   "\"tree_in_smem\": %s, \"stack_levels\": %d, \"n_nodes\": %zu, \"n_prims\": %zu, \"shards\": %d, "
                   "\"macro_tiles\": %d, \"optimize\": %d}",
-                  kThreads, c->shards[0].grid, sms, c->smem_bytes, tree_bytes, c->tree_in_smem ? "true" : "false",
+                  c->threads, c->shards[0].grid, sms, c->smem_bytes, tree_bytes, c->tree_in_smem ? "true" : "false",
                   c->stack_levels, c->tree.nodes.size(), c->tree.prims.size(), shard_count, total_macros, scene->scene.optimize);
     c->info = buf;
     *out = c;
@@ -840,6 +1017,7 @@ void csg_free_context(csg_context* c)
     cudaFree(c->d_aov_hit);
     cudaFree(c->d_aov_prim);
     cudaFree(c->d_aov_t);
+    cudaFree(c->d_aov_iters);
     cudaGetLastError();
     delete c;
 }
@@ -960,6 +1138,19 @@ int csg_render_f32(csg_context* ctx, const csg_camera* cam, const csg_light* lig
     return sync_frame(ctx);
 }
 
+int csg_render_stats(csg_context* ctx, const csg_camera* cam, int32_t* iterations)
+{
+    if (!ctx || !cam || !iterations) return fail(CSG_ERR_ARG, "null argument");
+    if (ctx->shards.size() != 1) return fail(CSG_ERR_ARG, "csg_render_stats needs a single-GPU context");
+    CU(cudaSetDevice(ctx->shards[0].device));
+    const size_t n = (size_t)ctx->width * ctx->height;
+    if (!ctx->d_aov_iters) CU(cudaMalloc(&ctx->d_aov_iters, n * 4));
+    int rc = csg_render_aov(ctx, cam, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpy(iterations, ctx->d_aov_iters, n * 4, cudaMemcpyDeviceToHost));
+    return CSG_OK;
+}
+
 int csg_render_aov(csg_context* ctx, const csg_camera* cam, uint8_t* hit, int32_t* prim_id, float* t)
 {
     if (!ctx || !cam) return fail(CSG_ERR_ARG, "null argument");
@@ -979,6 +1170,16 @@ int csg_render_aov(csg_context* ctx, const csg_camera* cam, uint8_t* hit, int32_
     if (hit) CU(cudaMemcpy(hit, ctx->d_aov_hit, n, cudaMemcpyDeviceToHost));
     if (prim_id) CU(cudaMemcpy(prim_id, ctx->d_aov_prim, n * 4, cudaMemcpyDeviceToHost));
     if (t) CU(cudaMemcpy(t, ctx->d_aov_t, n * 4, cudaMemcpyDeviceToHost));
+    return CSG_OK;
+}
+
+int csg_set_supersampling(csg_context* ctx, int samples_per_axis)
+{
+    if (!ctx) return fail(CSG_ERR_ARG, "null context");
+    if (samples_per_axis < 1 || samples_per_axis > 16) return fail(CSG_ERR_ARG, "samples_per_axis must be in [1, 16]");
+    if ((long long)ctx->width * samples_per_axis > 16777216ll || (long long)ctx->height * samples_per_axis > 16777216ll)
+        return fail(CSG_ERR_ARG, "virtual grid too large for exact float pixel coordinates");
+    ctx->ss = samples_per_axis;
     return CSG_OK;
 }
 

@@ -499,6 +499,23 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
     };
     emit(root, -1, 0);
     out.root_is_leaf = b.w[root].prim != -1;
+    {
+        Box rb = b.w[root].box;
+        if (out.root_is_leaf && b.w[root].type == kCylinder) {   // true bounds: sphere of radius sqrt(r^2 + (h/2)^2) about the centre
+            const RefPrim& p = s.prims[b.w[root].prim];
+            const float rad = std::sqrt(p.p[0] * p.p[0] + 0.25f * p.p[1] * p.p[1]) * 1.001f;
+            const float c[3] = {p.x, p.y, p.z};
+            for (int k = 0; k < 3; ++k) { rb.mn[k] = c[k] - rad; rb.mx[k] = c[k] + rad; }
+        }
+        bool ok = true;
+        for (int k = 0; k < 3; ++k) {
+            ok = ok && std::isfinite(rb.mn[k]) && std::isfinite(rb.mx[k]) && rb.mn[k] <= rb.mx[k];
+            const float pad = 1e-4f * (std::fabs(rb.mn[k]) + std::fabs(rb.mx[k])) + 1e-6f;
+            out.root_box[k] = rb.mn[k] - pad;
+            out.root_box[3 + k] = rb.mx[k] + pad;
+        }
+        out.root_box_valid = ok;
+    }
 }
 
 }  // namespace csgb

@@ -55,6 +55,10 @@ struct FlatTree {
     std::vector<PrimRec> prims;
     int depth = 0;        // operator levels on the longest path = stack slots the kernel needs
     bool root_is_leaf = false;
+    // Box outside which every ray is a Miss (the root's culling box; for a root primitive its true bounds, since a root leaf
+    // is intersected without the reference's gating box, Q7).  Used for the per-frame screen-space bound.
+    bool root_box_valid = false;
+    float root_box[6] = {0, 0, 0, 0, 0, 0};
 };
 
 struct Scene {

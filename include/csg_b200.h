@@ -103,6 +103,15 @@ int csg_render_f32(csg_context* ctx, const csg_camera* cam, const csg_light* lig
  * (RayCasting/Utils/Ray.cuh:24-34).  Host pointers; any may be NULL. */
 int csg_render_aov(csg_context* ctx, const csg_camera* cam, uint8_t* hit, int32_t* prim_id, float* t);
 
+/* Supersampling (BASELINE.json configs[4]: 16 rays/pixel = 4 per axis).  Sub-sample (sx,sy) of pixel (x,y) is the reference's
+ * ray generation at virtual pixel (x*k+sx, y*k+sy) of a (width*k) x (height*k) frame; the k*k linear colours are box-filtered.
+ * I.e. the result equals the reference kernel run at k times the resolution and averaged k x k.  Default 1. */
+int csg_set_supersampling(csg_context* ctx, int samples_per_axis);
+
+/* Work statistics: traversal loop iterations per pixel of THIS implementation (the reference algorithm's counts come from
+ * the instrumented oracle).  Host pointer, width*height int32. */
+int csg_render_stats(csg_context* ctx, const csg_camera* cam, int32_t* iterations);
+
 /* ---- asynchronous / device-resident form (benchmarks, interop viewers, multi-process gather) */
 /* Enqueues one frame on the context's stream(s); rgba8_dev NULL = the context's own framebuffer
  * (or the gather target).  Returns without waiting. */

@@ -171,6 +171,30 @@ def test_odd_sizes_and_partial_tiles(csg, oracle):
         ctx.close()
 
 
+@pytest.mark.parametrize("k", [2, 4])
+def test_supersampling_is_reference_at_k_times_resolution_box_filtered(k, csg, oracle):
+    """BASELINE.json configs[4]: 16 rays/pixel (k = 4) == the reference ray generation on the k-times finer grid,
+    k x k linear colours averaged."""
+    w, h = 96, 54
+    for scene_id in ["inline:nested", "inline:deep_left_chain", "inline:coincident_cubes"]:
+        txt = scenes.text_of(scene_id)
+        v = orbit_view(w, h, 11, radius=5.0)
+        sc = csg.Scene.parse(txt)
+        ctx = sc.upload(w, h).set_supersampling(k)
+        cam, light = cam_of(csg, v), light_of(csg, v)
+        got8 = ctx.render(cam, light).reshape(h, w, 4)
+        got32 = ctx.render_f32(cam, light).reshape(h, w, 4)
+        fine = orbit_view(w * k, h * k, 11, radius=5.0)
+        ref = oracle.render(txt, fine, tan_half_fov=ctx.device_tan_half_fov(cam.c.fov))
+        avg = ref.rgba.reshape(h, k, w, k, 4).astype(np.float64).mean(axis=(1, 3))
+        assert np.abs(got32 - avg).max() < 2e-6 * 16
+        want8 = (np.clip(avg, 0, 1) * 255 + 0.5).astype(np.uint8)
+        assert np.abs(got8.astype(int) - want8.astype(int)).max() <= 1
+        with pytest.raises(csg.CsgError):
+            ctx.render_aov(cam)          # AOVs are per primary ray
+        ctx.close()
+
+
 def test_multi_gpu_in_process_equals_single_gpu(csg):
     import torch
     if torch.cuda.device_count() < 2:
