@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -107,23 +108,37 @@ __device__ __forceinline__ uint32_t to_u8(float c)
 //   x = saved tmin (F_FIRST_*) or saved hit t (F_LOAD_*),  y = saved hit meta | return state,
 //   z = F_FIRST_*: lower bound of the pending sibling's hits (prune test),  w = byte offset of the operator's record.
 //
-// Two additions over the reference's traversal order, both result-preserving (DESIGN.md §"Culling contract"):
+// Additions over the reference's traversal order, all result-preserving (DESIGN.md §"Culling contract"):
 //   * a Union evaluates the child whose box the ray enters first; Difference/Intersection keep left-first;
 //   * when the first child returns a hit at t and the pending sibling's box starts beyond t, the sibling cannot change
 //     the outcome (Union: every cell with a farther Enter or a Miss on the other side returns this hit; Difference: same
-//     for the right operand) and is skipped.
+//     for the right operand) and is skipped;
+//   * nearest-Enter search (ST_SEARCH): a "pure" subtree (Unions over spheres/cubes only) whose box lies ahead of tmin is
+//     evaluated as a closest-hit BVH search with a shrinking limit instead of the frame machine.  With every leaf result an
+//     Enter or a Miss, each Union of the subtree returns the nearer Enter (EE lt/gt, EM, ME cells), i.e. the subtree returns
+//     its globally nearest Enter; the search aborts — and the subtree is re-evaluated by the frame machine — as soon as a
+//     leaf reports an Exit or two leaves tie for the nearest hit (the only inputs on which the cells differ from "min").
+//     The limit starts at the hit already known on the other side of the parent when every farther Enter (or a Miss) of
+//     this side gives the same parent outcome (Union either side, Difference right side): such results are equivalent, so
+//     subtrees beyond the limit need not be looked at.
+constexpr uint32_t kSearchMark = 0xfffffffeu;
+
 template <bool COUNT>
 __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, const float4* __restrict__ prims,
                                         const uint32_t* __restrict__ table, uint4* __restrict__ stack,
-                                        const int stack_stride, const Ray& r, const bool root_is_leaf, int& iters)
+                                        const int stack_stride, const Ray& r, const bool root_is_leaf, const bool root_pure, const bool root_gated, int& iters)
 {
-    enum { ST_ENTER = 0, ST_LOOPL = 1, ST_LOOPR = 2, ST_COMPUTE = 3, ST_RETURN = 4, ST_DONE = 5 };
-    Hit L = make_miss(), R = make_miss();
+    enum { ST_ENTER = 0, ST_SEARCH = 1, ST_LOOPL = 2, ST_LOOPR = 3, ST_COMPUTE = 4, ST_RETURN = 5, ST_DONE = 6 };
+    Hit L = make_miss(), R = make_miss();      // ST_SEARCH: L = nearest Enter so far, R.t = limit
     float tmin = 0.0f;                        // :466
-    if (root_is_leaf) {                        // GoTo's leaf branch on the virtual root: no box test (:582-594, Q7)
+    if (root_is_leaf) {
+        // The scene's root is a primitive: GoTo's leaf branch on the virtual root, no box test (:582-594, Q7).
+        // A pruned tile tree that collapsed to one primitive (root_gated): the primitive is still reached through its
+        // operators in the reference, so a cylinder keeps its gating box (Q6).
         bool go;
         float tn;
-        eval_child(tree, prims, 0u, r, tmin, false, L, go, tn);
+        uint32_t cm;
+        eval_child(tree, prims, 0u, r, tmin, root_gated, L, go, tn, cm);
         return L;
     }
     uint32_t n = 0u;                           // byte offset of the current operator's record
@@ -131,43 +146,102 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     *sp = make_uint4(0u, 0u, 0u, 0xffffffffu); // sentinel frame: popping it ends the traversal (no base pointer to keep)
     sp += stack_stride;
     int st = ST_ENTER;
+    if (root_pure) {                           // the whole scene is one pure subtree
+        *sp = make_uint4(0u, 0u, 0u, kSearchMark);
+        sp += stack_stride;
+        R.t = INFINITY;
+        st = ST_SEARCH;
+    }
     while (st != ST_DONE) {
-        if (COUNT) ++iters;
+        if (COUNT) iters += (st == ST_SEARCH) ? (1 << 20) : (st == ST_ENTER) ? (1 << 10) : 1;   // packed: search visits | frame-machine visits | other iterations
         if (st <= ST_LOOPR) {
             const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
             const uint32_t op = meta & 7u;
             const uint32_t cl = n + 32u, cr = (meta >> 8) << 5;
-            bool goL = false, goR = false;
-            float tnL = -INFINITY, tnR = -INFINITY;
-            if (st != ST_LOOPR) eval_child(tree, prims, cl, r, tmin, st == ST_ENTER, L, goL, tnL);
-            if (st == ST_ENTER && op != 0u && !goL && is_miss(L)) {
+            Hit a = make_miss(), b = make_miss();
+            bool goA = false, goB = false;
+            float tnA = -INFINITY, tnB = -INFINITY;
+            uint32_t mA = 0u, mB = 0u;
+            if (st != ST_LOOPR) eval_child(tree, prims, cl, r, tmin, st <= ST_SEARCH, a, goA, tnA, mA);
+            if (st == ST_ENTER && op != 0u && !goA && is_miss(a)) {
                 // left operand of a Difference/Intersection already missed: the node's result is Miss whatever the right
                 // operand does (all M* cells of both tables, :670-677) — skip the right subtree (Q8)
-                R = L;
+                L = a; R = a;
                 st = ST_RETURN;
             } else {
-                if (st != ST_LOOPL) eval_child(tree, prims, cr, r, tmin, st == ST_ENTER, R, goR, tnR);
-                if (st != ST_ENTER) {
-                    st = ST_COMPUTE;
+                if (st != ST_LOOPL) eval_child(tree, prims, cr, r, tmin, st <= ST_SEARCH, b, goB, tnB, mB);
+                if (st == ST_LOOPL) { L = a; st = ST_COMPUTE; }
+                else if (st == ST_LOOPR) { R = b; st = ST_COMPUTE; }
+                else if (st == ST_SEARCH) {
+                    // leaf results are candidates; an Exit or a tie for the nearest hit ends the search
+                    bool abort = false;
+                    float lim = R.t;
+                    if (!is_miss(a)) {
+                        if ((a.m & H_CLS) == H_EXIT) abort = true;
+                        else if (a.t < lim) { L = a; lim = a.t; }
+                        else if (a.t == lim) { if (is_miss(L)) L = a; else abort = true; }
+                    }
+                    if (!is_miss(b)) {
+                        if ((b.m & H_CLS) == H_EXIT) abort = true;
+                        else if (b.t < lim) { L = b; lim = b.t; }
+                        else if (b.t == lim) { if (is_miss(L)) L = b; else abort = true; }
+                    }
+                    R.t = lim;
+                    if (abort) {                 // back to the subtree's root, this time through the frame machine
+                        uint4 f;
+                        do { sp -= stack_stride; f = *sp; } while (f.w != kSearchMark);
+                        n = f.z; st = ST_ENTER;
+                    } else {
+                        goA = goA && !(tnA > lim);
+                        goB = goB && !(tnB > lim);
+                        if (goA && goB) {
+                            const bool right_first = tnB < tnA;
+                            *sp = make_uint4(__float_as_uint(right_first ? tnA : tnB), 0u, 0u, right_first ? cl : cr);
+                            sp += stack_stride; n = right_first ? cr : cl;
+                        } else if (goA) { n = cl; }
+                        else if (goB) { n = cr; }
+                        else {
+                            for (;;) {
+                                sp -= stack_stride;
+                                const uint4 f = *sp;
+                                if (f.w == kSearchMark) { R = L; st = ST_RETURN; break; }   // the subtree's result: nearest Enter or Miss
+                                if (!(__uint_as_float(f.x) > lim)) { n = f.w; break; }
+                            }
+                        }
+                    }
                 } else {
+                    L = a; R = b;
                     // sibling pruning against a leaf hit that is already known
                     if (op != 2u) {
-                        if (goR && !goL && !is_miss(L) && tnR > L.t) { goR = false; R = make_miss(); }
-                        if (op == 0u && goL && !goR && !is_miss(R) && tnL > R.t) { goL = false; L = make_miss(); }
+                        if (goB && !goA && !is_miss(L) && tnB > L.t) goB = false;
+                        if (op == 0u && goA && !goB && !is_miss(R) && tnA > R.t) goA = false;
                     }
-                    if (!goL && !goR) {
+                    if (!goA && !goB) {
                         st = ST_COMPUTE;                                                   // :578
-                    } else if (!goL) {                                                     // :556-561
-                        *sp = make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n);
-                        sp += stack_stride; n = cr;
-                    } else if (!goR) {                                                     // :562-567
-                        *sp = make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n);
-                        sp += stack_stride; n = cl;
-                    } else {                                                               // :568-574
-                        const bool right_first = (op == 0u) && (tnR < tnL);
-                        const float bound = (op == 2u) ? -INFINITY : (right_first ? tnL : tnR);
-                        *sp = make_uint4(__float_as_uint(tmin), right_first ? F_FIRST_RGH : F_FIRST_LFT, __float_as_uint(bound), n);
-                        sp += stack_stride; n = right_first ? cr : cl;
+                    } else {
+                        uint32_t first, fm;   // subtree to descend into now, and its meta word
+                        float ftn, lim = INFINITY;
+                        if (!goA) {                                                        // :556-561
+                            *sp = make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n);
+                            first = cr; fm = mB; ftn = tnB;
+                            if (op != 2u && !is_miss(L)) lim = L.t;
+                        } else if (!goB) {                                                 // :562-567
+                            *sp = make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n);
+                            first = cl; fm = mA; ftn = tnA;
+                            if (op == 0u && !is_miss(R)) lim = R.t;
+                        } else {                                                           // :568-574
+                            const bool right_first = (op == 0u) && (tnB < tnA);
+                            const uint32_t pend_pure = ((right_first ? mA : mB) >> 6) & 1u;
+                            *sp = make_uint4(__float_as_uint(tmin), (right_first ? F_FIRST_RGH : F_FIRST_LFT) | pend_pure,
+                                             __float_as_uint(right_first ? tnA : tnB), n);
+                            first = right_first ? cr : cl; fm = right_first ? mB : mA; ftn = right_first ? tnB : tnA;
+                        }
+                        sp += stack_stride; n = first;
+                        if ((fm & kMetaPure) && ftn > tmin) {   // pure subtree ahead of tmin: nearest-Enter search
+                            *sp = make_uint4(0u, 0u, first, kSearchMark);
+                            sp += stack_stride;
+                            L = make_miss(); R.t = lim; st = ST_SEARCH;
+                        }
                     }
                 }
             }
@@ -205,16 +279,28 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                 } else {                        // SaveLft :476-481: restore tmin, keep the first result, evaluate the sibling
                     tmin = __uint_as_float(f.x);
                     const uint32_t pm = *reinterpret_cast<const uint32_t*>(tree + n + 28);
+                    const uint32_t pop = pm & 7u;
                     const bool miss = is_miss(L);
-                    if (miss ? ((pm & 7u) != 0u) : (__uint_as_float(f.z) > L.t)) {
+                    const float ptn = __uint_as_float(f.z);     // entry distance of the pending sibling's box (-inf: not a bound)
+                    if (miss ? (pop != 0u) : (pop != 2u && ptn > L.t)) {
                         // Difference/Intersection whose left operand missed -> Miss; or the sibling lies beyond this hit -> this hit.
                         // Either way the node's result is what L == R already hold; stay in ST_RETURN.
-                    } else if (ret == F_FIRST_LFT) {
-                        *sp = make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n);
-                        sp += stack_stride; n = (pm >> 8) << 5; st = ST_ENTER;
                     } else {
-                        *sp = make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n);
-                        sp += stack_stride; n = n + 32u; st = ST_ENTER;
+                        uint32_t sib;
+                        if (ret == F_FIRST_LFT) {
+                            *sp = make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n);
+                            sib = (pm >> 8) << 5;
+                        } else {
+                            *sp = make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n);
+                            sib = n + 32u;
+                        }
+                        sp += stack_stride; n = sib; st = ST_ENTER;
+                        if ((f.y & 1u) && ptn > tmin) {
+                            const float lim = (pop != 2u && !miss) ? L.t : INFINITY;
+                            *sp = make_uint4(0u, 0u, sib, kSearchMark);
+                            sp += stack_stride;
+                            L = make_miss(); R.t = lim; st = ST_SEARCH;
+                        }
                     }
                 }
             }
@@ -223,38 +309,20 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     return L;                                   // :511
 }
 
-template <int MODE, bool TREE_SMEM, int kThreads>
+template <int MODE, int kThreads>
 __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_kernel(const __grid_constant__ FrameParams p)
 {
-    // shared memory: [outcome table 128 B][stack: (levels+1) x kThreads x 16 B][staged tree 32 B/node]
+    // shared memory: [outcome table 128 B][stack: (levels+2) x kThreads x 16 B].  The tree is read through L1: every
+    // 64x32-pixel macro tile has its own pruned, origin-relative copy (csg_prune_kernel), a few hundred bytes to a few KB.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_table = reinterpret_cast<uint32_t*>(smem_raw);
     uint4* s_stack = reinterpret_cast<uint4*>(smem_raw + 128);
-    uint4* s_nodes = s_stack + (size_t)(p.stack_levels + 1) * kThreads;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const float ox = p.cam_pos[0], oy = p.cam_pos[1], oz = p.cam_pos[2];
 
     if (tid < 27) s_table[tid] = kOutcomeTable[tid];
-    if (TREE_SMEM) {
-        // Stage the tree once per CTA, origin-relative: every primary ray shares the camera position, so the
-        // (bound - origin) / (origin - centre) subtractions of isBVHNodeHit :724-729, cubeHit :389-394 and
-        // sphereHit :139-143 are done here once per node instead of once per ray (same single FADD, same bits).
-        for (int i = tid; i < p.n_nodes; i += kThreads) {
-            uint4 ua = p.nodes[2 * i], ub = p.nodes[2 * i + 1];
-            float4 a = as_float4(ua), b = as_float4(ub);
-            if ((ub.w & 7u) == 3u) {
-                a.x = __fsub_rn(ox, a.x); a.y = __fsub_rn(oy, a.y); a.z = __fsub_rn(oz, a.z);
-            } else {
-                a.x = __fsub_rn(a.x, ox); a.y = __fsub_rn(a.y, oy); a.z = __fsub_rn(a.z, oz);
-                a.w = __fsub_rn(a.w, ox); b.x = __fsub_rn(b.x, oy); b.y = __fsub_rn(b.y, oz);
-            }
-            s_nodes[2 * i] = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
-            s_nodes[2 * i + 1] = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), ub.z, ub.w);
-        }
-    }
     __syncthreads();
-    const unsigned char* tree = reinterpret_cast<const unsigned char*>(TREE_SMEM ? s_nodes : p.nodes);   // !TREE_SMEM: staged by csg_stage_kernel
     uint4* my_stack = s_stack + tid;
 
     // per-frame constants of ray generation, RaycastKernel :11-16
@@ -333,9 +401,14 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         Ray r;
         r.ox = ox; r.oy = oy; r.oz = oz;
         float accx = 0.f, accy = 0.f, accz = 0.f;
+        // this macro tile's pruned tree (csg_prune_kernel): only the primitives its rays can reach, operators whose other
+        // operand cannot be reached collapsed away.  n_nodes == 0: every ray of the tile is a Miss.
+        const int slot = (my * p.macro_x + mx) / p.shard_count;
+        const uint4 td = p.desc ? __ldg(reinterpret_cast<const uint4*>(p.desc) + slot) : make_uint4(0u, (uint32_t)p.n_nodes, p.full_flags, 0u);
+        const unsigned char* tree = reinterpret_cast<const unsigned char*>(p.pool + 2 * (size_t)td.x);
         // whole warp tile outside the screen-space bound of the root box: every ray is a Miss (:109 background colour)
         const int tx0 = x - (lane & 7), ty0 = y - (lane >> 3);
-        const bool tile_empty = tx0 > p.rect_x1 || tx0 + (kWarpTileW - 1) < p.rect_x0 || ty0 > p.rect_y1 || ty0 + (kWarpTileH - 1) < p.rect_y0;
+        const bool tile_empty = td.y == 0u || tx0 > p.rect_x1 || tx0 + (kWarpTileW - 1) < p.rect_x0 || ty0 > p.rect_y1 || ty0 + (kWarpTileH - 1) < p.rect_y0;
         if (tile_empty) {
             const float w = (float)(ss * ss);
             accx = 0.08f * w; accy = 0.08f * w; accz = 0.11f * w;
@@ -358,7 +431,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                 }
                 r.dx = cx; r.dy = cy; r.dz = cz;
                 r.ix = __frcp_rn(cx); r.iy = __frcp_rn(cy); r.iz = __frcp_rn(cz);
-                res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, kThreads, r, p.root_is_leaf != 0, iters);
+                res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, kThreads, r, (td.z & kTileRootLeaf) != 0u, (td.z & kTileRootPure) != 0u,
+                                                p.root_is_leaf == 0, iters);
                 if (MODE != OUT_AOV) {
                     const float4 c = shade_pixel(res, r, p.prims, p);
                     accx += c.x; accy += c.y; accz += c.z;
@@ -404,12 +478,17 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
 // the frame kernel: tanf's large-argument path needs a local-memory scratch array).
 __global__ void csg_tan_kernel(float fov, float* out) { *out = tanf(__fmul_rn(fov, 0.5f)); }
 
-// Pre-stages an origin-relative copy of the tree in global memory for trees that do not fit in shared memory.
-__global__ void csg_stage_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n_nodes, float ox, float oy, float oz)
+// ---- per-tile tree pruning ---------------------------------------------------------------------------------------------
+// One CTA per traced macro tile builds the tile's own tree: a primitive whose culling box lies outside the tile's frustum
+// (the 64x32 pixels plus a margin of one pixel) is a Miss for every ray of the tile, whatever tmin; an operator with such an
+// operand behaves exactly like its other operand (Union: [x][M] -> RetL, [M][x] -> RetR; Difference: [x][M] -> RetL) or is a
+// Miss itself (Difference without its left operand, Intersection without either: all M* cells, RaycastingKernels.cu:666-677),
+// without ever looping — so dropping those primitives and collapsing those operators changes no result.  The surviving
+// nodes are written in preorder, origin-relative (the subtractions of isBVHNodeHit :724-729, cubeHit :389-394 and
+// sphereHit :139-143 are done here once per node and tile instead of once per ray: same single FADD, same bits), with
+// operator boxes recomputed over what is left.
+__device__ __forceinline__ void stage_record(const uint4 ua, const uint4 ub, float ox, float oy, float oz, uint4& oa, uint4& ob)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    uint4 ua = src[2 * i], ub = src[2 * i + 1];
     float4 a = as_float4(ua), b = as_float4(ub);
     if ((ub.w & 7u) == 3u) {
         a.x = __fsub_rn(ox, a.x); a.y = __fsub_rn(oy, a.y); a.z = __fsub_rn(oz, a.z);
@@ -417,8 +496,228 @@ __global__ void csg_stage_kernel(const uint4* __restrict__ src, uint4* __restric
         a.x = __fsub_rn(a.x, ox); a.y = __fsub_rn(a.y, oy); a.z = __fsub_rn(a.z, oz);
         a.w = __fsub_rn(a.w, ox); b.x = __fsub_rn(b.x, oy); b.y = __fsub_rn(b.y, oz);
     }
-    dst[2 * i] = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
-    dst[2 * i + 1] = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), ub.z, ub.w);
+    oa = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+    ob = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), ub.z, ub.w);
+}
+
+// culling box of a node relative to the origin: operators, cubes, cylinders carry it; spheres: centre +- r, padded like the host does
+__device__ __forceinline__ void rel_cull_box(const uint4 ua, const uint4 ub, float ox, float oy, float oz, float lo[3], float hi[3])
+{
+    const float4 a = as_float4(ua), b = as_float4(ub);
+    if ((ub.w & 7u) == 3u) {
+        const float r = fabsf(a.w);
+        const float c[3] = {a.x, a.y, a.z}, o[3] = {ox, oy, oz};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float pad = r * 1e-4f + fabsf(c[k]) * 4e-7f + 1e-30f;
+            lo[k] = (c[k] - r - pad) - o[k];
+            hi[k] = (c[k] + r + pad) - o[k];
+        }
+    } else {
+        lo[0] = a.x - ox; lo[1] = a.y - oy; lo[2] = a.z - oz;
+        hi[0] = a.w - ox; hi[1] = b.x - oy; hi[2] = b.y - oz;
+    }
+}
+
+constexpr int kPruneThreads = 256;
+
+__global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_constant__ PruneParams q)
+{
+    constexpr int T = kPruneThreads;
+    extern __shared__ __align__(16) unsigned char psm[];
+    const int N = q.n_nodes, S = q.slot_nodes;
+    uint4* orec = reinterpret_cast<uint4*>(psm);            // S x 2: the surviving records
+    float* obox = reinterpret_cast<float*>(orec + 2 * S);   // S x 6: culling box of each surviving node (origin-relative)
+    int* rep = reinterpret_cast<int*>(obox + 6 * S);        // N: representative of each node's subtree: itself, a descendant, or -1
+    int* idx = rep + N;                                     // N: reachability flag, then (new index << 1) | flag
+    uint8_t* oflg = reinterpret_cast<uint8_t*>(idx + N);    // S: bit0 pure, bit1 bounded
+    __shared__ int s_part[T];
+    __shared__ int s_total;
+    const int tid = threadIdx.x;
+    const float ox = q.cam_pos[0], oy = q.cam_pos[1], oz = q.cam_pos[2];
+
+    if ((int)blockIdx.x >= q.n_tiles) {
+        // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
+        const int nb = (int)gridDim.x - q.n_tiles;
+        for (int i = ((int)blockIdx.x - q.n_tiles) * T + tid; i < N; i += nb * T) {
+            uint4 oa, ob;
+            stage_record(q.nodes[2 * i], q.nodes[2 * i + 1], ox, oy, oz, oa, ob);
+            q.pool[2 * i] = oa;
+            q.pool[2 * i + 1] = ob;
+        }
+        return;
+    }
+
+    // ---- the tile and its frustum
+    const int j = (int)blockIdx.x * q.shard_count + q.shard_rank;
+    const int jy = q.rm_magic ? (int)__umulhi((unsigned int)j, q.rm_magic) : j / q.rm_w;
+    const int mx = q.rm_x0 + (j - jy * q.rm_w), my = q.rm_y0 + jy;
+    const int slot = (my * q.macro_x + mx) / q.shard_count;
+    TileDesc* desc = q.desc + slot;
+    float pn[5][3];   // inward plane normals: 4 sides through the origin + the camera plane
+    {
+        const float x0 = (float)(mx * kMacroW - 1) * q.ss, x1 = (float)(min(mx * kMacroW + kMacroW, q.width) + 1) * q.ss;
+        const float y0 = (float)(my * kMacroH - 1) * q.ss, y1 = (float)(min(my * kMacroH + kMacroH, q.height) + 1) * q.ss;
+        float d[4][3];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {   // corner rays (RaycastKernel :11-25, un-normalised), counter-clockwise: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
+            const float fx = (c == 1 || c == 2) ? x1 : x0, fy = (c >= 2) ? y1 : y0;
+            const float u = fx / q.wm1, v = fy / q.hm1;     // pixel edges: (x - 0.5 + 0.5)
+            const float nx = q.aspect * (2.0f * u - 1.0f) * q.tan_half_fov, ny = (1.0f - 2.0f * v) * q.tan_half_fov;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) d[c][k] = q.forward[k] + q.right[k] * nx + q.up[k] * ny;
+        }
+        float dc[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dc[k] = d[0][k] + d[1][k] + d[2][k] + d[3][k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float* a = d[c];
+            const float* b = d[(c + 1) & 3];
+            float n0 = a[1] * b[2] - a[2] * b[1], n1 = a[2] * b[0] - a[0] * b[2], n2 = a[0] * b[1] - a[1] * b[0];
+            if (n0 * dc[0] + n1 * dc[1] + n2 * dc[2] < 0.0f) { n0 = -n0; n1 = -n1; n2 = -n2; }
+            pn[c][0] = n0; pn[c][1] = n1; pn[c][2] = n2;
+        }
+        pn[4][0] = q.forward[0]; pn[4][1] = q.forward[1]; pn[4][2] = q.forward[2];
+    }
+
+    // ---- which nodes can any ray of the tile reach
+    for (int i = tid; i < N; i += T) {
+        float lo[3], hi[3];
+        rel_cull_box(q.nodes[2 * i], q.nodes[2 * i + 1], ox, oy, oz, lo, hi);
+        bool outside = false;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
+                            fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
+            outside = outside || (m < 0.0f);
+        }
+        rep[i] = outside ? -1 : i;
+        idx[i] = 0;
+    }
+    __syncthreads();
+    // operators, deepest level first: kept (both operands matter), collapsed to one operand, or gone
+    for (int lv = q.n_levels - 1; lv >= 0; --lv) {
+        for (int k = q.level_start[lv] + tid; k < q.level_start[lv + 1]; k += T) {
+            const int n = q.level_nodes[k];
+            if (rep[n] < 0) continue;
+            const uint32_t meta = q.nodes[2 * n + 1].w;
+            const uint32_t kind = meta & 7u;
+            if (kind >= 3u) continue;
+            const int a = rep[n + 1], b = rep[meta >> 8];
+            rep[n] = kind == 0u ? (a < 0 ? b : (b < 0 ? a : n)) : kind == 1u ? (a < 0 ? -1 : (b < 0 ? a : n)) : ((a < 0 || b < 0) ? -1 : n);
+        }
+        __syncthreads();
+    }
+    const int r0 = rep[0];
+    if (r0 < 0) {
+        if (tid == 0) *desc = TileDesc{0u, 0u, 0u, 0u};
+        return;
+    }
+    if (tid == 0) idx[r0] = 1;
+    __syncthreads();
+    for (int lv = 0; lv < q.n_levels; ++lv) {   // survivors reachable from the root's representative
+        for (int k = q.level_start[lv] + tid; k < q.level_start[lv + 1]; k += T) {
+            const int n = q.level_nodes[k];
+            if (!idx[n]) continue;
+            const uint32_t meta = q.nodes[2 * n + 1].w;
+            if ((meta & 7u) >= 3u) continue;
+            idx[rep[n + 1]] = 1;
+            idx[rep[meta >> 8]] = 1;
+        }
+        __syncthreads();
+    }
+    // preorder positions of the survivors: exclusive scan of the flags
+    const int chunk = (N + T - 1) / T;
+    const int c0 = min(tid * chunk, N), c1 = min(c0 + chunk, N);
+    int sum = 0;
+    for (int i = c0; i < c1; ++i) sum += idx[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid < 32) {
+        int acc = 0;
+        for (int base = 0; base < T; base += 32) {
+            const int v = s_part[base + tid];
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= o) inc += t;
+            }
+            s_part[base + tid] = acc + inc - v;
+            acc += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (tid == 0) s_total = acc;
+    }
+    __syncthreads();
+    {
+        int run = s_part[tid];
+        for (int i = c0; i < c1; ++i) {
+            const int f = idx[i];
+            idx[i] = (run << 1) | f;
+            run += f;
+        }
+    }
+    __syncthreads();
+    const int kept = s_total;
+    if (kept > S) {   // does not fit a slot: this tile reads the staged copy of the whole tree
+        if (tid == 0) *desc = TileDesc{0u, (uint32_t)N, q.full_flags, 0u};
+        return;
+    }
+    for (int i = tid; i < N; i += T) {
+        const int e = idx[i];
+        if (!(e & 1)) continue;
+        const int jn = e >> 1;
+        const uint4 ua = q.nodes[2 * i], ub = q.nodes[2 * i + 1];
+        uint4 oa, ob;
+        stage_record(ua, ub, ox, oy, oz, oa, ob);
+        const uint32_t kind = ub.w & 7u;
+        if (kind < 3u) ob.w = kind | ((uint32_t)(idx[rep[ub.w >> 8]] >> 1) << 8);   // new right child; flags and box follow below
+        orec[2 * jn] = oa;
+        orec[2 * jn + 1] = ob;
+        float lo[3], hi[3];
+        rel_cull_box(ua, ub, ox, oy, oz, lo, hi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { obox[6 * jn + k] = lo[k]; obox[6 * jn + 3 + k] = hi[k]; }
+        oflg[jn] = (uint8_t)(((kind == 3u || kind == 5u) ? 1 : 0) | ((kind != 4u) ? 2 : 0));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // children follow their parent in preorder: walking backwards sees both operands before the operator
+        for (int i = kept - 1; i >= 0; --i) {
+            uint4 ob = orec[2 * i + 1];
+            const uint32_t kind = ob.w & 7u;
+            if (kind >= 3u) continue;
+            const int l = i + 1, r = (int)(ob.w >> 8);
+            const uint32_t kl = orec[2 * l + 1].w & 7u, kr = orec[2 * r + 1].w & 7u;
+            const float* bl = obox + 6 * l;
+            const float* br = obox + 6 * r;
+            float* bo = obox + 6 * i;
+            if (kind == 0u) {                   // Union: both operands
+                for (int k = 0; k < 3; ++k) { bo[k] = fminf(bl[k], br[k]); bo[3 + k] = fmaxf(bl[3 + k], br[3 + k]); }
+            } else if (kind == 1u) {            // Difference: a subset of the left operand
+                for (int k = 0; k < 6; ++k) bo[k] = bl[k];
+            } else {                            // Intersection: a subset of both; the smaller box
+                float vl = 1.f, vr = 1.f;
+                for (int k = 0; k < 3; ++k) { vl *= fmaxf(bl[3 + k] - bl[k], 0.f); vr *= fmaxf(br[3 + k] - br[k], 0.f); }
+                const float* bs = vl <= vr ? bl : br;
+                for (int k = 0; k < 6; ++k) bo[k] = bs[k];
+            }
+            const uint32_t fl = oflg[l], fr = oflg[r];
+            const uint32_t pure = (kind == 0u) ? (fl & fr & 1u) : 0u, bounded = (fl & fr & 2u) >> 1;
+            oflg[i] = (uint8_t)(pure | (bounded << 1));
+            ob.w |= (kl >= 3u ? kMetaLeftLeaf : 0u) | (kr >= 3u ? kMetaRightLeaf : 0u) | (bounded ? kMetaBounded : 0u) | (pure ? kMetaPure : 0u);
+            orec[2 * i] = make_uint4(__float_as_uint(bo[0]), __float_as_uint(bo[1]), __float_as_uint(bo[2]), __float_as_uint(bo[3]));
+            ob.x = __float_as_uint(bo[4]); ob.y = __float_as_uint(bo[5]);
+            orec[2 * i + 1] = ob;
+        }
+        const uint32_t rk = orec[1].w & 7u;
+        *desc = TileDesc{q.slots_off32 + (uint32_t)slot * (uint32_t)S, (uint32_t)kept,
+                         (rk >= 3u ? kTileRootLeaf : 0u) | ((oflg[0] & 1u) && rk < 3u ? kTileRootPure : 0u), 0u};
+    }
+    __syncthreads();
+    uint4* dst = q.pool + 2 * ((size_t)q.slots_off32 + (size_t)slot * S);
+    for (int i = tid; i < 2 * kept; i += T) dst[i] = orec[i];
 }
 
 // FP32 roofline probe: 8 independent FFMA chains per thread, nothing else.
@@ -463,7 +762,11 @@ struct Shard {  // one GPU's share of the frame
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_done = nullptr;
     uint4* d_nodes = nullptr;
-    uint4* d_staged = nullptr;   // only when the tree does not fit in shared memory
+    uint4* d_pool = nullptr;     // [staged whole tree][one slot of slot_nodes records per macro tile of this shard]
+    TileDesc* d_desc = nullptr;  // per macro tile of this shard
+    int* d_level_start = nullptr;
+    int* d_level_nodes = nullptr;
+    int n_slots = 0;
     float4* d_prims = nullptr;
     unsigned int* d_counter = nullptr;
     unsigned int counter_base = 0;
@@ -482,7 +785,10 @@ struct csg_context {
     int shard_count = 1;
     bool multi_process = false;
     FlatTree tree;
-    bool tree_in_smem = true;
+    bool prune = true;           // per-tile pruned trees (csg_prune_kernel); off for trees too large for its shared memory
+    int slot_nodes = 0;          // records per tile slot
+    size_t prune_smem = 0;
+    uint32_t full_flags = 0;
     size_t smem_bytes = 0;
     int stack_levels = 1;
     int threads = 256;           // CTA shape chosen at upload (one of kShapeThreads)
@@ -505,55 +811,48 @@ struct csg_context {
 
 namespace {
 
-template <int MODE, bool SM, int T>
+template <int MODE, int T>
 int launch_one(csg_context* c, Shard& s, const FrameParams& fp)
 {
-    csg_frame_kernel<MODE, SM, T><<<s.grid, T, c->smem_bytes, s.stream>>>(fp);
+    csg_frame_kernel<MODE, T><<<s.grid, T, c->smem_bytes, s.stream>>>(fp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return CSG_OK;
 }
 
-template <int MODE, bool SM>
-int launch_shape(csg_context* c, Shard& s, const FrameParams& fp)
-{
-    switch (c->threads) {
-        case 768: return launch_one<MODE, SM, 768>(c, s, fp);
-        case 384: return launch_one<MODE, SM, 384>(c, s, fp);
-        default: return launch_one<MODE, SM, 256>(c, s, fp);
-    }
-}
-
 template <int MODE>
 int launch_mode(csg_context* c, Shard& s, const FrameParams& fp)
 {
-    return c->tree_in_smem ? launch_shape<MODE, true>(c, s, fp) : launch_shape<MODE, false>(c, s, fp);
+    switch (c->threads) {
+        case 768: return launch_one<MODE, 768>(c, s, fp);
+        case 384: return launch_one<MODE, 384>(c, s, fp);
+        default: return launch_one<MODE, 256>(c, s, fp);
+    }
 }
 
-template <int MODE, bool SM, int T>
+template <int MODE, int T>
 int configure_one(size_t smem, int* blocks_per_sm)
 {
-    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, SM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, SM, T>, T, smem));
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, T>, T, smem));
     return CSG_OK;
 }
 
-template <bool SM, int T>
+template <int T>
 int configure_modes(size_t smem, int* bps)
 {
     int rc;
-    if ((rc = configure_one<OUT_F32, SM, T>(smem, bps))) return rc;
-    if ((rc = configure_one<OUT_AOV, SM, T>(smem, bps))) return rc;
-    return configure_one<OUT_RGBA8, SM, T>(smem, bps);
+    if ((rc = configure_one<OUT_F32, T>(smem, bps))) return rc;
+    if ((rc = configure_one<OUT_AOV, T>(smem, bps))) return rc;
+    return configure_one<OUT_RGBA8, T>(smem, bps);
 }
 
-template <bool SM>
 int configure_shape(int threads, size_t smem, int* bps)
 {
     switch (threads) {
-        case 768: return configure_modes<SM, 768>(smem, bps);
-        case 384: return configure_modes<SM, 384>(smem, bps);
-        default: return configure_modes<SM, 256>(smem, bps);
+        case 768: return configure_modes<768>(smem, bps);
+        case 384: return configure_modes<384>(smem, bps);
+        default: return configure_modes<256>(smem, bps);
     }
 }
 
@@ -611,10 +910,13 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
     fp.shard_count = c->shard_count;
     fp.counter_base = s.counter_base;
     fp.tile_counter = s.d_counter;
-    fp.nodes = c->tree_in_smem ? s.d_nodes : s.d_staged;
+    fp.pool = s.d_pool;
+    fp.desc = c->prune ? s.d_desc : nullptr;
+    fp.full_flags = c->full_flags;
     fp.prims = s.d_prims;
     fp.n_nodes = (int)c->tree.nodes.size();
     fp.root_is_leaf = c->tree.root_is_leaf ? 1 : 0;
+    fp.root_pure = c->tree.root_pure ? 1 : 0;
     fp.stack_levels = c->stack_levels;
     fp.ss = c->ss;
     const float wf = (float)(c->width * c->ss), hf = (float)(c->height * c->ss);
@@ -664,9 +966,25 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
         CU(cudaSetDevice(s.device));
         FrameParams fp;
         fill_params(c, s, cam, light, fp);
-        if (!c->tree_in_smem) {
-            const int n = (int)c->tree.nodes.size();
-            csg_stage_kernel<<<(n + 255) / 256, 256, 0, s.stream>>>(s.d_nodes, s.d_staged, n, cam->pos[0], cam->pos[1], cam->pos[2]);
+        {   // per-tile pruned trees + the staged copy of the whole tree for this camera
+            PruneParams q;
+            std::memset(&q, 0, sizeof q);
+            for (int i = 0; i < 3; ++i) {
+                q.cam_pos[i] = fp.cam_pos[i]; q.forward[i] = fp.forward[i]; q.right[i] = fp.right[i]; q.up[i] = fp.up[i];
+            }
+            q.tan_half_fov = fp.tan_half_fov; q.wm1 = fp.wm1; q.hm1 = fp.hm1; q.aspect = fp.aspect; q.ss = fp.ss;
+            q.width = fp.width; q.height = fp.height; q.macro_x = fp.macro_x;
+            q.rm_x0 = fp.rm_x0; q.rm_y0 = fp.rm_y0; q.rm_w = fp.rm_w; q.rm_magic = fp.rm_magic;
+            q.shard_rank = fp.shard_rank; q.shard_count = fp.shard_count;
+            q.n_tiles = c->prune ? fp.n_local_warp_tiles / 64 : 0;
+            q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes; q.n_levels = (int)c->tree.level_start.size() - 1;
+            q.level_start = s.d_level_start; q.level_nodes = s.d_level_nodes;
+            q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes;
+            q.slots_off32 = (uint32_t)fp.n_nodes; q.full_flags = c->full_flags;
+            const int stage_ctas = std::max(1, std::min(64, (fp.n_nodes + kPruneThreads - 1) / kPruneThreads));
+            csg_prune_kernel<<<q.n_tiles + stage_ctas, kPruneThreads, c->prune_smem, s.stream>>>(q);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("prune kernel launch: ") + cudaGetErrorString(e));
             c->launches++;
         }
         int rc = CSG_OK;
@@ -748,7 +1066,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
 
     auto cleanup_fail = [&](int code) { csg_free_context(c); return code; };
 
-    // shared memory plan: [table 128 B][stack 16 B x (levels+1) x threads][tree 32 B/node]
+    // shared memory plan: [table 128 B][stack 16 B x (levels+2) x threads][tree 32 B/node]
     CU(cudaSetDevice(devices[0]));
     int max_optin = 0, sms = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, devices[0]));
@@ -756,20 +1074,26 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     const size_t tree_bytes = c->tree.nodes.size() * sizeof(NodeRec);
     const size_t table_bytes = 32 * sizeof(uint32_t);
     {
+        // per-tile pruning: a slot holds up to 256 records (8 KB); the pruning CTA needs 8 bytes of shared memory per node
+        const size_t n = c->tree.nodes.size();
+        c->full_flags = (c->tree.root_is_leaf ? kTileRootLeaf : 0u) | (c->tree.root_pure ? kTileRootPure : 0u);
+        c->slot_nodes = (int)std::min<size_t>(n, 256);
+        c->prune_smem = (size_t)c->slot_nodes * (32 + 24 + 1) + 8 * n + 16;
+        const char* off = std::getenv("CSG_B200_NO_PRUNE");   // tuning aid
+        c->prune = c->prune_smem <= (size_t)max_optin && !(off && off[0] == '1');
+        if (!c->prune) c->prune_smem = 0;
+    }
+    {
         // resident warps per SM for every (shape, tree placement); +1 KB per CTA is what the driver reserves
         const size_t sm_total = (size_t)max_optin + 1024;
         int best_warps = -1;
-        for (int pass = 0; pass < 2 && best_warps < 16; ++pass) {   // pass 0: tree in shared memory, pass 1: tree in global memory / L1
-            const bool in_smem = pass == 0;
-            for (int i = 0; i < kShapes; ++i) {
-                const int T = kShapeThreads[i];
-                const size_t stack_bytes = (size_t)(c->stack_levels + 1) * T * sizeof(uint4);   // +1: sentinel frame
-                const size_t need = (in_smem ? tree_bytes : 0) + stack_bytes + table_bytes;
-                if (need > (size_t)max_optin) continue;
-                const int ctas = (int)std::min<size_t>(min_blocks_for(T), sm_total / (need + 1024));
-                const int warps = ctas * T / 32;
-                if (warps > best_warps) { best_warps = warps; c->threads = T; c->tree_in_smem = in_smem; c->smem_bytes = need; }
-            }
+        for (int i = 0; i < kShapes; ++i) {
+            const int T = kShapeThreads[i];
+            const size_t need = (size_t)(c->stack_levels + 2) * T * sizeof(uint4) + table_bytes;   // +2: sentinel frame, search marker
+            if (need > (size_t)max_optin) continue;
+            const int ctas = (int)std::min<size_t>(min_blocks_for(T), sm_total / (need + 1024));
+            const int warps = ctas * T / 32;
+            if (warps > best_warps) { best_warps = warps; c->threads = T; c->smem_bytes = need; }
         }
         if (best_warps <= 0) {
             g_err = "tree depth " + std::to_string(c->tree.depth) + " needs more traversal stack than one SM's shared memory (" +
@@ -786,7 +1110,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         s.rank = shard_rank0 + (int)i;
         CU(cudaSetDevice(s.device));
         int bps = 0, rc;
-        rc = c->tree_in_smem ? configure_shape<true>(c->threads, c->smem_bytes, &bps) : configure_shape<false>(c->threads, c->smem_bytes, &bps);
+        rc = configure_shape(c->threads, c->smem_bytes, &bps);
         if (rc) return cleanup_fail(rc);
         if (bps < 1) { g_err = "kernel does not fit on an SM"; return cleanup_fail(CSG_ERR_LIMIT); }
         int dev_sms = 0;
@@ -800,7 +1124,21 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         CU(cudaEventCreate(&s.ev_done));
         CU(cudaMalloc(&s.d_nodes, std::max<size_t>(tree_bytes, 32)));
         CU(cudaMemcpy(s.d_nodes, c->tree.nodes.data(), tree_bytes, cudaMemcpyHostToDevice));
-        if (!c->tree_in_smem) CU(cudaMalloc(&s.d_staged, tree_bytes));
+        {
+            s.n_slots = my_macros;
+            const size_t pool_records = c->tree.nodes.size() + (c->prune ? (size_t)s.n_slots * c->slot_nodes : 0);
+            CU(cudaMalloc(&s.d_pool, std::max<size_t>(pool_records, 1) * sizeof(NodeRec)));
+            CU(cudaMalloc(&s.d_desc, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
+            CU(cudaMemset(s.d_desc, 0, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
+            const std::vector<int>& ls = c->tree.level_start;
+            const std::vector<int>& ln = c->tree.level_nodes;
+            CU(cudaMalloc(&s.d_level_start, ls.size() * sizeof(int)));
+            CU(cudaMemcpy(s.d_level_start, ls.data(), ls.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMalloc(&s.d_level_nodes, std::max<size_t>(ln.size(), 1) * sizeof(int)));
+            CU(cudaMemcpy(s.d_level_nodes, ln.data(), ln.size() * sizeof(int), cudaMemcpyHostToDevice));
+            if (c->prune_smem > 48 * 1024)
+                CU(cudaFuncSetAttribute(csg_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->prune_smem));
+        }
         const size_t prim_bytes = c->tree.prims.size() * sizeof(PrimRec);
         CU(cudaMalloc(&s.d_prims, std::max<size_t>(prim_bytes, 80)));
         CU(cudaMemcpy(s.d_prims, c->tree.prims.data(), prim_bytes, cudaMemcpyHostToDevice));
@@ -824,9 +1162,9 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     char buf[512];
     std::snprintf(buf, sizeof buf,
                   "{\"threads_per_cta\": %d, \"ctas\": %d, \"sms\": %d, \"smem_bytes_per_cta\": %zu, \"tree_bytes\": %zu, "
-                  "\"tree_in_smem\": %s, \"stack_levels\": %d, \"n_nodes\": %zu, \"n_prims\": %zu, \"shards\": %d, "
+                  "\"prune\": %s, \"slot_nodes\": %d, \"stack_levels\": %d, \"n_nodes\": %zu, \"n_prims\": %zu, \"shards\": %d, "
                   "\"macro_tiles\": %d, \"optimize\": %d}",
-                  c->threads, c->shards[0].grid, sms, c->smem_bytes, tree_bytes, c->tree_in_smem ? "true" : "false",
+                  c->threads, c->shards[0].grid, sms, c->smem_bytes, tree_bytes, c->prune ? "true" : "false", c->slot_nodes,
                   c->stack_levels, c->tree.nodes.size(), c->tree.prims.size(), shard_count, total_macros, scene->scene.optimize);
     c->info = buf;
     *out = c;
@@ -1003,7 +1341,10 @@ void csg_free_context(csg_context* c)
         if (s.stream) cudaStreamSynchronize(s.stream);
         if (s.ipc_mapped) cudaIpcCloseMemHandle(s.ipc_mapped);
         cudaFree(s.d_nodes);
-        cudaFree(s.d_staged);
+        cudaFree(s.d_pool);
+        cudaFree(s.d_desc);
+        cudaFree(s.d_level_start);
+        cudaFree(s.d_level_nodes);
         cudaFree(s.d_prims);
         cudaFree(s.d_counter);
         cudaFree(s.d_tan);

@@ -302,6 +302,7 @@ struct Work {  // working tree node
     int type, prim, left, right;
     Box box;
     bool has_cylinder = false;  // some cylinder below: the box only GATES (Q6), it does not bound the hits
+    bool pure = false;          // leaf: sphere or cube; operator: Union of two pure subtrees
 };
 
 // Culling box of a leaf.  Culling boxes only decide whether a subtree is skipped; the proof that any box
@@ -336,6 +337,7 @@ struct Builder {
     {
         Work n{type, prim, l, r, Box{}, false};
         n.has_cylinder = prim != -1 ? type == kCylinder : (w[l].has_cylinder || w[r].has_cylinder);
+        n.pure = prim != -1 ? (type == kSphere || type == kCube) : (type == kUnion && w[l].pure && w[r].pure);
         w.push_back(n);
         return (int)w.size() - 1;
     }
@@ -425,6 +427,9 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
     out.prims.clear();
     out.depth = 0;
     out.root_is_leaf = false;
+    out.root_pure = false;
+    out.level_start.clear();
+    out.level_nodes.clear();
     if (s.nodes.empty()) return;
     Builder b(s);
     int root = optimize >= 1 ? b.build_optimized(0) : b.copy(0);
@@ -464,10 +469,12 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
     out.nodes.reserve(b.w.size());
     struct Item { int id, parent, depth; bool is_right; };
     std::vector<int> index(b.w.size(), -1);
+    std::vector<int> node_depth;
     std::function<void(int, int, int)> emit = [&](int id, int parent, int depth) {
         const Work& n = b.w[id];
         const int me = (int)out.nodes.size();
         index[id] = me;
+        node_depth.push_back(depth);
         out.nodes.push_back(NodeRec{});
         NodeRec& r = out.nodes[me];
         std::memset(&r, 0, sizeof r);
@@ -495,10 +502,22 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
         if (b.w[n.left].prim != -1) meta |= kMetaLeftLeaf;
         if (b.w[n.right].prim != -1) meta |= kMetaRightLeaf;
         if (!n.has_cylinder) meta |= kMetaBounded;
+        if (n.pure) meta |= kMetaPure;
         out.nodes[me].meta = meta;
     };
     emit(root, -1, 0);
+    {
+        int levels = 0;
+        for (int d : node_depth) levels = std::max(levels, d + 1);
+        out.level_start.assign(levels + 1, 0);
+        for (int d : node_depth) out.level_start[d + 1]++;
+        for (int l = 0; l < levels; ++l) out.level_start[l + 1] += out.level_start[l];
+        out.level_nodes.resize(node_depth.size());
+        std::vector<int> fill(out.level_start.begin(), out.level_start.end() - 1);
+        for (size_t i = 0; i < node_depth.size(); ++i) out.level_nodes[fill[node_depth[i]]++] = (int)i;
+    }
     out.root_is_leaf = b.w[root].prim != -1;
+    out.root_pure = !out.root_is_leaf && b.w[root].pure;
     {
         Box rb = b.w[root].box;
         if (out.root_is_leaf && b.w[root].type == kCylinder) {   // true bounds: sphere of radius sqrt(r^2 + (h/2)^2) about the centre

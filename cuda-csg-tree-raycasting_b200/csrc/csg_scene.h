@@ -27,7 +27,7 @@ static_assert(sizeof(RefNode) == 44 && sizeof(RefPrim) == 48, "reference layouts
 
 // ---- flattened GPU tree -------------------------------------------------------------------
 // One 32-byte record per node, preorder (left child of operator n is n+1):
-//   word 7 (all kinds)   kind | leftIsLeaf<<3 | rightIsLeaf<<4 | bounded<<5 | idx<<8   idx = right child (operator) / primitive id (leaf)
+//   word 7 (all kinds)   kind | leftIsLeaf<<3 | rightIsLeaf<<4 | bounded<<5 | pure<<6 | idx<<8   idx = right child (operator) / primitive id (leaf)
 //                        bounded = no cylinder below: the culling box really bounds every hit of the subtree (allows pruning)
 //   operator   w0..5 = culling box (min xyz, max xyz),  w6 = parent node (-1 at the root)
 //   sphere     w0..2 = centre, w3 = radius, w4..6 = centre again (the kernel turns w0..2 into origin-centre while staging)
@@ -39,6 +39,9 @@ struct NodeRec {
 };
 static_assert(sizeof(NodeRec) == 32, "record");
 constexpr uint32_t kMetaLeftLeaf = 1u << 3, kMetaRightLeaf = 1u << 4, kMetaBounded = 1u << 5;
+// pure = a Union whose subtree holds only Unions, spheres and cubes (every leaf convex and truly bounded by its box):
+// such a subtree may be evaluated as a nearest-Enter search (csg_render.cu, ST_SEARCH)
+constexpr uint32_t kMetaPure = 1u << 6;
 
 // Per-primitive data kept in global memory (read on accepted hits / cylinder + cube tests / shading): 5 x float4.
 struct PrimRec {
@@ -55,6 +58,9 @@ struct FlatTree {
     std::vector<PrimRec> prims;
     int depth = 0;        // operator levels on the longest path = stack slots the kernel needs
     bool root_is_leaf = false;
+    bool root_pure = false;
+    // nodes grouped by depth (root = level 0), for the per-tile pruning kernel's bottom-up / top-down passes
+    std::vector<int> level_start, level_nodes;
     // Box outside which every ray is a Miss (the root's culling box; for a root primitive its true bounds, since a root leaf
     // is intersected without the reference's gating box, Q7).  Used for the per-frame screen-space bound.
     bool root_box_valid = false;

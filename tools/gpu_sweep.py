@@ -25,7 +25,7 @@ for name, view, key in [("testCheese512", View(3840, 2160), "c512"), ("testChees
     res[key] = round(float(np.median(ms)), 4)
     info = ctx.info()
     ctx.close()
-res["ctas"] = info["ctas"]; res["smem"] = info["smem_bytes_per_cta"]; res["in_smem"] = info["tree_in_smem"]
+res["ctas"] = info["ctas"]; res["smem"] = info["smem_bytes_per_cta"]; res["prune"] = info["prune"]
 print(json.dumps(res))
 '''
 libs = [None] + sorted(glob.glob(os.path.join(ROOT, "build", "variants", "*.so")))
