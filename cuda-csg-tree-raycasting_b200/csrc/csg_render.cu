@@ -384,7 +384,10 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         unsigned int next = 0;
         if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
         const int k = (int)(cur & 63u);
-        const int j = (int)(cur >> 6) * p.shard_count + p.shard_rank;
+        // traced tiles are handed out heaviest first (order[] from csg_prune_kernel: tiles whose pruned tree is larger come
+        // first, so that the expensive tiles are not the ones still running when the ticket counter runs dry)
+        const int tile_no = p.order ? (int)__ldg(p.order + (cur >> 6)) : (int)(cur >> 6);
+        const int j = tile_no * p.shard_count + p.shard_rank;
         // j / rm_w by multiply-high with a host-computed reciprocal (exact for the ranges the host enables it for)
         const int jy = p.rm_magic ? (int)__umulhi((unsigned int)j, p.rm_magic) : j / p.rm_w;
         const int mx = p.rm_x0 + (j - jy * p.rm_w), my = p.rm_y0 + jy;
@@ -519,27 +522,39 @@ __device__ __forceinline__ void rel_cull_box(const uint4 ua, const uint4 ub, flo
     }
 }
 
-constexpr int kPruneThreads = 256;
+constexpr int kPruneWarps = 4, kPruneThreads = kPruneWarps * 32;
+constexpr int kListMax = 512;     // nodes one tile may look at (alive nodes + their tested children)
+constexpr int kSlotMax = 256;     // records per tile slot
+constexpr int kLevelMax = 64;
+constexpr int kCostBuckets = 64;
 
+struct PruneWarpSmem {            // working set of one warp = one tile
+    int lnode[kListMax];          // node id, in breadth-first order of discovery
+    short lchild[kListMax];       // operators: list position of the left child (the right child follows it)
+    short lrep[kListMax];         // list position of the node standing for this subtree: itself, a descendant, or -1
+    short lsize[kListMax];        // survivors in the subtree (valid where lrep[p] == p)
+    short lidx[kListMax];         // preorder index among the survivors
+    unsigned char lkind[kListMax];   // kind | alive << 3 | reachable << 4
+    unsigned char flg[kListMax];  // bit0 pure, bit1 bounded
+    float box[kListMax][6];       // culling box, origin-relative (operators: recomputed over what survives)
+    short lvl[kLevelMax + 2];     // list position where each level starts
+};
+
+// One WARP per traced macro tile, top-down: only nodes whose parent is reachable from the tile are ever looked at, so the
+// cost follows the size of the tile's own tree, not of the scene.  Three passes over the levels of the visited part:
+// down (frustum tests), up (which operators survive, their boxes), down (preorder numbering and emission).
 __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_constant__ PruneParams q)
 {
-    constexpr int T = kPruneThreads;
     extern __shared__ __align__(16) unsigned char psm[];
-    const int N = q.n_nodes, S = q.slot_nodes;
-    uint4* orec = reinterpret_cast<uint4*>(psm);            // S x 2: the surviving records
-    float* obox = reinterpret_cast<float*>(orec + 2 * S);   // S x 6: culling box of each surviving node (origin-relative)
-    int* rep = reinterpret_cast<int*>(obox + 6 * S);        // N: representative of each node's subtree: itself, a descendant, or -1
-    int* idx = rep + N;                                     // N: reachability flag, then (new index << 1) | flag
-    uint8_t* oflg = reinterpret_cast<uint8_t*>(idx + N);    // S: bit0 pure, bit1 bounded
-    __shared__ int s_part[T];
-    __shared__ int s_total;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float ox = q.cam_pos[0], oy = q.cam_pos[1], oz = q.cam_pos[2];
+    const int N = q.n_nodes, S = q.slot_nodes;
+    const int tile_ctas = (q.n_tiles + kPruneWarps - 1) / kPruneWarps;
 
-    if ((int)blockIdx.x >= q.n_tiles) {
+    if ((int)blockIdx.x >= tile_ctas) {
         // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
-        const int nb = (int)gridDim.x - q.n_tiles;
-        for (int i = ((int)blockIdx.x - q.n_tiles) * T + tid; i < N; i += nb * T) {
+        const int nb = (int)gridDim.x - tile_ctas;
+        for (int i = ((int)blockIdx.x - tile_ctas) * kPruneThreads + tid; i < N; i += nb * kPruneThreads) {
             uint4 oa, ob;
             stage_record(q.nodes[2 * i], q.nodes[2 * i + 1], ox, oy, oz, oa, ob);
             q.pool[2 * i] = oa;
@@ -547,22 +562,25 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
         }
         return;
     }
+    const int tile = (int)blockIdx.x * kPruneWarps + warp;
+    if (tile >= q.n_tiles) return;
+    PruneWarpSmem& w = reinterpret_cast<PruneWarpSmem*>(psm)[warp];
+    const unsigned int lt = (1u << lane) - 1u;
 
     // ---- the tile and its frustum
-    const int j = (int)blockIdx.x * q.shard_count + q.shard_rank;
+    const int j = tile * q.shard_count + q.shard_rank;
     const int jy = q.rm_magic ? (int)__umulhi((unsigned int)j, q.rm_magic) : j / q.rm_w;
     const int mx = q.rm_x0 + (j - jy * q.rm_w), my = q.rm_y0 + jy;
     const int slot = (my * q.macro_x + mx) / q.shard_count;
-    TileDesc* desc = q.desc + slot;
     float pn[5][3];   // inward plane normals: 4 sides through the origin + the camera plane
     {
         const float x0 = (float)(mx * kMacroW - 1) * q.ss, x1 = (float)(min(mx * kMacroW + kMacroW, q.width) + 1) * q.ss;
         const float y0 = (float)(my * kMacroH - 1) * q.ss, y1 = (float)(min(my * kMacroH + kMacroH, q.height) + 1) * q.ss;
         float d[4][3];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {   // corner rays (RaycastKernel :11-25, un-normalised), counter-clockwise: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
+        for (int c = 0; c < 4; ++c) {   // corner rays (RaycastKernel :11-25, un-normalised), around the tile: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
             const float fx = (c == 1 || c == 2) ? x1 : x0, fy = (c >= 2) ? y1 : y0;
-            const float u = fx / q.wm1, v = fy / q.hm1;     // pixel edges: (x - 0.5 + 0.5)
+            const float u = fx / q.wm1, v = fy / q.hm1;
             const float nx = q.aspect * (2.0f * u - 1.0f) * q.tan_half_fov, ny = (1.0f - 2.0f * v) * q.tan_half_fov;
 #pragma unroll
             for (int k = 0; k < 3; ++k) d[c][k] = q.forward[k] + q.right[k] * nx + q.up[k] * ny;
@@ -581,143 +599,184 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
         pn[4][0] = q.forward[0]; pn[4][1] = q.forward[1]; pn[4][2] = q.forward[2];
     }
 
-    // ---- which nodes can any ray of the tile reach
-    for (int i = tid; i < N; i += T) {
-        float lo[3], hi[3];
-        rel_cull_box(q.nodes[2 * i], q.nodes[2 * i + 1], ox, oy, oz, lo, hi);
-        bool outside = false;
+    // ---- A. breadth-first from the root: test a node's box against the frustum, queue the operands of live operators
+    if (lane == 0) { w.lnode[0] = 0; w.lvl[0] = 0; }
+    __syncwarp();
+    int total = 1, lb = 0, le = 1, levels = 0;
+    bool overflow = false;
+    while (lb < le && !overflow) {
+        if (lane == 0) w.lvl[levels + 1] = (short)le;
+        int next_total = total;
+        for (int base = lb; base < le; base += 32) {
+            const int p = base + lane;
+            const bool have = p < le;
+            bool grow = false;
+            uint32_t meta = 0u;
+            if (have) {
+                const int n = w.lnode[p];
+                const uint4 ua = q.nodes[2 * n], ub = q.nodes[2 * n + 1];
+                meta = ub.w;
+                float lo[3], hi[3];
+                rel_cull_box(ua, ub, ox, oy, oz, lo, hi);
+                bool outside = false;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
-                            fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
-            outside = outside || (m < 0.0f);
-        }
-        rep[i] = outside ? -1 : i;
-        idx[i] = 0;
-    }
-    __syncthreads();
-    // operators, deepest level first: kept (both operands matter), collapsed to one operand, or gone
-    for (int lv = q.n_levels - 1; lv >= 0; --lv) {
-        for (int k = q.level_start[lv] + tid; k < q.level_start[lv + 1]; k += T) {
-            const int n = q.level_nodes[k];
-            if (rep[n] < 0) continue;
-            const uint32_t meta = q.nodes[2 * n + 1].w;
-            const uint32_t kind = meta & 7u;
-            if (kind >= 3u) continue;
-            const int a = rep[n + 1], b = rep[meta >> 8];
-            rep[n] = kind == 0u ? (a < 0 ? b : (b < 0 ? a : n)) : kind == 1u ? (a < 0 ? -1 : (b < 0 ? a : n)) : ((a < 0 || b < 0) ? -1 : n);
-        }
-        __syncthreads();
-    }
-    const int r0 = rep[0];
-    if (r0 < 0) {
-        if (tid == 0) *desc = TileDesc{0u, 0u, 0u, 0u};
-        return;
-    }
-    if (tid == 0) idx[r0] = 1;
-    __syncthreads();
-    for (int lv = 0; lv < q.n_levels; ++lv) {   // survivors reachable from the root's representative
-        for (int k = q.level_start[lv] + tid; k < q.level_start[lv + 1]; k += T) {
-            const int n = q.level_nodes[k];
-            if (!idx[n]) continue;
-            const uint32_t meta = q.nodes[2 * n + 1].w;
-            if ((meta & 7u) >= 3u) continue;
-            idx[rep[n + 1]] = 1;
-            idx[rep[meta >> 8]] = 1;
-        }
-        __syncthreads();
-    }
-    // preorder positions of the survivors: exclusive scan of the flags
-    const int chunk = (N + T - 1) / T;
-    const int c0 = min(tid * chunk, N), c1 = min(c0 + chunk, N);
-    int sum = 0;
-    for (int i = c0; i < c1; ++i) sum += idx[i];
-    s_part[tid] = sum;
-    __syncthreads();
-    if (tid < 32) {
-        int acc = 0;
-        for (int base = 0; base < T; base += 32) {
-            const int v = s_part[base + tid];
-            int inc = v;
+                for (int c = 0; c < 5; ++c) {
+                    const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
+                                    fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
+                    outside = outside || (m < 0.0f);
+                }
+                const uint32_t kind = meta & 7u;
+                w.lkind[p] = (unsigned char)(kind | (outside ? 0u : 8u));
+                w.lrep[p] = outside ? (short)-1 : (short)p;
+                w.lsize[p] = 1;
+                w.flg[p] = (unsigned char)(((kind == 3u || kind == 5u) ? 1u : 0u) | ((kind != 4u) ? 2u : 0u));
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (tid >= o) inc += t;
+                for (int c = 0; c < 3; ++c) { w.box[p][c] = lo[c]; w.box[p][3 + c] = hi[c]; }
+                grow = !outside && kind < 3u;
             }
-            s_part[base + tid] = acc + inc - v;
-            acc += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (tid == 0) s_total = acc;
-    }
-    __syncthreads();
-    {
-        int run = s_part[tid];
-        for (int i = c0; i < c1; ++i) {
-            const int f = idx[i];
-            idx[i] = (run << 1) | f;
-            run += f;
-        }
-    }
-    __syncthreads();
-    const int kept = s_total;
-    if (kept > S) {   // does not fit a slot: this tile reads the staged copy of the whole tree
-        if (tid == 0) *desc = TileDesc{0u, (uint32_t)N, q.full_flags, 0u};
-        return;
-    }
-    for (int i = tid; i < N; i += T) {
-        const int e = idx[i];
-        if (!(e & 1)) continue;
-        const int jn = e >> 1;
-        const uint4 ua = q.nodes[2 * i], ub = q.nodes[2 * i + 1];
-        uint4 oa, ob;
-        stage_record(ua, ub, ox, oy, oz, oa, ob);
-        const uint32_t kind = ub.w & 7u;
-        if (kind < 3u) ob.w = kind | ((uint32_t)(idx[rep[ub.w >> 8]] >> 1) << 8);   // new right child; flags and box follow below
-        orec[2 * jn] = oa;
-        orec[2 * jn + 1] = ob;
-        float lo[3], hi[3];
-        rel_cull_box(ua, ub, ox, oy, oz, lo, hi);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { obox[6 * jn + k] = lo[k]; obox[6 * jn + 3 + k] = hi[k]; }
-        oflg[jn] = (uint8_t)(((kind == 3u || kind == 5u) ? 1 : 0) | ((kind != 4u) ? 2 : 0));
-    }
-    __syncthreads();
-    if (tid == 0) {
-        // children follow their parent in preorder: walking backwards sees both operands before the operator
-        for (int i = kept - 1; i >= 0; --i) {
-            uint4 ob = orec[2 * i + 1];
-            const uint32_t kind = ob.w & 7u;
-            if (kind >= 3u) continue;
-            const int l = i + 1, r = (int)(ob.w >> 8);
-            const uint32_t kl = orec[2 * l + 1].w & 7u, kr = orec[2 * r + 1].w & 7u;
-            const float* bl = obox + 6 * l;
-            const float* br = obox + 6 * r;
-            float* bo = obox + 6 * i;
-            if (kind == 0u) {                   // Union: both operands
-                for (int k = 0; k < 3; ++k) { bo[k] = fminf(bl[k], br[k]); bo[3 + k] = fmaxf(bl[3 + k], br[3 + k]); }
-            } else if (kind == 1u) {            // Difference: a subset of the left operand
-                for (int k = 0; k < 6; ++k) bo[k] = bl[k];
-            } else {                            // Intersection: a subset of both; the smaller box
-                float vl = 1.f, vr = 1.f;
-                for (int k = 0; k < 3; ++k) { vl *= fmaxf(bl[3 + k] - bl[k], 0.f); vr *= fmaxf(br[3 + k] - br[k], 0.f); }
-                const float* bs = vl <= vr ? bl : br;
-                for (int k = 0; k < 6; ++k) bo[k] = bs[k];
+            const unsigned int mask = __ballot_sync(0xffffffffu, grow);
+            const int add = 2 * __popc(mask);
+            if (next_total + add > kListMax) { overflow = true; break; }
+            if (grow) {
+                const int c = next_total + 2 * __popc(mask & lt);
+                w.lnode[c] = w.lnode[p] + 1;
+                w.lnode[c + 1] = (int)(meta >> 8);
+                w.lchild[p] = (short)c;
             }
-            const uint32_t fl = oflg[l], fr = oflg[r];
-            const uint32_t pure = (kind == 0u) ? (fl & fr & 1u) : 0u, bounded = (fl & fr & 2u) >> 1;
-            oflg[i] = (uint8_t)(pure | (bounded << 1));
-            ob.w |= (kl >= 3u ? kMetaLeftLeaf : 0u) | (kr >= 3u ? kMetaRightLeaf : 0u) | (bounded ? kMetaBounded : 0u) | (pure ? kMetaPure : 0u);
-            orec[2 * i] = make_uint4(__float_as_uint(bo[0]), __float_as_uint(bo[1]), __float_as_uint(bo[2]), __float_as_uint(bo[3]));
-            ob.x = __float_as_uint(bo[4]); ob.y = __float_as_uint(bo[5]);
-            orec[2 * i + 1] = ob;
+            next_total += add;
         }
-        const uint32_t rk = orec[1].w & 7u;
-        *desc = TileDesc{q.slots_off32 + (uint32_t)slot * (uint32_t)S, (uint32_t)kept,
-                         (rk >= 3u ? kTileRootLeaf : 0u) | ((oflg[0] & 1u) && rk < 3u ? kTileRootPure : 0u), 0u};
+        __syncwarp();
+        lb = le; le = next_total; total = next_total;
+        if (++levels >= kLevelMax) overflow = true;
     }
-    __syncthreads();
+    uint32_t kept = 0u, flags = 0u;
     uint4* dst = q.pool + 2 * ((size_t)q.slots_off32 + (size_t)slot * S);
-    for (int i = tid; i < 2 * kept; i += T) dst[i] = orec[i];
+    int r0 = -1;
+    if (!overflow) {
+        // ---- B. deepest level first: an operator stays (both operands matter: box over what is left, flags), collapses to
+        //         one operand, or goes
+        for (int d = levels - 1; d >= 0; --d) {
+            for (int p = w.lvl[d] + lane; p < w.lvl[d + 1]; p += 32) {
+                const uint32_t k = w.lkind[p];
+                if (!(k & 8u) || (k & 7u) >= 3u) continue;
+                const int c = w.lchild[p];
+                const int a = w.lrep[c], b = w.lrep[c + 1];
+                const uint32_t kind = k & 7u;
+                const int rp = kind == 0u ? (a < 0 ? b : (b < 0 ? a : p)) : kind == 1u ? (a < 0 ? -1 : (b < 0 ? a : p)) : ((a < 0 || b < 0) ? -1 : p);
+                w.lrep[p] = (short)rp;
+                if (rp != p) continue;
+                w.lsize[p] = (short)(1 + w.lsize[a] + w.lsize[b]);
+                const float* bl = w.box[a];
+                const float* br = w.box[b];
+                float* bo = w.box[p];
+                if (kind == 0u) {                   // Union: both operands
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; ++c2) { bo[c2] = fminf(bl[c2], br[c2]); bo[3 + c2] = fmaxf(bl[3 + c2], br[3 + c2]); }
+                } else if (kind == 1u) {            // Difference: a subset of the left operand
+#pragma unroll
+                    for (int c2 = 0; c2 < 6; ++c2) bo[c2] = bl[c2];
+                } else {                            // Intersection: a subset of both; the smaller box
+                    float vl = 1.f, vr = 1.f;
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; ++c2) { vl *= fmaxf(bl[3 + c2] - bl[c2], 0.f); vr *= fmaxf(br[3 + c2] - br[c2], 0.f); }
+                    const float* bs = vl <= vr ? bl : br;
+#pragma unroll
+                    for (int c2 = 0; c2 < 6; ++c2) bo[c2] = bs[c2];
+                }
+                const uint32_t fl = w.flg[a], fr = w.flg[b];
+                w.flg[p] = (unsigned char)(((kind == 0u) ? (fl & fr & 1u) : 0u) | (fl & fr & 2u));
+            }
+            __syncwarp();
+        }
+        r0 = w.lrep[0];
+        if (r0 >= 0) {
+            kept = (uint32_t)w.lsize[r0];
+            if (kept > (uint32_t)S) overflow = true;
+        }
+    }
+    if (!overflow && r0 >= 0) {
+        // ---- C. root first: preorder index of every survivor (left operand right after its operator, right operand after the
+        //         left subtree), and its record
+        if (lane == 0) { w.lidx[r0] = 0; w.lkind[r0] |= 16u; }
+        __syncwarp();
+        for (int d = 0; d < levels; ++d) {
+            for (int p = w.lvl[d] + lane; p < w.lvl[d + 1]; p += 32) {
+                const uint32_t k = w.lkind[p];
+                if (!(k & 16u)) continue;
+                const int i = w.lidx[p];
+                if ((k & 7u) >= 3u) {           // primitive: origin-relative record
+                    const int n = w.lnode[p];
+                    uint4 oa, ob;
+                    stage_record(q.nodes[2 * n], q.nodes[2 * n + 1], ox, oy, oz, oa, ob);
+                    dst[2 * i] = oa;
+                    dst[2 * i + 1] = ob;
+                    continue;
+                }
+                const int c = w.lchild[p];
+                const int ra = w.lrep[c], rb = w.lrep[c + 1];
+                const int r = i + 1 + w.lsize[ra];
+                w.lidx[ra] = (short)(i + 1);
+                w.lidx[rb] = (short)r;
+                w.lkind[ra] |= 16u;
+                w.lkind[rb] |= 16u;
+                const uint32_t f = w.flg[p];
+                const uint32_t meta = (k & 7u) | ((uint32_t)r << 8) | ((w.lkind[ra] & 7u) >= 3u ? kMetaLeftLeaf : 0u) |
+                                      ((w.lkind[rb] & 7u) >= 3u ? kMetaRightLeaf : 0u) | ((f & 2u) ? kMetaBounded : 0u) | ((f & 1u) ? kMetaPure : 0u);
+                const float* bo = w.box[p];
+                dst[2 * i] = make_uint4(__float_as_uint(bo[0]), __float_as_uint(bo[1]), __float_as_uint(bo[2]), __float_as_uint(bo[3]));
+                dst[2 * i + 1] = make_uint4(__float_as_uint(bo[4]), __float_as_uint(bo[5]), 0u, meta);
+            }
+            __syncwarp();
+        }
+        const uint32_t rk = w.lkind[r0] & 7u;
+        flags = (rk >= 3u ? kTileRootLeaf : 0u) | ((rk < 3u && (w.flg[r0] & 1u)) ? kTileRootPure : 0u);
+    }
+    // ---- descriptor; heavy tiles (more nodes) are handed out first by the frame kernel: bucket lists, then one ordered list
+    const uint32_t cost = overflow ? (uint32_t)min(N, 2 * kCostBuckets - 1) : kept;
+    const int bucket = (int)min(cost / 2u, (uint32_t)(kCostBuckets - 1));
+    if (lane == 0) {
+        q.desc[slot] = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
+                                : TileDesc{kept ? q.slots_off32 + (uint32_t)slot * (uint32_t)S : 0u, kept, flags, 0u};
+        if (q.order) {
+            const unsigned int rank = atomicAdd(&q.hist[bucket], 1u);
+            q.lists[(size_t)bucket * q.n_slots + rank] = (unsigned short)tile;
+            __threadfence();
+        }
+    }
+    if (!q.order) return;
+    unsigned int done = 0;
+    if (lane == 0) done = atomicAdd(q.done, 1u);
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done != (unsigned int)q.n_tiles - 1u) return;
+    // last warp of the grid: concatenate the bucket lists, heaviest bucket first, and reset the counters for the next frame
+    __threadfence();
+    static_assert(kCostBuckets == 64, "two buckets per lane");
+    unsigned int* start = reinterpret_cast<unsigned int*>(&w);   // the warp's own scratch is free now
+    {
+        // k = 63 - bucket: heaviest bucket first.  lane l owns k = l and k = 32 + l; start[k] = first position of bucket k in order[]
+        const unsigned int c0 = __ldcg(&q.hist[63 - lane]), c1 = __ldcg(&q.hist[31 - lane]);
+        unsigned int i0 = c0, i1 = c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+            if (lane >= o) { i0 += t0; i1 += t1; }
+        }
+        const unsigned int first_half = __shfl_sync(0xffffffffu, i0, 31);
+        start[lane] = i0 - c0;
+        start[32 + lane] = first_half + i1 - c1;
+    }
+    __syncwarp();
+    for (int b = lane; b < kCostBuckets; b += 32) q.hist[b] = 0u;
+    if (lane == 0) *q.done = 0u;
+    // every output position looks up its bucket (largest k with start[k] <= i): independent loads, several in flight per lane
+#pragma unroll 4
+    for (int i = lane; i < q.n_tiles; i += 32) {
+        int k = 0;
+#pragma unroll
+        for (int step = 32; step >= 1; step >>= 1)
+            if (k + step < kCostBuckets && start[k + step] <= (unsigned int)i) k += step;
+        q.order[i] = __ldcg(q.lists + (size_t)(63 - k) * q.n_slots + ((unsigned int)i - start[k]));
+    }
 }
 
 // FP32 roofline probe: 8 independent FFMA chains per thread, nothing else.
@@ -764,8 +823,9 @@ struct Shard {  // one GPU's share of the frame
     uint4* d_nodes = nullptr;
     uint4* d_pool = nullptr;     // [staged whole tree][one slot of slot_nodes records per macro tile of this shard]
     TileDesc* d_desc = nullptr;  // per macro tile of this shard
-    int* d_level_start = nullptr;
-    int* d_level_nodes = nullptr;
+    unsigned int* d_hist = nullptr;      // kCostBuckets counters + 1 "done" counter
+    unsigned short* d_lists = nullptr;   // kCostBuckets x n_slots
+    unsigned short* d_order = nullptr;   // n_slots
     int n_slots = 0;
     float4* d_prims = nullptr;
     unsigned int* d_counter = nullptr;
@@ -912,6 +972,7 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
     fp.tile_counter = s.d_counter;
     fp.pool = s.d_pool;
     fp.desc = c->prune ? s.d_desc : nullptr;
+    fp.order = c->prune ? s.d_order : nullptr;
     fp.full_flags = c->full_flags;
     fp.prims = s.d_prims;
     fp.n_nodes = (int)c->tree.nodes.size();
@@ -977,12 +1038,13 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.rm_x0 = fp.rm_x0; q.rm_y0 = fp.rm_y0; q.rm_w = fp.rm_w; q.rm_magic = fp.rm_magic;
             q.shard_rank = fp.shard_rank; q.shard_count = fp.shard_count;
             q.n_tiles = c->prune ? fp.n_local_warp_tiles / 64 : 0;
-            q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes; q.n_levels = (int)c->tree.level_start.size() - 1;
-            q.level_start = s.d_level_start; q.level_nodes = s.d_level_nodes;
+            q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes;
+            q.n_slots = s.n_slots; q.hist = s.d_hist; q.done = s.d_hist ? s.d_hist + kCostBuckets : nullptr;
+            q.lists = s.d_lists; q.order = s.d_order;
             q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes;
             q.slots_off32 = (uint32_t)fp.n_nodes; q.full_flags = c->full_flags;
             const int stage_ctas = std::max(1, std::min(64, (fp.n_nodes + kPruneThreads - 1) / kPruneThreads));
-            csg_prune_kernel<<<q.n_tiles + stage_ctas, kPruneThreads, c->prune_smem, s.stream>>>(q);
+            csg_prune_kernel<<<(q.n_tiles + kPruneWarps - 1) / kPruneWarps + stage_ctas, kPruneThreads, c->prune_smem, s.stream>>>(q);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("prune kernel launch: ") + cudaGetErrorString(e));
             c->launches++;
@@ -1074,14 +1136,13 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     const size_t tree_bytes = c->tree.nodes.size() * sizeof(NodeRec);
     const size_t table_bytes = 32 * sizeof(uint32_t);
     {
-        // per-tile pruning: a slot holds up to 256 records (8 KB); the pruning CTA needs 8 bytes of shared memory per node
+        // per-tile pruning: a slot holds up to kSlotMax records (8 KB)
         const size_t n = c->tree.nodes.size();
         c->full_flags = (c->tree.root_is_leaf ? kTileRootLeaf : 0u) | (c->tree.root_pure ? kTileRootPure : 0u);
-        c->slot_nodes = (int)std::min<size_t>(n, 256);
-        c->prune_smem = (size_t)c->slot_nodes * (32 + 24 + 1) + 8 * n + 16;
+        c->slot_nodes = (int)std::min<size_t>(n, kSlotMax);
+        c->prune_smem = kPruneWarps * sizeof(PruneWarpSmem);
         const char* off = std::getenv("CSG_B200_NO_PRUNE");   // tuning aid
-        c->prune = c->prune_smem <= (size_t)max_optin && !(off && off[0] == '1');
-        if (!c->prune) c->prune_smem = 0;
+        c->prune = !(off && off[0] == '1');
     }
     {
         // resident warps per SM for every (shape, tree placement); +1 KB per CTA is what the driver reserves
@@ -1130,12 +1191,12 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
             CU(cudaMalloc(&s.d_pool, std::max<size_t>(pool_records, 1) * sizeof(NodeRec)));
             CU(cudaMalloc(&s.d_desc, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
             CU(cudaMemset(s.d_desc, 0, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
-            const std::vector<int>& ls = c->tree.level_start;
-            const std::vector<int>& ln = c->tree.level_nodes;
-            CU(cudaMalloc(&s.d_level_start, ls.size() * sizeof(int)));
-            CU(cudaMemcpy(s.d_level_start, ls.data(), ls.size() * sizeof(int), cudaMemcpyHostToDevice));
-            CU(cudaMalloc(&s.d_level_nodes, std::max<size_t>(ln.size(), 1) * sizeof(int)));
-            CU(cudaMemcpy(s.d_level_nodes, ln.data(), ln.size() * sizeof(int), cudaMemcpyHostToDevice));
+            if (c->prune && s.n_slots <= 65535) {   // tile numbers are stored as 16-bit
+                CU(cudaMalloc(&s.d_hist, (kCostBuckets + 1) * sizeof(unsigned int)));
+                CU(cudaMemset(s.d_hist, 0, (kCostBuckets + 1) * sizeof(unsigned int)));
+                CU(cudaMalloc(&s.d_lists, (size_t)kCostBuckets * std::max(s.n_slots, 1) * sizeof(unsigned short)));
+                CU(cudaMalloc(&s.d_order, (size_t)std::max(s.n_slots, 1) * sizeof(unsigned short)));
+            }
             if (c->prune_smem > 48 * 1024)
                 CU(cudaFuncSetAttribute(csg_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->prune_smem));
         }
@@ -1343,8 +1404,9 @@ void csg_free_context(csg_context* c)
         cudaFree(s.d_nodes);
         cudaFree(s.d_pool);
         cudaFree(s.d_desc);
-        cudaFree(s.d_level_start);
-        cudaFree(s.d_level_nodes);
+        cudaFree(s.d_hist);
+        cudaFree(s.d_lists);
+        cudaFree(s.d_order);
         cudaFree(s.d_prims);
         cudaFree(s.d_counter);
         cudaFree(s.d_tan);
