@@ -34,7 +34,7 @@ constexpr int kWarpTileW = 8, kWarpTileH = 4;   // one warp = one 8x4 pixel tile
 constexpr int kMacroW = 64, kMacroH = 32;       // sharding unit: 8x8 warp tiles
 
 // Hit details + Phong (sphere/cylinder/cubeHitDetails :183-200/:338-372/:436-457 and LightningKernel :49-111).
-__device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const float4* __restrict__ prims, const FrameParams& p)
+__device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const float4* __restrict__ prims, const FrameParams& p, const float* __restrict__ s_light)
 {
     if (is_miss(res)) return make_float4(0.08f, 0.08f, 0.11f, 1.0f);   // :109
     const uint32_t id = (res.m & H_META_MASK) >> H_ID_SHIFT;
@@ -74,8 +74,7 @@ __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const flo
     if ((res.m & H_CLS) == H_EXIT) { nx = -nx; ny = -ny; nz = -nz; }
 
     // LightningKernel :78-103
-    const float il = __frcp_rn(__fsqrt_rn(dot_ref(p.light[0], p.light[1], p.light[2], p.light[0], p.light[1], p.light[2])));
-    const float Lx = p.light[0] * il, Ly = p.light[1] * il, Lz = p.light[2] * il;
+    const float Lx = s_light[0], Ly = s_light[1], Lz = s_light[2];   // normalize(lightDir), once per CTA
     float vx = p.cam_pos[0] - px, vy = p.cam_pos[1] - py, vz = p.cam_pos[2] - pz;
     const float iv = __frcp_rn(__fsqrt_rn(dot_ref(vx, vy, vz, vx, vy, vz)));
     vx *= iv; vy *= iv; vz *= iv;
@@ -322,8 +321,14 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     const float ox = p.cam_pos[0], oy = p.cam_pos[1], oz = p.cam_pos[2];
 
     if (tid < 27) s_table[tid] = kOutcomeTable[tid];
+    if (tid == 27) {   // L = normalize(lightDir), LightningKernel :78: the same for every pixel of the frame
+        const float il = __frcp_rn(__fsqrt_rn(dot_ref(p.light[0], p.light[1], p.light[2], p.light[0], p.light[1], p.light[2])));
+        float* s_light = reinterpret_cast<float*>(s_table + 28);
+        s_light[0] = p.light[0] * il; s_light[1] = p.light[1] * il; s_light[2] = p.light[2] * il;
+    }
     __syncthreads();
     uint4* my_stack = s_stack + tid;
+    const float* s_light = reinterpret_cast<const float*>(s_table + 28);
 
     // per-frame constants of ray generation, RaycastKernel :11-16
     // Per-frame constants of ray generation (RaycastKernel :11-16) arrive precomputed in the parameter block (wm1 = w-1,
@@ -373,6 +378,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         }
     }
 
+    // everything below reads what csg_prune_kernel wrote (tile descriptors, pruned trees, hand-out order)
+    cudaGridDependencySynchronize();
+
     // ---- phase 2: dynamic tile scheduling over the macro tiles that touch the bound: one ticket per warp tile; the next
     // ticket is requested before the current tile is rendered so the atomic's round trip hides behind the traversal.
     // Ticket t -> macro tile number (t >> 6) * shard_count + shard_rank of the rm_w x rm_h macro rectangle, warp tile t & 63.
@@ -406,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         float accx = 0.f, accy = 0.f, accz = 0.f;
         // this macro tile's pruned tree (csg_prune_kernel): only the primitives its rays can reach, operators whose other
         // operand cannot be reached collapsed away.  n_nodes == 0: every ray of the tile is a Miss.
-        const int slot = (my * p.macro_x + mx) / p.shard_count;
+        const int slot = p.shard_shift >= 0 ? (my * p.macro_x + mx) >> p.shard_shift : (my * p.macro_x + mx) / p.shard_count;
         const uint4 td = p.desc ? __ldg(reinterpret_cast<const uint4*>(p.desc) + slot) : make_uint4(0u, (uint32_t)p.n_nodes, p.full_flags, 0u);
         const unsigned char* tree = reinterpret_cast<const unsigned char*>(p.pool + 2 * (size_t)td.x);
         // whole warp tile outside the screen-space bound of the root box: every ray is a Miss (:109 background colour)
@@ -417,8 +425,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             accx = 0.08f * w; accy = 0.08f * w; accz = 0.11f * w;
         } else if (active) {
 #pragma unroll 1
-            for (int s = 0; s < ss * ss; ++s) {
-                const int vx = x * ss + (s % ss), vy = y * ss + (s / ss);
+            for (int s = 0, sx = 0, sy = 0; s < ss * ss; ++s) {
+                const int vx = x * ss + sx, vy = y * ss + sy;
+                if (++sx == ss) { sx = 0; ++sy; }
                 // RaycastKernel :11-27 + Ray ctor (Ray.cuh:12-18)
                 const float u = __fdiv_rn(__fadd_rn((float)vx, 0.5f), p.wm1);
                 const float v = __fdiv_rn(__fadd_rn((float)vy, 0.5f), p.hm1);
@@ -433,11 +442,11 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                     cx = __fmul_rn(inv, cx); cy = __fmul_rn(inv, cy); cz = __fmul_rn(inv, cz);
                 }
                 r.dx = cx; r.dy = cy; r.dz = cz;
-                r.ix = __frcp_rn(cx); r.iy = __frcp_rn(cy); r.iz = __frcp_rn(cz);
+                r.ix = rcp_approx(cx); r.iy = rcp_approx(cy); r.iz = rcp_approx(cz);   // culling boxes only: they carry 1e-5 of slack
                 res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, kThreads, r, (td.z & kTileRootLeaf) != 0u, (td.z & kTileRootPure) != 0u,
                                                 p.root_is_leaf == 0, iters);
                 if (MODE != OUT_AOV) {
-                    const float4 c = shade_pixel(res, r, p.prims, p);
+                    const float4 c = shade_pixel(res, r, p.prims, p, s_light);
                     accx += c.x; accy += c.y; accz += c.z;
                 }
             }
@@ -550,6 +559,7 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
     const float ox = q.cam_pos[0], oy = q.cam_pos[1], oz = q.cam_pos[2];
     const int N = q.n_nodes, S = q.slot_nodes;
     const int tile_ctas = (q.n_tiles + kPruneWarps - 1) / kPruneWarps;
+    cudaTriggerProgrammaticLaunchCompletion();   // the frame kernel may be scheduled now; it waits for this grid before it reads our output
 
     if ((int)blockIdx.x >= tile_ctas) {
         // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
@@ -874,8 +884,20 @@ namespace {
 template <int MODE, int T>
 int launch_one(csg_context* c, Shard& s, const FrameParams& fp)
 {
-    csg_frame_kernel<MODE, T><<<s.grid, T, c->smem_bytes, s.stream>>>(fp);
-    cudaError_t e = cudaGetLastError();
+    // Programmatic dependent launch: the frame kernel may start while csg_prune_kernel is still draining; it fills the
+    // background macro tiles first and waits for the pruned trees (cudaGridDependencySynchronize) before tracing.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)s.grid);
+    cfg.blockDim = dim3((unsigned)T);
+    cfg.dynamicSmemBytes = c->smem_bytes;
+    cfg.stream = s.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T>, fp);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return CSG_OK;
 }
@@ -968,6 +990,8 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
                        ? (unsigned int)((1ull << 32) / (unsigned long long)c->macro_x + 1ull) : 0u;
     fp.shard_rank = s.rank;
     fp.shard_count = c->shard_count;
+    fp.shard_shift = -1;
+    for (int b = 0; b < 16; ++b) if ((1 << b) == c->shard_count) fp.shard_shift = b;
     fp.counter_base = s.counter_base;
     fp.tile_counter = s.d_counter;
     fp.pool = s.d_pool;
