@@ -23,7 +23,7 @@ EXPORTS = [
     "csg_load_scene", "csg_parse_scene", "csg_free_scene", "csg_scene_counts", "csg_scene_dump", "csg_scene_write",
     "csg_generate_scene", "csg_camera_default", "csg_camera_set", "csg_camera_set_fov_degrees", "csg_light_default",
     "csg_light_direction", "csg_upload", "csg_upload_shard", "csg_free_context", "csg_scene_set_optimize",
-    "csg_render", "csg_render_f32", "csg_render_aov", "csg_render_stats", "csg_set_supersampling", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
+    "csg_render", "csg_render_f32", "csg_render_aov", "csg_render_stats", "csg_set_supersampling", "csg_set_pruning", "csg_prune_stats", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
     "csg_launch_count", "csg_framebuffer", "csg_framebuffer_ipc_handle", "csg_set_gather_target_ipc",
     "csg_set_gather_target", "csg_read_framebuffer", "csg_device_tan_half_fov", "csg_fp32_peak_tflops", "csg_context_info",
     "csg_last_error", "csg_version",
@@ -75,6 +75,8 @@ def _load():
         "csg_render_aov": (i, [vp, C.POINTER(CCamera), vp, vp, vp]),
         "csg_render_stats": (i, [vp, C.POINTER(CCamera), vp]),
         "csg_set_supersampling": (i, [vp, i]),
+        "csg_set_pruning": (i, [vp, i]),
+        "csg_prune_stats": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(C.c_longlong)]),
         "csg_render_enqueue": (i, [vp, C.POINTER(CCamera), C.POINTER(CLight), vp]),
         "csg_sync": (i, [vp]),
         "csg_last_frame_ms": (i, [vp, C.POINTER(f)]),
@@ -267,6 +269,15 @@ class Context:
     def set_supersampling(self, samples_per_axis):
         _check(lib.csg_set_supersampling(self.h, int(samples_per_axis)))
         return self
+
+    def set_pruning(self, enabled):
+        _check(lib.csg_set_pruning(self.h, int(bool(enabled))))
+        return self
+
+    def prune_stats(self):
+        a, b, c_, n = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        _check(lib.csg_prune_stats(self.h, C.byref(a), C.byref(b), C.byref(c_), C.byref(n)))
+        return {"traced_tiles": a.value, "empty_tiles": b.value, "fallback_tiles": c_.value, "pruned_nodes": n.value}
 
     def render_stats(self, cam):
         it = np.empty(self.width * self.height, np.int32)

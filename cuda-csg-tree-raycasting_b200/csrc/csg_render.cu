@@ -609,25 +609,28 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
         pn[4][0] = q.forward[0]; pn[4][1] = q.forward[1]; pn[4][2] = q.forward[2];
     }
 
-    // ---- A. breadth-first from the root: test a node's box against the frustum, queue the operands of live operators
-    if (lane == 0) { w.lnode[0] = 0; w.lvl[0] = 0; }
-    __syncwarp();
-    int total = 1, lb = 0, le = 1, levels = 0;
-    bool overflow = false;
-    while (lb < le && !overflow) {
-        if (lane == 0) w.lvl[levels + 1] = (short)le;
-        int next_total = total;
-        for (int base = lb; base < le; base += 32) {
-            const int p = base + lane;
-            const bool have = p < le;
-            bool grow = false;
-            uint32_t meta = 0u;
-            if (have) {
-                const int n = w.lnode[p];
-                const uint4 ua = q.nodes[2 * n], ub = q.nodes[2 * n + 1];
-                meta = ub.w;
+    // ---- A. breadth-first from the root, queueing the operands of live operators.  Two ways to decide "live":
+    //   pass 0 (frustum walk): test every visited node's box against the frustum.  Cost follows the number of boxes the
+    //          frustum touches — small when the tree is spatially coherent.
+    //   pass 1 (leaf marks; taken when pass 0 overflows its list, or first for small trees): test all primitives once, mark
+    //          the way from every reachable primitive up to the root (2 bits per node: left / right operand has something
+    //          below), then walk down along the marks only.  An operator with one marked side either stands for that side
+    //          (Union; Difference when it is the left one) or is gone (Difference without its left operand, Intersection) and
+    //          is skipped on the spot, so the list holds only operators with both sides marked, and primitives.
+    uint32_t* mk = reinterpret_cast<uint32_t*>(psm + kPruneWarps * sizeof(PruneWarpSmem)) + (size_t)warp * q.mark_words;
+    int total = 1, levels = 0;
+    bool overflow = true;
+    for (int pass = q.marks_first ? 1 : 0; pass < 2 && overflow; ++pass) {
+        if (pass == 1) {
+            if (q.mark_words == 0) break;           // tree too large for the marks
+            for (int i = lane; i < q.mark_words; i += 32) mk[i] = 0u;
+            __syncwarp();
+#pragma unroll 2
+            for (int i = lane; i < N; i += 32) {
+                const uint4 ub = q.nodes[2 * i + 1];
+                if ((ub.w & 7u) < 3u) continue;
                 float lo[3], hi[3];
-                rel_cull_box(ua, ub, ox, oy, oz, lo, hi);
+                rel_cull_box(q.nodes[2 * i], ub, ox, oy, oz, lo, hi);
                 bool outside = false;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
@@ -635,29 +638,84 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
                                     fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
                     outside = outside || (m < 0.0f);
                 }
-                const uint32_t kind = meta & 7u;
-                w.lkind[p] = (unsigned char)(kind | (outside ? 0u : 8u));
-                w.lrep[p] = outside ? (short)-1 : (short)p;
-                w.lsize[p] = 1;
-                w.flg[p] = (unsigned char)(((kind == 3u || kind == 5u) ? 1u : 0u) | ((kind != 4u) ? 2u : 0u));
-#pragma unroll
-                for (int c = 0; c < 3; ++c) { w.box[p][c] = lo[c]; w.box[p][3 + c] = hi[c]; }
-                grow = !outside && kind < 3u;
+                if (outside) continue;
+                atomicOr(&mk[i >> 4], 1u << ((i & 15) * 2));
+                int c = i, par = q.parent[i];
+                while (par >= 0) {                   // up to the root, or to a node somebody else already marked
+                    const int sh = (par & 15) * 2;
+                    const uint32_t old = atomicOr(&mk[par >> 4], (c == par + 1 ? 1u : 2u) << sh);
+                    if ((old >> sh) & 3u) break;
+                    c = par; par = q.parent[par];
+                }
             }
-            const unsigned int mask = __ballot_sync(0xffffffffu, grow);
-            const int add = 2 * __popc(mask);
-            if (next_total + add > kListMax) { overflow = true; break; }
-            if (grow) {
-                const int c = next_total + 2 * __popc(mask & lt);
-                w.lnode[c] = w.lnode[p] + 1;
-                w.lnode[c + 1] = (int)(meta >> 8);
-                w.lchild[p] = (short)c;
-            }
-            next_total += add;
+            __syncwarp();
         }
+        if (lane == 0) { w.lnode[0] = 0; w.lvl[0] = 0; }
         __syncwarp();
-        lb = le; le = next_total; total = next_total;
-        if (++levels >= kLevelMax) overflow = true;
+        int lb = 0, le = 1;
+        total = 1; levels = 0; overflow = false;
+        while (lb < le && !overflow) {
+            if (lane == 0) w.lvl[levels + 1] = (short)le;
+            int next_total = total;
+            for (int base = lb; base < le; base += 32) {
+                const int p = base + lane;
+                const bool have = p < le;
+                bool grow = false;
+                uint32_t meta = 0u;
+                int n = 0;
+                if (have) {
+                    n = w.lnode[p];
+                    bool outside = false;
+                    uint4 ua, ub;
+                    if (pass == 1) {
+                        for (;;) {
+                            meta = q.nodes[2 * n + 1].w;
+                            const uint32_t kind = meta & 7u, m = (mk[n >> 4] >> ((n & 15) * 2)) & 3u;
+                            if (kind >= 3u) { outside = !(m & 1u); break; }
+                            if (m == 3u) break;
+                            if (m == 1u && kind != 2u) { n = n + 1; continue; }              // stands for its left operand
+                            if (m == 2u && kind == 0u) { n = (int)(meta >> 8); continue; }   // Union: stands for its right operand
+                            outside = true;
+                            break;
+                        }
+                        w.lnode[p] = n;
+                    }
+                    ua = q.nodes[2 * n]; ub = q.nodes[2 * n + 1];
+                    meta = ub.w;
+                    float lo[3], hi[3];
+                    rel_cull_box(ua, ub, ox, oy, oz, lo, hi);
+                    if (pass == 0) {
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) {
+                            const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
+                                            fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
+                            outside = outside || (m < 0.0f);
+                        }
+                    }
+                    const uint32_t kind = meta & 7u;
+                    w.lkind[p] = (unsigned char)(kind | (outside ? 0u : 8u));
+                    w.lrep[p] = outside ? (short)-1 : (short)p;
+                    w.lsize[p] = 1;
+                    w.flg[p] = (unsigned char)(((kind == 3u || kind == 5u) ? 1u : 0u) | ((kind != 4u) ? 2u : 0u));
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { w.box[p][c] = lo[c]; w.box[p][3 + c] = hi[c]; }
+                    grow = !outside && kind < 3u;
+                }
+                const unsigned int mask = __ballot_sync(0xffffffffu, grow);
+                const int add = 2 * __popc(mask);
+                if (next_total + add > kListMax) { overflow = true; break; }
+                if (grow) {
+                    const int c = next_total + 2 * __popc(mask & lt);
+                    w.lnode[c] = n + 1;
+                    w.lnode[c + 1] = (int)(meta >> 8);
+                    w.lchild[p] = (short)c;
+                }
+                next_total += add;
+            }
+            __syncwarp();
+            lb = le; le = next_total; total = next_total;
+            if (++levels >= kLevelMax) overflow = true;
+        }
     }
     uint32_t kept = 0u, flags = 0u;
     uint4* dst = q.pool + 2 * ((size_t)q.slots_off32 + (size_t)slot * S);
@@ -833,6 +891,7 @@ struct Shard {  // one GPU's share of the frame
     uint4* d_nodes = nullptr;
     uint4* d_pool = nullptr;     // [staged whole tree][one slot of slot_nodes records per macro tile of this shard]
     TileDesc* d_desc = nullptr;  // per macro tile of this shard
+    int* d_parent = nullptr;
     unsigned int* d_hist = nullptr;      // kCostBuckets counters + 1 "done" counter
     unsigned short* d_lists = nullptr;   // kCostBuckets x n_slots
     unsigned short* d_order = nullptr;   // n_slots
@@ -859,6 +918,9 @@ struct csg_context {
     int slot_nodes = 0;          // records per tile slot
     size_t prune_smem = 0;
     uint32_t full_flags = 0;
+    int mark_words = 0, marks_first = 0;
+    bool prune_alloc = false;    // tile slots were allocated at upload
+    int last_rm[4] = {0, 0, 0, 0};   // traced macro-tile rectangle of the last frame (x0, y0, w, h)
     size_t smem_bytes = 0;
     int stack_levels = 1;
     int threads = 256;           // CTA shape chosen at upload (one of kShapeThreads)
@@ -1051,6 +1113,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
         CU(cudaSetDevice(s.device));
         FrameParams fp;
         fill_params(c, s, cam, light, fp);
+        c->last_rm[0] = fp.rm_x0; c->last_rm[1] = fp.rm_y0; c->last_rm[2] = fp.n_local_warp_tiles ? fp.rm_w : 0; c->last_rm[3] = fp.n_local_warp_tiles ? fp.rm_h : 0;
         {   // per-tile pruned trees + the staged copy of the whole tree for this camera
             PruneParams q;
             std::memset(&q, 0, sizeof q);
@@ -1062,7 +1125,8 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.rm_x0 = fp.rm_x0; q.rm_y0 = fp.rm_y0; q.rm_w = fp.rm_w; q.rm_magic = fp.rm_magic;
             q.shard_rank = fp.shard_rank; q.shard_count = fp.shard_count;
             q.n_tiles = c->prune ? fp.n_local_warp_tiles / 64 : 0;
-            q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes;
+            q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes; q.parent = s.d_parent;
+            q.mark_words = c->mark_words; q.marks_first = c->marks_first;
             q.n_slots = s.n_slots; q.hist = s.d_hist; q.done = s.d_hist ? s.d_hist + kCostBuckets : nullptr;
             q.lists = s.d_lists; q.order = s.d_order;
             q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes;
@@ -1164,9 +1228,14 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         const size_t n = c->tree.nodes.size();
         c->full_flags = (c->tree.root_is_leaf ? kTileRootLeaf : 0u) | (c->tree.root_pure ? kTileRootPure : 0u);
         c->slot_nodes = (int)std::min<size_t>(n, kSlotMax);
-        c->prune_smem = kPruneWarps * sizeof(PruneWarpSmem);
+        // leaf marks: 2 bits per node and warp; above 128K nodes (32 KB per warp) only the frustum walk is available
+        c->mark_words = n <= 131072 ? (int)((n + 15) / 16) : 0;
+        const char* mf = std::getenv("CSG_B200_MARKS_FIRST");   // tuning aid
+        c->marks_first = mf ? (mf[0] == '1') : 0;   // the frustum walk first; the marks when it overflows
+        c->prune_smem = kPruneWarps * (sizeof(PruneWarpSmem) + (size_t)c->mark_words * 4);
         const char* off = std::getenv("CSG_B200_NO_PRUNE");   // tuning aid
         c->prune = !(off && off[0] == '1');
+        c->prune_alloc = c->prune;
     }
     {
         // resident warps per SM for every (shape, tree placement); +1 KB per CTA is what the driver reserves
@@ -1215,6 +1284,8 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
             CU(cudaMalloc(&s.d_pool, std::max<size_t>(pool_records, 1) * sizeof(NodeRec)));
             CU(cudaMalloc(&s.d_desc, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
             CU(cudaMemset(s.d_desc, 0, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
+            CU(cudaMalloc(&s.d_parent, std::max<size_t>(c->tree.parent.size(), 1) * sizeof(int)));
+            CU(cudaMemcpy(s.d_parent, c->tree.parent.data(), c->tree.parent.size() * sizeof(int), cudaMemcpyHostToDevice));
             if (c->prune && s.n_slots <= 65535) {   // tile numbers are stored as 16-bit
                 CU(cudaMalloc(&s.d_hist, (kCostBuckets + 1) * sizeof(unsigned int)));
                 CU(cudaMemset(s.d_hist, 0, (kCostBuckets + 1) * sizeof(unsigned int)));
@@ -1428,6 +1499,7 @@ void csg_free_context(csg_context* c)
         cudaFree(s.d_nodes);
         cudaFree(s.d_pool);
         cudaFree(s.d_desc);
+        cudaFree(s.d_parent);
         cudaFree(s.d_hist);
         cudaFree(s.d_lists);
         cudaFree(s.d_order);
@@ -1597,6 +1669,43 @@ int csg_render_aov(csg_context* ctx, const csg_camera* cam, uint8_t* hit, int32_
     if (hit) CU(cudaMemcpy(hit, ctx->d_aov_hit, n, cudaMemcpyDeviceToHost));
     if (prim_id) CU(cudaMemcpy(prim_id, ctx->d_aov_prim, n * 4, cudaMemcpyDeviceToHost));
     if (t) CU(cudaMemcpy(t, ctx->d_aov_t, n * 4, cudaMemcpyDeviceToHost));
+    return CSG_OK;
+}
+
+int csg_set_pruning(csg_context* ctx, int enabled)
+{
+    if (!ctx) return fail(CSG_ERR_ARG, "null context");
+    ctx->prune = enabled != 0 && ctx->prune_alloc;
+    return CSG_OK;
+}
+
+int csg_prune_stats(csg_context* ctx, int* traced_tiles, int* empty_tiles, int* fallback_tiles, long long* pruned_nodes)
+{
+    if (!ctx) return fail(CSG_ERR_ARG, "null context");
+    int rc = sync_frame(ctx);
+    if (rc) return rc;
+    Shard& s = ctx->shards[0];
+    CU(cudaSetDevice(s.device));
+    std::vector<TileDesc> d((size_t)std::max(s.n_slots, 1));
+    CU(cudaMemcpy(d.data(), s.d_desc, d.size() * sizeof(TileDesc), cudaMemcpyDeviceToHost));
+    int traced = 0, empty = 0, fb = 0;
+    long long nodes = 0;
+    // the traced rectangle of the last frame, in this shard's slots
+    for (int jy = 0; jy < ctx->last_rm[3]; ++jy)
+        for (int jx = 0; jx < ctx->last_rm[2]; ++jx) {
+            const int j = jy * ctx->last_rm[2] + jx;
+            if (j % ctx->shard_count != s.rank) continue;
+            const int m = (ctx->last_rm[1] + jy) * ctx->macro_x + ctx->last_rm[0] + jx;
+            const TileDesc& t = d[(size_t)(m / ctx->shard_count)];
+            ++traced;
+            if (t.n_nodes == 0) ++empty;
+            else if (t.offset32 == 0 && ctx->prune) ++fb;
+            else nodes += t.n_nodes;
+        }
+    if (traced_tiles) *traced_tiles = traced;
+    if (empty_tiles) *empty_tiles = empty;
+    if (fallback_tiles) *fallback_tiles = fb;
+    if (pruned_nodes) *pruned_nodes = nodes;
     return CSG_OK;
 }
 

@@ -428,8 +428,7 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
     out.depth = 0;
     out.root_is_leaf = false;
     out.root_pure = false;
-    out.level_start.clear();
-    out.level_nodes.clear();
+    out.parent.clear();
     if (s.nodes.empty()) return;
     Builder b(s);
     int root = optimize >= 1 ? b.build_optimized(0) : b.copy(0);
@@ -469,12 +468,11 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
     out.nodes.reserve(b.w.size());
     struct Item { int id, parent, depth; bool is_right; };
     std::vector<int> index(b.w.size(), -1);
-    std::vector<int> node_depth;
     std::function<void(int, int, int)> emit = [&](int id, int parent, int depth) {
         const Work& n = b.w[id];
         const int me = (int)out.nodes.size();
         index[id] = me;
-        node_depth.push_back(depth);
+        out.parent.push_back(parent);
         out.nodes.push_back(NodeRec{});
         NodeRec& r = out.nodes[me];
         std::memset(&r, 0, sizeof r);
@@ -506,16 +504,6 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
         out.nodes[me].meta = meta;
     };
     emit(root, -1, 0);
-    {
-        int levels = 0;
-        for (int d : node_depth) levels = std::max(levels, d + 1);
-        out.level_start.assign(levels + 1, 0);
-        for (int d : node_depth) out.level_start[d + 1]++;
-        for (int l = 0; l < levels; ++l) out.level_start[l + 1] += out.level_start[l];
-        out.level_nodes.resize(node_depth.size());
-        std::vector<int> fill(out.level_start.begin(), out.level_start.end() - 1);
-        for (size_t i = 0; i < node_depth.size(); ++i) out.level_nodes[fill[node_depth[i]]++] = (int)i;
-    }
     out.root_is_leaf = b.w[root].prim != -1;
     out.root_pure = !out.root_is_leaf && b.w[root].pure;
     {

@@ -59,8 +59,7 @@ struct FlatTree {
     int depth = 0;        // operator levels on the longest path = stack slots the kernel needs
     bool root_is_leaf = false;
     bool root_pure = false;
-    // nodes grouped by depth (root = level 0), for the per-tile pruning kernel's bottom-up / top-down passes
-    std::vector<int> level_start, level_nodes;
+    std::vector<int> parent;   // parent node of every record (-1 at the root), for the pruning kernel's upward marking
     // Box outside which every ray is a Miss (the root's culling box; for a root primitive its true bounds, since a root leaf
     // is intersected without the reference's gating box, Q7).  Used for the per-frame screen-space bound.
     bool root_box_valid = false;

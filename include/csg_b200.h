@@ -112,6 +112,14 @@ int csg_set_supersampling(csg_context* ctx, int samples_per_axis);
  * the instrumented oracle).  Host pointer, width*height int32. */
 int csg_render_stats(csg_context* ctx, const csg_camera* cam, int32_t* iterations);
 
+/* Per-tile tree pruning (on by default): before each frame every 64x32-pixel tile gets its own copy of the tree holding only
+ * the primitives its rays can reach (operators left with one operand collapse to it).  Results are identical with and
+ * without it; csg_set_pruning(ctx, 0) makes every tile read the whole tree.
+ * csg_prune_stats reports the last frame of shard 0: traced tiles, tiles no primitive reaches, tiles whose tree did not fit
+ * its slot (they read the whole tree), and the total number of nodes over all pruned trees. */
+int csg_set_pruning(csg_context* ctx, int enabled);
+int csg_prune_stats(csg_context* ctx, int* traced_tiles, int* empty_tiles, int* fallback_tiles, long long* pruned_nodes);
+
 /* ---- asynchronous / device-resident form (benchmarks, interop viewers, multi-process gather) */
 /* Enqueues one frame on the context's stream(s); rgba8_dev NULL = the context's own framebuffer
  * (or the gather target).  Returns without waiting. */
