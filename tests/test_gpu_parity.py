@@ -224,3 +224,61 @@ def test_deep_tree_limit_is_an_error_not_a_crash(csg):
     assert e.value.code == csg.CSG_ERR_LIMIT
     ok = csg.Scene.parse(txt, optimize=1).upload(64, 36)   # re-balancing brings the union chain back to log depth
     ok.close()
+
+
+def _frames(csg, ctx, cam, light):
+    hit, prim, t = ctx.render_aov(cam)
+    return hit.copy(), prim.copy(), t.copy(), ctx.render(cam, light).copy()
+
+
+@pytest.mark.parametrize("scene_id", ["inline:nested", "inline:deep_left_chain", "inline:rotated_cylinder_union", "inline:duplicate_spheres",
+                                      "inline:single_cylinder", "corpus:testCheese256", "corpus:testCubeCutEdges", "synthetic:600"])
+def test_per_tile_pruning_changes_nothing(scene_id, csg, monkeypatch):
+    """csg_prune_kernel: every tile's own tree (unreachable primitives dropped, one-operand operators collapsed) gives the
+    frame of the whole tree, byte for byte — through the frustum walk and through the leaf-mark path."""
+    if scene_id.startswith("corpus:") and scene_id[7:] not in scenes.corpus_names():
+        pytest.skip("scene corpus not staged")
+    txt = csg.Scene.generate_text(600, seed=7) if scene_id.startswith("synthetic:") else scenes.text_of(scene_id)
+    w, h = 640, 360
+    vs = [View(w, h), orbit_view(w, h, 13, pitch_deg=25.0, radius=6.0), View(w, h, pos=(0.3, 0.2, -0.4), pitch=0.2, yaw=2.5)]
+    if "Cheese" in scene_id:
+        vs = [View(w, h), oblique_view(w, h), View(w, h, pos=(0.5, 1.0, -19.0), pitch=0.3, yaw=2.0)]
+    for marks_first in ("0", "1"):
+        monkeypatch.setenv("CSG_B200_MARKS_FIRST", marks_first)
+        for optimize in (0, 1):
+            sc = csg.Scene.parse(txt, optimize=optimize)
+            ctx = sc.upload(w, h)
+            for v in vs:
+                cam, light = cam_of(csg, v), light_of(csg, v)
+                ctx.set_pruning(True)
+                a = _frames(csg, ctx, cam, light)
+                st = ctx.prune_stats()
+                ctx.set_pruning(False)
+                b = _frames(csg, ctx, cam, light)
+                for x, y in zip(a, b):
+                    assert np.array_equal(x, y), f"{scene_id} opt={optimize} marks_first={marks_first}"
+                assert st["fallback_tiles"] == 0 and st["traced_tiles"] >= st["empty_tiles"]
+            ctx.close()
+            sc.close()
+
+
+def test_pruning_statistics_and_slot_overflow(csg):
+    """A tile whose pruned tree does not fit its 256-record slot reads the whole tree instead: same frame."""
+    # 400 concentric-ish spheres all visible from every tile around the centre: nothing can be pruned there
+    leaves = [f"Sphere {0.001 * i} 0 0 FF8000 {1.0 + 0.001 * i}" for i in range(400)]
+
+    def union(xs):
+        if len(xs) == 1:
+            return xs[0]
+        m = len(xs) // 2
+        return "Union\n" + union(xs[:m]) + "\n" + union(xs[m:])
+    txt = union(leaves)
+    sc = csg.Scene.parse(txt)
+    ctx = sc.upload(256, 144)
+    cam, light = csg.Camera(), csg.Light()
+    a = ctx.render(cam, light).copy()
+    st = ctx.prune_stats()
+    assert st["fallback_tiles"] > 0                      # 799 nodes > 256 per slot
+    ctx.set_pruning(False)
+    assert np.array_equal(ctx.render(cam, light), a)
+    ctx.close()
