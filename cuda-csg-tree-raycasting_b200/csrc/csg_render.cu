@@ -311,8 +311,9 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
 template <int MODE, int kThreads>
 __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_kernel(const __grid_constant__ FrameParams p)
 {
-    // shared memory: [outcome table 128 B][stack: (levels+2) x kThreads x 16 B].  The tree is read through L1: every
-    // 64x32-pixel macro tile has its own pruned, origin-relative copy (csg_prune_kernel), a few hundred bytes to a few KB.
+    // shared memory: [outcome table 128 B][stack: (levels+2) x kThreads x 16 B][per-warp tree copy: warp_tree_nodes x 32 B].
+    // Every 64x32-pixel macro tile has its own pruned, origin-relative tree (csg_prune_kernel), a few hundred bytes to a few
+    // KB; a warp copies the tree of its current tile into shared memory when it fits, and reads it through L1 otherwise.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_table = reinterpret_cast<uint32_t*>(smem_raw);
     uint4* s_stack = reinterpret_cast<uint4*>(smem_raw + 128);
@@ -328,6 +329,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     }
     __syncthreads();
     uint4* my_stack = s_stack + tid;
+    // per-warp copy of the current tile's tree (when it fits): traversal then reads shared memory instead of L1/L2
+    uint4* my_tree = s_stack + (size_t)(p.stack_levels + 2) * kThreads + (size_t)(tid >> 5) * (2 * p.warp_tree_nodes);
     const float* s_light = reinterpret_cast<const float*>(s_table + 28);
 
     // per-frame constants of ray generation, RaycastKernel :11-16
@@ -417,6 +420,12 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         const int slot = p.shard_shift >= 0 ? (my * p.macro_x + mx) >> p.shard_shift : (my * p.macro_x + mx) / p.shard_count;
         const uint4 td = p.desc ? __ldg(reinterpret_cast<const uint4*>(p.desc) + slot) : make_uint4(0u, (uint32_t)p.n_nodes, p.full_flags, 0u);
         const unsigned char* tree = reinterpret_cast<const unsigned char*>(p.pool + 2 * (size_t)td.x);
+        if (td.y != 0u && td.y <= (uint32_t)p.warp_tree_nodes) {
+            __syncwarp();   // everybody is done with the previous tile's copy
+            for (uint32_t i = lane; i < 2u * td.y; i += 32u) my_tree[i] = __ldg(p.pool + 2 * (size_t)td.x + i);
+            __syncwarp();
+            tree = reinterpret_cast<const unsigned char*>(my_tree);
+        }
         // whole warp tile outside the screen-space bound of the root box: every ray is a Miss (:109 background colour)
         const int tx0 = x - (lane & 7), ty0 = y - (lane >> 3);
         const bool tile_empty = td.y == 0u || tx0 > p.rect_x1 || tx0 + (kWarpTileW - 1) < p.rect_x0 || ty0 > p.rect_y1 || ty0 + (kWarpTileH - 1) < p.rect_y0;
@@ -566,7 +575,7 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
         const int nb = (int)gridDim.x - tile_ctas;
         for (int i = ((int)blockIdx.x - tile_ctas) * kPruneThreads + tid; i < N; i += nb * kPruneThreads) {
             uint4 oa, ob;
-            stage_record(q.nodes[2 * i], q.nodes[2 * i + 1], ox, oy, oz, oa, ob);
+            stage_record(__ldg(&q.nodes[2 * i]), __ldg(&q.nodes[2 * i + 1]), ox, oy, oz, oa, ob);
             q.pool[2 * i] = oa;
             q.pool[2 * i + 1] = ob;
         }
@@ -574,6 +583,12 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
     }
     const int tile = (int)blockIdx.x * kPruneWarps + warp;
     if (tile >= q.n_tiles) return;
+    {   // pull the tree into L2 in one go (the walk below touches it level by level, one dependent miss at a time otherwise)
+        const char* base = reinterpret_cast<const char*>(q.nodes);
+        const size_t bytes = (size_t)N * 32;
+        for (size_t off = ((size_t)(tile & 7) * 32 + lane) * 128; off < bytes && off < (size_t)(1 << 20); off += 8 * 32 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    }
     PruneWarpSmem& w = reinterpret_cast<PruneWarpSmem*>(psm)[warp];
     const unsigned int lt = (1u << lane) - 1u;
 
@@ -627,10 +642,10 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
             __syncwarp();
 #pragma unroll 2
             for (int i = lane; i < N; i += 32) {
-                const uint4 ub = q.nodes[2 * i + 1];
+                const uint4 ub = __ldg(&q.nodes[2 * i + 1]);
                 if ((ub.w & 7u) < 3u) continue;
                 float lo[3], hi[3];
-                rel_cull_box(q.nodes[2 * i], ub, ox, oy, oz, lo, hi);
+                rel_cull_box(__ldg(&q.nodes[2 * i]), ub, ox, oy, oz, lo, hi);
                 bool outside = false;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
@@ -669,7 +684,7 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
                     uint4 ua, ub;
                     if (pass == 1) {
                         for (;;) {
-                            meta = q.nodes[2 * n + 1].w;
+                            meta = __ldg(&q.nodes[2 * n + 1]).w;
                             const uint32_t kind = meta & 7u, m = (mk[n >> 4] >> ((n & 15) * 2)) & 3u;
                             if (kind >= 3u) { outside = !(m & 1u); break; }
                             if (m == 3u) break;
@@ -680,7 +695,7 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
                         }
                         w.lnode[p] = n;
                     }
-                    ua = q.nodes[2 * n]; ub = q.nodes[2 * n + 1];
+                    ua = __ldg(&q.nodes[2 * n]); ub = __ldg(&q.nodes[2 * n + 1]);
                     meta = ub.w;
                     float lo[3], hi[3];
                     rel_cull_box(ua, ub, ox, oy, oz, lo, hi);
@@ -775,7 +790,7 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
                 if ((k & 7u) >= 3u) {           // primitive: origin-relative record
                     const int n = w.lnode[p];
                     uint4 oa, ob;
-                    stage_record(q.nodes[2 * n], q.nodes[2 * n + 1], ox, oy, oz, oa, ob);
+                    stage_record(__ldg(&q.nodes[2 * n]), __ldg(&q.nodes[2 * n + 1]), ox, oy, oz, oa, ob);
                     dst[2 * i] = oa;
                     dst[2 * i + 1] = ob;
                     continue;
@@ -919,6 +934,7 @@ struct csg_context {
     size_t prune_smem = 0;
     uint32_t full_flags = 0;
     int mark_words = 0, marks_first = 0;
+    int warp_tree_nodes = 0;     // per-warp shared-memory copy of the current tile's tree: capacity in records
     bool prune_alloc = false;    // tile slots were allocated at upload
     int last_rm[4] = {0, 0, 0, 0};   // traced macro-tile rectangle of the last frame (x0, y0, w, h)
     size_t smem_bytes = 0;
@@ -1065,6 +1081,7 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
     fp.root_is_leaf = c->tree.root_is_leaf ? 1 : 0;
     fp.root_pure = c->tree.root_pure ? 1 : 0;
     fp.stack_levels = c->stack_levels;
+    fp.warp_tree_nodes = c->prune ? c->warp_tree_nodes : 0;
     fp.ss = c->ss;
     const float wf = (float)(c->width * c->ss), hf = (float)(c->height * c->ss);
     fp.wm1 = wf - 1.0f;       // (width - 1), :11
@@ -1243,11 +1260,20 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         int best_warps = -1;
         for (int i = 0; i < kShapes; ++i) {
             const int T = kShapeThreads[i];
-            const size_t need = (size_t)(c->stack_levels + 2) * T * sizeof(uint4) + table_bytes;   // +2: sentinel frame, search marker
-            if (need > (size_t)max_optin) continue;
-            const int ctas = (int)std::min<size_t>(min_blocks_for(T), sm_total / (need + 1024));
+            const size_t base_need = (size_t)(c->stack_levels + 2) * T * sizeof(uint4) + table_bytes;   // +2: sentinel frame, search marker
+            if (base_need > (size_t)max_optin) continue;
+            const int ctas = (int)std::min<size_t>(min_blocks_for(T), sm_total / (base_need + 1024));
             const int warps = ctas * T / 32;
-            if (warps > best_warps) { best_warps = warps; c->threads = T; c->smem_bytes = need; }
+            if (warps > best_warps) {
+                best_warps = warps; c->threads = T;
+                // per-warp tree copies out of what is left of the SM's shared memory: 64, 32 or 0 nodes per warp
+                c->warp_tree_nodes = 0;
+                for (int cap : {64, 32}) {
+                    const size_t need = base_need + (size_t)(T / 32) * cap * sizeof(NodeRec);
+                    if (c->prune && need <= (size_t)max_optin && (size_t)ctas * (need + 1024) <= sm_total) { c->warp_tree_nodes = cap; break; }
+                }
+                c->smem_bytes = base_need + (size_t)(T / 32) * c->warp_tree_nodes * sizeof(NodeRec);
+            }
         }
         if (best_warps <= 0) {
             g_err = "tree depth " + std::to_string(c->tree.depth) + " needs more traversal stack than one SM's shared memory (" +
