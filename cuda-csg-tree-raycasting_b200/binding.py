@@ -23,7 +23,7 @@ EXPORTS = [
     "csg_load_scene", "csg_parse_scene", "csg_free_scene", "csg_scene_counts", "csg_scene_dump", "csg_scene_write",
     "csg_generate_scene", "csg_camera_default", "csg_camera_set", "csg_camera_set_fov_degrees", "csg_light_default",
     "csg_light_direction", "csg_upload", "csg_upload_shard", "csg_free_context", "csg_scene_set_optimize",
-    "csg_render", "csg_render_f32", "csg_render_aov", "csg_render_stats", "csg_set_supersampling", "csg_set_pruning", "csg_prune_stats", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
+    "csg_render", "csg_render_batch", "csg_render_f32", "csg_render_aov", "csg_render_stats", "csg_set_supersampling", "csg_set_pruning", "csg_prune_stats", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
     "csg_launch_count", "csg_framebuffer", "csg_framebuffer_ipc_handle", "csg_set_gather_target_ipc",
     "csg_set_gather_target", "csg_read_framebuffer", "csg_device_tan_half_fov", "csg_fp32_peak_tflops", "csg_context_info",
     "csg_last_error", "csg_version",
@@ -71,6 +71,7 @@ def _load():
         "csg_free_context": (None, [vp]),
         "csg_scene_set_optimize": (i, [vp, i]),
         "csg_render": (i, [vp, C.POINTER(CCamera), C.POINTER(CLight), vp]),
+        "csg_render_batch": (i, [vp, vp, i, C.POINTER(CLight), vp]),
         "csg_render_f32": (i, [vp, C.POINTER(CCamera), C.POINTER(CLight), vp]),
         "csg_render_aov": (i, [vp, C.POINTER(CCamera), vp, vp, vp]),
         "csg_render_stats": (i, [vp, C.POINTER(CCamera), vp]),
@@ -269,6 +270,17 @@ class Context:
     def set_supersampling(self, samples_per_axis):
         _check(lib.csg_set_supersampling(self.h, int(samples_per_axis)))
         return self
+
+    def render_batch(self, cams, light, out=None):
+        """n frames, one per camera, pipelined over two frame slots; out = host array / pinned or device pointer, or None."""
+        n = len(cams)
+        arr = (CCamera * n)(*[c.c for c in cams])
+        ret = None
+        if out is None:
+            ret = np.empty((n, self.height, self.width, 4), np.uint8)
+            out = ret
+        _check(lib.csg_render_batch(self.h, arr, n, C.byref(light.c), _ptr(out)))
+        return ret
 
     def set_pruning(self, enabled):
         _check(lib.csg_set_pruning(self.h, int(bool(enabled))))

@@ -124,8 +124,8 @@ constexpr uint32_t kSearchMark = 0xfffffffeu;
 
 template <bool COUNT>
 __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, const float4* __restrict__ prims,
-                                        const uint32_t* __restrict__ table, uint4* __restrict__ stack,
-                                        const int stack_stride, const Ray& r, const bool root_is_leaf, const bool root_pure, const bool root_gated, int& iters)
+                                        const uint32_t* __restrict__ table, const uint32_t stack,
+                                        const uint32_t stack_stride, const Ray& r, const bool root_is_leaf, const bool root_pure, const bool root_gated, int& iters)
 {
     enum { ST_ENTER = 0, ST_SEARCH = 1, ST_LOOPL = 2, ST_LOOPR = 3, ST_COMPUTE = 4, ST_RETURN = 5, ST_DONE = 6 };
     Hit L = make_miss(), R = make_miss();      // ST_SEARCH: L = nearest Enter so far, R.t = limit
@@ -141,12 +141,12 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
         return L;
     }
     uint32_t n = 0u;                           // byte offset of the current operator's record
-    uint4* sp = stack;                         // next free frame
-    *sp = make_uint4(0u, 0u, 0u, 0xffffffffu); // sentinel frame: popping it ends the traversal (no base pointer to keep)
+    uint32_t sp = stack;                       // next free frame (shared-memory address; stack_stride = bytes between levels)
+    sts128(sp, make_uint4(0u, 0u, 0u, 0xffffffffu)); // sentinel frame: popping it ends the traversal (no base pointer to keep)
     sp += stack_stride;
     int st = ST_ENTER;
     if (root_pure) {                           // the whole scene is one pure subtree
-        *sp = make_uint4(0u, 0u, 0u, kSearchMark);
+        sts128(sp, make_uint4(0u, 0u, 0u, kSearchMark));
         sp += stack_stride;
         R.t = INFINITY;
         st = ST_SEARCH;
@@ -188,21 +188,21 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                     R.t = lim;
                     if (abort) {                 // back to the subtree's root, this time through the frame machine
                         uint4 f;
-                        do { sp -= stack_stride; f = *sp; } while (f.w != kSearchMark);
+                        do { sp -= stack_stride; f = lds128(sp); } while (f.w != kSearchMark);
                         n = f.z; st = ST_ENTER;
                     } else {
                         goA = goA && !(tnA > lim);
                         goB = goB && !(tnB > lim);
                         if (goA && goB) {
                             const bool right_first = tnB < tnA;
-                            *sp = make_uint4(__float_as_uint(right_first ? tnA : tnB), 0u, 0u, right_first ? cl : cr);
+                            sts128(sp, make_uint4(__float_as_uint(right_first ? tnA : tnB), 0u, 0u, right_first ? cl : cr));
                             sp += stack_stride; n = right_first ? cr : cl;
                         } else if (goA) { n = cl; }
                         else if (goB) { n = cr; }
                         else {
                             for (;;) {
                                 sp -= stack_stride;
-                                const uint4 f = *sp;
+                                const uint4 f = lds128(sp);
                                 if (f.w == kSearchMark) { R = L; st = ST_RETURN; break; }   // the subtree's result: nearest Enter or Miss
                                 if (!(__uint_as_float(f.x) > lim)) { n = f.w; break; }
                             }
@@ -221,23 +221,23 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                         uint32_t first, fm;   // subtree to descend into now, and its meta word
                         float ftn, lim = INFINITY;
                         if (!goA) {                                                        // :556-561
-                            *sp = make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n);
+                            sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n));
                             first = cr; fm = mB; ftn = tnB;
                             if (op != 2u && !is_miss(L)) lim = L.t;
                         } else if (!goB) {                                                 // :562-567
-                            *sp = make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n);
+                            sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n));
                             first = cl; fm = mA; ftn = tnA;
                             if (op == 0u && !is_miss(R)) lim = R.t;
                         } else {                                                           // :568-574
                             const bool right_first = (op == 0u) && (tnB < tnA);
                             const uint32_t pend_pure = ((right_first ? mA : mB) >> 6) & 1u;
-                            *sp = make_uint4(__float_as_uint(tmin), (right_first ? F_FIRST_RGH : F_FIRST_LFT) | pend_pure,
-                                             __float_as_uint(right_first ? tnA : tnB), n);
+                            sts128(sp, make_uint4(__float_as_uint(tmin), (right_first ? F_FIRST_RGH : F_FIRST_LFT) | pend_pure,
+                                             __float_as_uint(right_first ? tnA : tnB), n));
                             first = right_first ? cr : cl; fm = right_first ? mB : mA; ftn = right_first ? tnB : tnA;
                         }
                         sp += stack_stride; n = first;
                         if ((fm & kMetaPure) && ftn > tmin) {   // pure subtree ahead of tmin: nearest-Enter search
-                            *sp = make_uint4(0u, 0u, first, kSearchMark);
+                            sts128(sp, make_uint4(0u, 0u, first, kSearchMark));
                             sp += stack_stride;
                             L = make_miss(); R.t = lim; st = ST_SEARCH;
                         }
@@ -257,16 +257,16 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
             } else if (o == O_LOOPL) {                                                 // :640-646
                 tmin = L.t;
                 if (meta & kMetaLeftLeaf) st = ST_LOOPL;
-                else { *sp = make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n); sp += stack_stride; n = n + 32u; st = ST_ENTER; }
+                else { sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride; n = n + 32u; st = ST_ENTER; }
             } else if (o == O_LOOPR) {                                                 // :647-653
                 tmin = R.t;
                 if (meta & kMetaRightLeaf) st = ST_LOOPR;
-                else { *sp = make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n); sp += stack_stride; n = (meta >> 8) << 5; st = ST_ENTER; }
+                else { sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride; n = (meta >> 8) << 5; st = ST_ENTER; }
             } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
         }
         if (st == ST_RETURN) {                  // action = actionStack.pop(); node = GetParent() (:624-625 etc.); L == R == result
             sp -= stack_stride;
-            const uint4 f = *sp;
+            const uint4 f = lds128(sp);
             if (f.w == 0xffffffffu) { st = ST_DONE; }
             else {
                 n = f.w;
@@ -287,16 +287,16 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                     } else {
                         uint32_t sib;
                         if (ret == F_FIRST_LFT) {
-                            *sp = make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n);
+                            sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n));
                             sib = (pm >> 8) << 5;
                         } else {
-                            *sp = make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n);
+                            sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n));
                             sib = n + 32u;
                         }
                         sp += stack_stride; n = sib; st = ST_ENTER;
                         if ((f.y & 1u) && ptn > tmin) {
                             const float lim = (pop != 2u && !miss) ? L.t : INFINITY;
-                            *sp = make_uint4(0u, 0u, sib, kSearchMark);
+                            sts128(sp, make_uint4(0u, 0u, sib, kSearchMark));
                             sp += stack_stride;
                             L = make_miss(); R.t = lim; st = ST_SEARCH;
                         }
@@ -308,7 +308,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     return L;                                   // :511
 }
 
-template <int MODE, int kThreads>
+template <int MODE, int kThreads, bool kSuper>   // kSuper: more than one ray per pixel (keeps the sample loop and its accumulators out of the common case)
 __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_kernel(const __grid_constant__ FrameParams p)
 {
     // shared memory: [outcome table 128 B][stack: (levels+2) x kThreads x 16 B][per-warp tree copy: warp_tree_nodes x 32 B].
@@ -328,9 +328,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         s_light[0] = p.light[0] * il; s_light[1] = p.light[1] * il; s_light[2] = p.light[2] * il;
     }
     __syncthreads();
-    uint4* my_stack = s_stack + tid;
+    const uint32_t my_stack = (uint32_t)__cvta_generic_to_shared(s_stack + tid);   // frames are addressed in the shared window: 32-bit
     // per-warp copy of the current tile's tree (when it fits): traversal then reads shared memory instead of L1/L2
-    uint4* my_tree = s_stack + (size_t)(p.stack_levels + 2) * kThreads + (size_t)(tid >> 5) * (2 * p.warp_tree_nodes);
+    const uint32_t my_tree_off = 128u + 16u * (uint32_t)((p.stack_levels + 2) * kThreads + (tid >> 5) * (2 * p.warp_tree_nodes));   // bytes from smem_raw
     const float* s_light = reinterpret_cast<const float*>(s_table + 28);
 
     // per-frame constants of ray generation, RaycastKernel :11-16
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     // hm1 = h-1, aspect = w/h: single IEEE operations, identical on the host; tan(fov/2) from the device, see csg_tan_kernel).
     // With supersampling (ss samples per axis) they describe the virtual (width*ss) x (height*ss) grid: sub-sample (sx,sy)
     // of pixel (x,y) is virtual pixel (x*ss+sx, y*ss+sy), SURVEY.md §8(d) row 5.
-    const int ss = p.ss;
+    const int ss = kSuper ? p.ss : 1;
 
     // ---- phase 1: macro tiles entirely outside the screen-space bound of the scene are Miss everywhere (:109): fill them
     // with the background, statically partitioned over the warps of this shard (no traversal, no tickets).
@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         const int x = mx * kMacroW + kx * kWarpTileW + (lane & 7);
         const int y = my * kMacroH + ky * kWarpTileH + (lane >> 3);
         const bool active = x < p.width && y < p.height;
+        const uint32_t pix = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;   // :33 (csg_upload keeps width*height below 2^31)
         ticket = 0xffffffffu;   // placeholder; the real value is broadcast at the end of the iteration
         if (__ballot_sync(0xffffffffu, active) == 0u) { ticket = __shfl_sync(0xffffffffu, next, 0); continue; }
 
@@ -421,6 +422,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         const uint4 td = p.desc ? __ldg(reinterpret_cast<const uint4*>(p.desc) + slot) : make_uint4(0u, (uint32_t)p.n_nodes, p.full_flags, 0u);
         const unsigned char* tree = reinterpret_cast<const unsigned char*>(p.pool + 2 * (size_t)td.x);
         if (td.y != 0u && td.y <= (uint32_t)p.warp_tree_nodes) {
+            uint4* my_tree = reinterpret_cast<uint4*>(smem_raw + my_tree_off);
             __syncwarp();   // everybody is done with the previous tile's copy
             for (uint32_t i = lane; i < 2u * td.y; i += 32u) my_tree[i] = __ldg(p.pool + 2 * (size_t)td.x + i);
             __syncwarp();
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                 }
                 r.dx = cx; r.dy = cy; r.dz = cz;
                 r.ix = rcp_approx(cx); r.iy = rcp_approx(cy); r.iz = rcp_approx(cz);   // culling boxes only: they carry 1e-5 of slack
-                res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, kThreads, r, (td.z & kTileRootLeaf) != 0u, (td.z & kTileRootPure) != 0u,
+                res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u, (td.z & kTileRootPure) != 0u,
                                                 p.root_is_leaf == 0, iters);
                 if (MODE != OUT_AOV) {
                     const float4 c = shade_pixel(res, r, p.prims, p, s_light);
@@ -461,7 +463,6 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             }
         }
 
-        const size_t pix = (size_t)y * p.width + x;   // :33
         if (MODE == OUT_AOV) {
             if (active) {
                 const bool hit = !is_miss(res);
@@ -934,6 +935,9 @@ struct csg_context {
     size_t prune_smem = 0;
     uint32_t full_flags = 0;
     int mark_words = 0, marks_first = 0;
+    csg_scene scene_copy;        // for the second frame slot of csg_render_batch
+    csg_context* twin = nullptr; // second frame slot (own stream, trees, framebuffer), created on first use
+    cudaEvent_t ev_batch0 = nullptr, ev_batch1 = nullptr;
     int warp_tree_nodes = 0;     // per-warp shared-memory copy of the current tile's tree: capacity in records
     bool prune_alloc = false;    // tile slots were allocated at upload
     int last_rm[4] = {0, 0, 0, 0};   // traced macro-tile rectangle of the last frame (x0, y0, w, h)
@@ -974,7 +978,8 @@ int launch_one(csg_context* c, Shard& s, const FrameParams& fp)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T>, fp);
+    cudaError_t e = c->ss > 1 ? cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, true>, fp)
+                              : cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false>, fp);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return CSG_OK;
@@ -993,8 +998,9 @@ int launch_mode(csg_context* c, Shard& s, const FrameParams& fp)
 template <int MODE, int T>
 int configure_one(size_t smem, int* blocks_per_sm)
 {
-    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, T>, T, smem));
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, T, true>, T, smem));
     return CSG_OK;
 }
 
@@ -1210,6 +1216,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
 {
     if (!scene || !out) return fail(CSG_ERR_ARG, "null argument");
     if (width < 2 || height < 2) return fail(CSG_ERR_ARG, "width and height must be >= 2");  // (w-1),(h-1) divisors, Q1
+    if ((long long)width * height >= (1ll << 31)) return fail(CSG_ERR_ARG, "width*height must be below 2^31");
     if (scene->scene.nodes.empty()) return fail(CSG_ERR_ARG, "empty scene");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -1226,6 +1233,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     c->macro_y = (height + kMacroH - 1) / kMacroH;
     c->shard_count = shard_count;
     c->multi_process = multi_process;
+    c->scene_copy.scene = scene->scene;
     flatten(scene->scene, scene->scene.optimize, c->tree);
     c->stack_levels = std::max(1, c->tree.depth);
     c->root_box_valid = c->tree.root_box_valid;
@@ -1258,8 +1266,10 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         // resident warps per SM for every (shape, tree placement); +1 KB per CTA is what the driver reserves
         const size_t sm_total = (size_t)max_optin + 1024;
         int best_warps = -1;
+        const char* force_shape = std::getenv("CSG_B200_SHAPE");   // tuning aid: force a CTA shape
         for (int i = 0; i < kShapes; ++i) {
             const int T = kShapeThreads[i];
+            if (force_shape && std::atoi(force_shape) != T) continue;
             const size_t base_need = (size_t)(c->stack_levels + 2) * T * sizeof(uint4) + table_bytes;   // +2: sentinel frame, search marker
             if (base_need > (size_t)max_optin) continue;
             const int ctas = (int)std::min<size_t>(min_blocks_for(T), sm_total / (base_need + 1024));
@@ -1518,6 +1528,9 @@ int csg_upload_shard(const csg_scene* scene, int width, int height, int device, 
 void csg_free_context(csg_context* c)
 {
     if (!c) return;
+    if (c->twin) csg_free_context(c->twin);
+    if (c->ev_batch0) cudaEventDestroy(c->ev_batch0);
+    if (c->ev_batch1) cudaEventDestroy(c->ev_batch1);
     for (Shard& s : c->shards) {
         cudaSetDevice(s.device);
         if (s.stream) cudaStreamSynchronize(s.stream);
@@ -1572,7 +1585,7 @@ int csg_last_frame_ms(csg_context* ctx, float* ms)
     return CSG_OK;
 }
 
-uint64_t csg_launch_count(const csg_context* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t csg_launch_count(const csg_context* ctx) { return ctx ? ctx->launches + (ctx->twin ? ctx->twin->launches : 0) : 0; }
 
 int csg_framebuffer(csg_context* ctx, uint8_t** rgba8_dev)
 {
@@ -1641,6 +1654,57 @@ int csg_render(csg_context* ctx, const csg_camera* cam, const csg_light* light, 
         CU(cudaStreamSynchronize(root.stream));
     }
     return sync_frame(ctx);
+}
+
+int csg_render_batch(csg_context* ctx, const csg_camera* cams, int n_frames, const csg_light* light, uint8_t* rgba8_out)
+{
+    if (!ctx || !cams || !light || !rgba8_out || n_frames < 1) return fail(CSG_ERR_ARG, "bad argument");
+    if (ctx->shards.size() != 1 || ctx->multi_process) return fail(CSG_ERR_ARG, "csg_render_batch needs a single-GPU context");
+    Shard& s0 = ctx->shards[0];
+    CU(cudaSetDevice(s0.device));
+    if (!ctx->twin) {
+        std::vector<int> devs{s0.device};
+        int rc = create_context(&ctx->scene_copy, ctx->width, ctx->height, devs, 0, 1, false, &ctx->twin);
+        if (rc) return rc;
+        CU(cudaEventCreate(&ctx->ev_batch0));
+        CU(cudaEventCreate(&ctx->ev_batch1));
+    }
+    csg_context* slot[2] = {ctx, ctx->twin};
+    ctx->twin->ss = ctx->ss;
+    ctx->twin->prune = ctx->prune;
+    const bool dev = is_device_pointer(rgba8_out);
+    const size_t bytes = (size_t)ctx->width * ctx->height * 4;
+    float ld[3];
+    csg_light_direction(light, ld);
+    // the device tanf(fov/2) is fetched with a blocking round trip the first time a field of view is seen: do that up front
+    for (int k = 0; k < n_frames; ++k)
+        for (csg_context* c : slot)
+            if (!(cams[k].fov == c->cached_fov)) {
+                float t;
+                int rc = csg_device_tan_half_fov(c, cams[k].fov, &t);
+                if (rc) return rc;
+                c->cached_fov = cams[k].fov; c->cached_tan = t;
+            }
+    CU(cudaEventRecord(ctx->ev_batch0, s0.stream));
+    CU(cudaStreamWaitEvent(ctx->twin->shards[0].stream, ctx->ev_batch0, 0));
+    for (int k = 0; k < n_frames; ++k) {
+        csg_context* c = slot[k & 1];
+        uint8_t* dst = rgba8_out + (size_t)k * bytes;
+        int rc = enqueue_frame(c, &cams[k], ld, OUT_RGBA8, dev ? (void*)dst : nullptr);
+        if (rc) return rc;
+        if (!dev) CU(cudaMemcpyAsync(dst, c->d_fb, bytes, cudaMemcpyDeviceToHost, c->shards[0].stream));
+    }
+    cudaStream_t t1 = ctx->twin->shards[0].stream;
+    CU(cudaEventRecord(ctx->ev_batch1, t1));
+    CU(cudaStreamWaitEvent(s0.stream, ctx->ev_batch1, 0));
+    CU(cudaEventRecord(ctx->ev_batch1, s0.stream));
+    CU(cudaEventSynchronize(ctx->ev_batch1));
+    CU(cudaStreamSynchronize(t1));
+    CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev_batch0, ctx->ev_batch1));
+    ctx->frame_pending = false;
+    ctx->twin->frame_pending = false;
+    CU(cudaGetLastError());
+    return CSG_OK;
 }
 
 int csg_render_f32(csg_context* ctx, const csg_camera* cam, const csg_light* light, float* rgba_f32_out)

@@ -103,6 +103,13 @@ int csg_render_f32(csg_context* ctx, const csg_camera* cam, const csg_light* lig
  * (RayCasting/Utils/Ray.cuh:24-34).  Host pointers; any may be NULL. */
 int csg_render_aov(csg_context* ctx, const csg_camera* cam, uint8_t* hit, int32_t* prim_id, float* t);
 
+/* Camera batch (BASELINE.json configs[1]: a 64-frame orbit).  Renders n_frames frames, camera cams[k] -> frame k at
+ * rgba8_out + k*width*height*4 (host or device pointer), all with the same light.  Frames alternate between two internal
+ * frame slots (own stream, pruned trees and framebuffer each), so frame k+1 is pruned and started while frame k drains and
+ * is copied out; returns when every frame is complete.  csg_last_frame_ms() then reports the whole batch.  Single-GPU
+ * contexts only.  Every frame is identical to what csg_render() produces for its camera. */
+int csg_render_batch(csg_context* ctx, const csg_camera* cams, int n_frames, const csg_light* light, uint8_t* rgba8_out);
+
 /* Supersampling (BASELINE.json configs[4]: 16 rays/pixel = 4 per axis).  Sub-sample (sx,sy) of pixel (x,y) is the reference's
  * ray generation at virtual pixel (x*k+sx, y*k+sy) of a (width*k) x (height*k) frame; the k*k linear colours are box-filtered.
  * I.e. the result equals the reference kernel run at k times the resolution and averaged k x k.  Default 1. */

@@ -282,3 +282,23 @@ def test_pruning_statistics_and_slot_overflow(csg):
     ctx.set_pruning(False)
     assert np.array_equal(ctx.render(cam, light), a)
     ctx.close()
+
+
+def test_camera_batch_equals_frame_by_frame(csg):
+    """csg_render_batch (two pipelined frame slots) == csg_render per camera; host and device outputs."""
+    import torch
+    txt = scenes.INLINE["nested"]
+    w, h, n = 320, 180, 7
+    sc = csg.Scene.parse(txt)
+    ctx = sc.upload(w, h)
+    light = csg.Light()
+    cams = [cam_of(csg, orbit_view(w, h, k, n=n, pitch_deg=20.0, radius=5.0)) for k in range(n)]
+    single = np.stack([ctx.render(c, light).copy().reshape(h, w, 4) for c in cams])
+    got = ctx.render_batch(cams, light)
+    assert np.array_equal(got, single)
+    dev = torch.empty(n * h * w * 4, dtype=torch.uint8, device="cuda")
+    ctx.render_batch(cams, light, dev.data_ptr())
+    assert np.array_equal(dev.cpu().numpy().reshape(n, h, w, 4), single)
+    assert ctx.last_frame_ms() > 0
+    assert np.array_equal(ctx.render(cams[3], light).reshape(h, w, 4), single[3])   # the context is still usable frame by frame
+    ctx.close()

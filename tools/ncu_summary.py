@@ -32,7 +32,9 @@ keep = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "lau
         "l1tex__t_bytes_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_bytes_pipe_lsu_mem_local_op_st.sum",
         "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "sm__cycles_elapsed.max", "lts__t_sectors_op_write.sum",
-        "lts__t_bytes.sum", "sm__cycles_active.avg"]
+        "lts__t_bytes.sum", "sm__cycles_active.avg", "sm__cycles_elapsed.avg",
+        "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed", "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores"]
 summ = []
 for r in data:
     d = {}
@@ -53,10 +55,33 @@ def num(d, k):
     return v * mult
 
 
-out = {"tag": tag, "command": "ncu --set full --clock-control none --import-source on -k regex:csg_frame_kernel -s 4 -c 2 python bench.py --steps 3 --warmup 3 --no-baselines",
+out = {"tag": tag, "command": "ncu --set full --clock-control none --import-source on -k regex:'csg_frame_kernel|csg_prune_kernel' -s 8 -c 4 python bench.py --steps 3 --warmup 3 --no-baselines",
        "launches": summ}
-if summ:
-    d = summ[-1]
+frame = [d for d in summ if "frame" in d["Kernel Name"]["value"]]
+prune = [d for d in summ if "prune" in d["Kernel Name"]["value"]]
+if frame:
+    d = frame[-1]
+    cyc = num(d, "sm__cycles_elapsed.avg") or 0
+    fadd, fmul, ffma = ((num(d, f"smsp__sass_thread_inst_executed_op_{k}_pred_on.sum.per_cycle_elapsed") or 0) * cyc for k in ("fadd", "fmul", "ffma"))
+    out["frame_kernel"] = {"us": num(d, "gpu__time_duration.sum"), "warp_instructions": num(d, "smsp__inst_executed.sum"),
+                           "executed_fp32_flop": fadd + fmul + 2 * ffma,
+                           "fp32_thread_instructions": {"fadd": fadd, "fmul": fmul, "ffma": ffma},
+                           "fma_pipe_pct": num(d, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                           "alu_pipe_pct": num(d, "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                           "issue_active_pct": num(d, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                           "warps_active_pct": num(d, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                           "branch_uniform_pct": num(d, "smsp__sass_average_branch_targets_threads_uniform.pct"),
+                           "threads_per_instruction": num(d, "smsp__thread_inst_executed_per_inst_executed.ratio"),
+                           "fp32_flop_per_cycle": (fadd + fmul + 2 * ffma) / cyc if cyc else None, "fp32_flop_per_cycle_peak": 148 * 128 * 2,
+                           "local_load_instructions": num(d, "sass__inst_executed_local_loads"),
+                           "local_store_instructions": num(d, "sass__inst_executed_local_stores"),
+                           "registers": num(d, "launch__registers_per_thread")}
+if prune:
+    d = prune[-1]
+    out["prune_kernel"] = {"us": num(d, "gpu__time_duration.sum"), "warp_instructions": num(d, "smsp__inst_executed.sum"),
+                           "registers": num(d, "launch__registers_per_thread")}
+if frame:
+    d = frame[-1]
     rd, wr = num(d, "dram__bytes_read.sum"), num(d, "dram__bytes_write.sum")
     out["dram_bytes_per_launch"] = (rd or 0) + (wr or 0)
     out["note"] = ("dram bytes are per launch of csg_frame_kernel; the 33 MB RGBA8 framebuffer is written into the 126 MB L2 and is "
