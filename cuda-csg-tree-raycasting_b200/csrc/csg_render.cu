@@ -641,12 +641,11 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
             if (q.mark_words == 0) break;           // tree too large for the marks
             for (int i = lane; i < q.mark_words; i += 32) mk[i] = 0u;
             __syncwarp();
-#pragma unroll 2
-            for (int i = lane; i < N; i += 32) {
-                const uint4 ub = __ldg(&q.nodes[2 * i + 1]);
-                if ((ub.w & 7u) < 3u) continue;
-                float lo[3], hi[3];
-                rel_cull_box(__ldg(&q.nodes[2 * i]), ub, ox, oy, oz, lo, hi);
+            // all primitives once, coalesced and several loads in flight: culling box (world space) + node number, 32 B each
+#pragma unroll 4
+            for (int k = lane; k < q.n_leaves; k += 32) {
+                const float4 la = __ldg(&q.leaf_boxes[2 * k]), lb4 = __ldg(&q.leaf_boxes[2 * k + 1]);
+                const float lo[3] = {la.x - ox, la.y - oy, la.z - oz}, hi[3] = {lb4.x - ox, lb4.y - oy, lb4.z - oz};
                 bool outside = false;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
@@ -655,13 +654,14 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
                     outside = outside || (m < 0.0f);
                 }
                 if (outside) continue;
+                const int i = __float_as_int(la.w);
                 atomicOr(&mk[i >> 4], 1u << ((i & 15) * 2));
-                int c = i, par = q.parent[i];
+                int c = i, par = __ldg(&q.parent[i]);
                 while (par >= 0) {                   // up to the root, or to a node somebody else already marked
                     const int sh = (par & 15) * 2;
                     const uint32_t old = atomicOr(&mk[par >> 4], (c == par + 1 ? 1u : 2u) << sh);
                     if ((old >> sh) & 3u) break;
-                    c = par; par = q.parent[par];
+                    c = par; par = __ldg(&q.parent[par]);
                 }
             }
             __syncwarp();
@@ -908,6 +908,7 @@ struct Shard {  // one GPU's share of the frame
     uint4* d_pool = nullptr;     // [staged whole tree][one slot of slot_nodes records per macro tile of this shard]
     TileDesc* d_desc = nullptr;  // per macro tile of this shard
     int* d_parent = nullptr;
+    float4* d_leaf_boxes = nullptr;      // per primitive: culling box (world space) + node number, 2 x float4
     unsigned int* d_hist = nullptr;      // kCostBuckets counters + 1 "done" counter
     unsigned short* d_lists = nullptr;   // kCostBuckets x n_slots
     unsigned short* d_order = nullptr;   // n_slots
@@ -1149,6 +1150,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.shard_rank = fp.shard_rank; q.shard_count = fp.shard_count;
             q.n_tiles = c->prune ? fp.n_local_warp_tiles / 64 : 0;
             q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes; q.parent = s.d_parent;
+            q.leaf_boxes = s.d_leaf_boxes; q.n_leaves = (int)(c->tree.leaf_boxes.size() / 8);
             q.mark_words = c->mark_words; q.marks_first = c->marks_first;
             q.n_slots = s.n_slots; q.hist = s.d_hist; q.done = s.d_hist ? s.d_hist + kCostBuckets : nullptr;
             q.lists = s.d_lists; q.order = s.d_order;
@@ -1322,6 +1324,8 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
             CU(cudaMemset(s.d_desc, 0, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
             CU(cudaMalloc(&s.d_parent, std::max<size_t>(c->tree.parent.size(), 1) * sizeof(int)));
             CU(cudaMemcpy(s.d_parent, c->tree.parent.data(), c->tree.parent.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMalloc(&s.d_leaf_boxes, std::max<size_t>(c->tree.leaf_boxes.size(), 8) * sizeof(float)));
+            CU(cudaMemcpy(s.d_leaf_boxes, c->tree.leaf_boxes.data(), c->tree.leaf_boxes.size() * sizeof(float), cudaMemcpyHostToDevice));
             if (c->prune && s.n_slots <= 65535) {   // tile numbers are stored as 16-bit
                 CU(cudaMalloc(&s.d_hist, (kCostBuckets + 1) * sizeof(unsigned int)));
                 CU(cudaMemset(s.d_hist, 0, (kCostBuckets + 1) * sizeof(unsigned int)));
@@ -1539,6 +1543,7 @@ void csg_free_context(csg_context* c)
         cudaFree(s.d_pool);
         cudaFree(s.d_desc);
         cudaFree(s.d_parent);
+        cudaFree(s.d_leaf_boxes);
         cudaFree(s.d_hist);
         cudaFree(s.d_lists);
         cudaFree(s.d_order);

@@ -429,6 +429,7 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
     out.root_is_leaf = false;
     out.root_pure = false;
     out.parent.clear();
+    out.leaf_boxes.clear();
     if (s.nodes.empty()) return;
     Builder b(s);
     int root = optimize >= 1 ? b.build_optimized(0) : b.copy(0);
@@ -487,6 +488,14 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
                 for (int k = 0; k < 3; ++k) { r.f[k] = rb.mn[k]; r.f[3 + k] = rb.mx[k]; }
             }
             r.meta = (uint32_t)n.type | ((uint32_t)n.prim << 8);
+            {
+                const Box cb = leaf_cull_box(p, n.type);
+                float idbits;
+                const int32_t me32 = me;
+                std::memcpy(&idbits, &me32, 4);
+                const float rec[8] = {cb.mn[0], cb.mn[1], cb.mn[2], idbits, cb.mx[0], cb.mx[1], cb.mx[2], 0.0f};
+                out.leaf_boxes.insert(out.leaf_boxes.end(), rec, rec + 8);
+            }
             return;
         }
         out.depth = std::max(out.depth, depth + 1);
