@@ -346,7 +346,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         const int warps_per_cta = kThreads / 32;
         const int gw = blockIdx.x * warps_per_cta + (tid >> 5), GW = gridDim.x * warps_per_cta;
         const int total_macros = p.macro_x * p.macro_y;
-        for (int m = gw * p.shard_count + p.shard_rank; m < total_macros; m += GW * p.shard_count) {
+        // fill_stride/fill_first: a single GPU or the root of a sharded frame fills every background tile itself (local
+        // stores); the other shards fill none — only traced pixels cross NVLink
+        for (int m = gw * p.fill_stride + p.fill_first; m < total_macros; m += GW * p.fill_stride) {
             const int my = p.div_magic ? (int)__umulhi((unsigned int)m, p.div_magic) : m / p.macro_x;
             const int mx = m - my * p.macro_x;
             if (mx >= p.rm_x0 && mx < p.rm_x0 + p.rm_w && my >= p.rm_y0 && my < p.rm_y0 + p.rm_h) continue;   // traced in phase 2
@@ -940,6 +942,7 @@ struct csg_context {
     csg_context* twin = nullptr; // second frame slot (own stream, trees, framebuffer), created on first use
     cudaEvent_t ev_batch0 = nullptr, ev_batch1 = nullptr;
     int warp_tree_nodes = 0;     // per-warp shared-memory copy of the current tile's tree: capacity in records
+    bool external_target = false;   // csg_set_gather_target: pixels go to a buffer that is not rank 0's own framebuffer
     bool prune_alloc = false;    // tile slots were allocated at upload
     int last_rm[4] = {0, 0, 0, 0};   // traced macro-tile rectangle of the last frame (x0, y0, w, h)
     size_t smem_bytes = 0;
@@ -1075,6 +1078,10 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
                        ? (unsigned int)((1ull << 32) / (unsigned long long)c->macro_x + 1ull) : 0u;
     fp.shard_rank = s.rank;
     fp.shard_count = c->shard_count;
+    // background tiles: the shard that owns the framebuffer fills all of them; with an external target everybody fills its own
+    const bool owns_fb = s.rank == 0 && !c->external_target;
+    fp.fill_stride = owns_fb ? 1 : c->shard_count;
+    fp.fill_first = owns_fb ? 0 : (c->external_target ? s.rank : (1 << 30));
     fp.shard_shift = -1;
     for (int b = 0; b < 16; ++b) if ((1 << b) == c->shard_count) fp.shard_shift = b;
     fp.counter_base = s.counter_base;
@@ -1629,6 +1636,7 @@ int csg_set_gather_target(csg_context* ctx, uint8_t* rgba8_dev)
 {
     if (!ctx) return fail(CSG_ERR_ARG, "null context");
     for (Shard& s : ctx->shards) s.target = rgba8_dev ? rgba8_dev : ctx->d_fb;
+    ctx->external_target = rgba8_dev != nullptr;
     return CSG_OK;
 }
 
