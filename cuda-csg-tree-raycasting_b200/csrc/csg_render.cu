@@ -392,8 +392,14 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     unsigned int ticket = 0;
     if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u) - p.counter_base;
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    // Supersampling with 4 or 16 rays per pixel (sp = log2 of that): the samples of a pixel sit in neighbouring lanes instead
+    // of being looped over by one lane: a warp pass covers 8 / 2 pixels of one row with one ray per lane, and a warp tile is
+    // 4 / 16 such passes, handed out in tickets of 1 << gp passes each — so a heavy pixel does not serialise 16 traversals in
+    // one warp, and the per-ticket set-up (descriptor, tree copy) is still shared by a few passes.
+    const int sp = kSuper ? p.sp_shift : 0, gp = kSuper ? p.sp_group : 0;
     while (ticket < (unsigned int)p.n_local_warp_tiles) {
-        const unsigned int cur = ticket;
+        const unsigned int cur = ticket >> (sp - gp);
+        const int pass0 = (int)(ticket & ((1u << (sp - gp)) - 1u)) << gp;
         unsigned int next = 0;
         if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
         const int k = (int)(cur & 63u);
@@ -406,18 +412,10 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         const int mx = p.rm_x0 + (j - jy * p.rm_w), my = p.rm_y0 + jy;
         const int kx = (k & 1) | ((k >> 1) & 2) | ((k >> 2) & 4);        // Morton order inside the macro tile
         const int ky = ((k >> 1) & 1) | ((k >> 2) & 2) | ((k >> 3) & 4);
-        const int x = mx * kMacroW + kx * kWarpTileW + (lane & 7);
-        const int y = my * kMacroH + ky * kWarpTileH + (lane >> 3);
-        const bool active = x < p.width && y < p.height;
-        const uint32_t pix = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;   // :33 (csg_upload keeps width*height below 2^31)
+        const int tx0 = mx * kMacroW + kx * kWarpTileW, ty0 = my * kMacroH + ky * kWarpTileH;   // the warp tile's corner
         ticket = 0xffffffffu;   // placeholder; the real value is broadcast at the end of the iteration
-        if (__ballot_sync(0xffffffffu, active) == 0u) { ticket = __shfl_sync(0xffffffffu, next, 0); continue; }
+        if (tx0 >= p.width || ty0 >= p.height) { ticket = __shfl_sync(0xffffffffu, next, 0); continue; }
 
-        Hit res = make_miss();
-        int iters = 0;
-        Ray r;
-        r.ox = ox; r.oy = oy; r.oz = oz;
-        float accx = 0.f, accy = 0.f, accz = 0.f;
         // this macro tile's pruned tree (csg_prune_kernel): only the primitives its rays can reach, operators whose other
         // operand cannot be reached collapsed away.  n_nodes == 0: every ray of the tile is a Miss.
         const int slot = p.shard_shift >= 0 ? (my * p.macro_x + mx) >> p.shard_shift : (my * p.macro_x + mx) / p.shard_count;
@@ -431,66 +429,102 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             tree = reinterpret_cast<const unsigned char*>(my_tree);
         }
         // whole warp tile outside the screen-space bound of the root box: every ray is a Miss (:109 background colour)
-        const int tx0 = x - (lane & 7), ty0 = y - (lane >> 3);
         const bool tile_empty = td.y == 0u || tx0 > p.rect_x1 || tx0 + (kWarpTileW - 1) < p.rect_x0 || ty0 > p.rect_y1 || ty0 + (kWarpTileH - 1) < p.rect_y0;
-        if (tile_empty) {
-            const float w = (float)(ss * ss);
-            accx = 0.08f * w; accy = 0.08f * w; accz = 0.11f * w;
-        } else if (active) {
-#pragma unroll 1
-            for (int s = 0, sx = 0, sy = 0; s < ss * ss; ++s) {
-                const int vx = x * ss + sx, vy = y * ss + sy;
-                if (++sx == ss) { sx = 0; ++sy; }
-                // RaycastKernel :11-27 + Ray ctor (Ray.cuh:12-18)
-                const float u = __fdiv_rn(__fadd_rn((float)vx, 0.5f), p.wm1);
-                const float v = __fdiv_rn(__fadd_rn((float)vy, 0.5f), p.hm1);
-                const float nx = __fmul_rn(__fmul_rn(p.aspect, __fmaf_rn(u, 2.0f, -1.0f)), p.tan_half_fov);
-                const float ny = __fmul_rn(__fsub_rn(1.0f, __fadd_rn(v, v)), p.tan_half_fov);
-                float cx = __fadd_rn(p.forward[0], __fmaf_rn(p.right[0], nx, __fmul_rn(p.up[0], ny)));
-                float cy = __fadd_rn(p.forward[1], __fmaf_rn(p.right[1], nx, __fmul_rn(p.up[1], ny)));
-                float cz = __fadd_rn(p.forward[2], __fmaf_rn(p.right[2], nx, __fmul_rn(p.up[2], ny)));
-#pragma unroll
-                for (int rep = 0; rep < 2; ++rep) {   // normalize() then the Ray ctor normalises again (Q3)
-                    const float inv = __frcp_rn(__fsqrt_rn(dot_ref(cx, cy, cz, cx, cy, cz)));
-                    cx = __fmul_rn(inv, cx); cy = __fmul_rn(inv, cy); cz = __fmul_rn(inv, cz);
-                }
-                r.dx = cx; r.dy = cy; r.dz = cz;
-                r.ix = rcp_approx(cx); r.iy = rcp_approx(cy); r.iz = rcp_approx(cz);   // culling boxes only: they carry 1e-5 of slack
-                res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u, (td.z & kTileRootPure) != 0u,
-                                                p.root_is_leaf == 0, iters);
-                if (MODE != OUT_AOV) {
-                    const float4 c = shade_pixel(res, r, p.prims, p, s_light);
-                    accx += c.x; accy += c.y; accz += c.z;
-                }
-            }
-        }
 
-        if (MODE == OUT_AOV) {
-            if (active) {
-                const bool hit = !is_miss(res);
-                if (p.aov_hit) p.aov_hit[pix] = hit ? 1 : 0;
-                if (p.aov_prim) p.aov_prim[pix] = hit ? (int32_t)((res.m & H_META_MASK) >> H_ID_SHIFT) : -1;
-                if (p.aov_t) p.aov_t[pix] = hit ? res.t : -1.0f;
-                if (p.aov_iters) p.aov_iters[pix] = iters;
+#pragma unroll 1
+        for (int pass = pass0; pass < pass0 + (1 << gp); ++pass) {
+            int x = tx0, y = ty0;   // this lane's pixel
+            if (sp == 0) { x += lane & 7; y += lane >> 3; }
+            else {   // 32 >> sp pixels of one row per pass, 1 << sp lanes per pixel
+                const int ppw = 32 >> sp, lg = sp > 2 ? sp - 2 : 0;   // 8 / ppw = 1 << lg passes per row of the warp tile
+                x += (pass & ((1 << lg) - 1)) * ppw + (lane >> sp);
+                y += pass >> lg;
             }
-        } else {
-            float4 c = make_float4(accx, accy, accz, 1.0f);
-            if (ss > 1) {   // box filter of the linear colour
-                const float w = __frcp_rn((float)(ss * ss));
-                c.x *= w; c.y *= w; c.z *= w;
+            const bool active = x < p.width && y < p.height;
+            const uint32_t pix = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;   // :33 (csg_upload keeps width*height below 2^31)
+            if (__ballot_sync(0xffffffffu, active) == 0u) continue;
+
+            Hit res = make_miss();
+            int iters = 0;
+            Ray r;
+            r.ox = ox; r.oy = oy; r.oz = oz;
+            float accx = 0.f, accy = 0.f, accz = 0.f;
+            if (tile_empty) {
+                const float w = (float)(ss * ss);
+                accx = 0.08f * w; accy = 0.08f * w; accz = 0.11f * w;
+            } else if (active) {
+                const int n_samples = sp ? 1 : ss * ss;
+#pragma unroll 1
+                for (int s = 0, sx = sp ? ((lane & ((1 << sp) - 1)) & (ss - 1)) : 0, sy = sp ? ((lane & ((1 << sp) - 1)) >> (sp >> 1)) : 0; s < n_samples; ++s) {
+                    const int vx = x * ss + sx, vy = y * ss + sy;
+                    if (++sx == ss) { sx = 0; ++sy; }
+                    // RaycastKernel :11-27 + Ray ctor (Ray.cuh:12-18)
+                    const float u = __fdiv_rn(__fadd_rn((float)vx, 0.5f), p.wm1);
+                    const float v = __fdiv_rn(__fadd_rn((float)vy, 0.5f), p.hm1);
+                    const float nx = __fmul_rn(__fmul_rn(p.aspect, __fmaf_rn(u, 2.0f, -1.0f)), p.tan_half_fov);
+                    const float ny = __fmul_rn(__fsub_rn(1.0f, __fadd_rn(v, v)), p.tan_half_fov);
+                    float cx = __fadd_rn(p.forward[0], __fmaf_rn(p.right[0], nx, __fmul_rn(p.up[0], ny)));
+                    float cy = __fadd_rn(p.forward[1], __fmaf_rn(p.right[1], nx, __fmul_rn(p.up[1], ny)));
+                    float cz = __fadd_rn(p.forward[2], __fmaf_rn(p.right[2], nx, __fmul_rn(p.up[2], ny)));
+#pragma unroll
+                    for (int rep = 0; rep < 2; ++rep) {   // normalize() then the Ray ctor normalises again (Q3)
+                        const float inv = __frcp_rn(__fsqrt_rn(dot_ref(cx, cy, cz, cx, cy, cz)));
+                        cx = __fmul_rn(inv, cx); cy = __fmul_rn(inv, cy); cz = __fmul_rn(inv, cz);
+                    }
+                    r.dx = cx; r.dy = cy; r.dz = cz;
+                    r.ix = rcp_approx(cx); r.iy = rcp_approx(cy); r.iz = rcp_approx(cz);   // culling boxes only: they carry 1e-5 of slack
+                    res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u,
+                                                    (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
+                    if (MODE != OUT_AOV) {
+                        const float4 c = shade_pixel(res, r, p.prims, p, s_light);
+                        accx += c.x; accy += c.y; accz += c.z;
+                    }
+                }
             }
-            if (MODE == OUT_F32) {
-                if (active) reinterpret_cast<float4*>(p.out)[pix] = c;
+
+            if (MODE == OUT_AOV) {
+                if (active) {
+                    const bool hit = !is_miss(res);
+                    if (p.aov_hit) p.aov_hit[pix] = hit ? 1 : 0;
+                    if (p.aov_prim) p.aov_prim[pix] = hit ? (int32_t)((res.m & H_META_MASK) >> H_ID_SHIFT) : -1;
+                    if (p.aov_t) p.aov_t[pix] = hit ? res.t : -1.0f;
+                    if (p.aov_iters) p.aov_iters[pix] = iters;
+                }
             } else {
-                const uint32_t px8 = to_u8(c.x) | (to_u8(c.y) << 8) | (to_u8(c.z) << 16) | 0xFF000000u;
-                // four horizontally adjacent pixels -> one 16-byte store
-                const uint32_t p1 = __shfl_down_sync(0xffffffffu, px8, 1);
-                const uint32_t p2 = __shfl_down_sync(0xffffffffu, px8, 2);
-                const uint32_t p3 = __shfl_down_sync(0xffffffffu, px8, 3);
-                if ((p.width & 3) == 0) {
-                    if (active && (lane & 3) == 0) reinterpret_cast<uint4*>(p.out)[pix >> 2] = make_uint4(px8, p1, p2, p3);
-                } else if (active) {
-                    reinterpret_cast<uint32_t*>(p.out)[pix] = px8;
+                if (kSuper && sp && !tile_empty) {
+                    // sum the pixel's samples in sample order (the order of the one-lane loop), in every lane of the pixel
+                    const int base = lane & ~((1 << sp) - 1);
+                    float sxr = 0.f, syr = 0.f, szr = 0.f;
+                    for (int s = 0; s < (1 << sp); ++s) {
+                        sxr += __shfl_sync(0xffffffffu, accx, base + s);
+                        syr += __shfl_sync(0xffffffffu, accy, base + s);
+                        szr += __shfl_sync(0xffffffffu, accz, base + s);
+                    }
+                    accx = sxr; accy = syr; accz = szr;
+                }
+                float4 c = make_float4(accx, accy, accz, 1.0f);
+                if (ss > 1) {   // box filter of the linear colour
+                    const float w = __frcp_rn((float)(ss * ss));
+                    c.x *= w; c.y *= w; c.z *= w;
+                }
+                if (kSuper && sp) {   // one lane per pixel stores
+                    if (active && (lane & ((1 << sp) - 1)) == 0) {
+                        if (MODE == OUT_F32) reinterpret_cast<float4*>(p.out)[pix] = c;
+                        else reinterpret_cast<uint32_t*>(p.out)[pix] = to_u8(c.x) | (to_u8(c.y) << 8) | (to_u8(c.z) << 16) | 0xFF000000u;
+                    }
+                } else if (MODE == OUT_F32) {
+                    if (active) reinterpret_cast<float4*>(p.out)[pix] = c;
+                } else {
+                    const uint32_t px8 = to_u8(c.x) | (to_u8(c.y) << 8) | (to_u8(c.z) << 16) | 0xFF000000u;
+                    // four horizontally adjacent pixels -> one 16-byte store
+                    const uint32_t p1 = __shfl_down_sync(0xffffffffu, px8, 1);
+                    const uint32_t p2 = __shfl_down_sync(0xffffffffu, px8, 2);
+                    const uint32_t p3 = __shfl_down_sync(0xffffffffu, px8, 3);
+                    if ((p.width & 3) == 0) {
+                        if (active && (lane & 3) == 0) reinterpret_cast<uint4*>(p.out)[pix >> 2] = make_uint4(px8, p1, p2, p3);
+                    } else if (active) {
+                        reinterpret_cast<uint32_t*>(p.out)[pix] = px8;
+                    }
                 }
             }
         }
@@ -1113,7 +1147,18 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
     }
     const long long traced = (long long)fp.rm_w * fp.rm_h;
     const long long mine = traced > s.rank ? (traced - s.rank + c->shard_count - 1) / c->shard_count : 0;
-    fp.n_local_warp_tiles = (int)(mine * 64);
+    fp.sp_shift = (c->ss == 2) ? 2 : (c->ss == 4) ? 4 : 0;   // sample-parallel supersampling: 4 or 16 rays per pixel
+    {
+        const char* serial = std::getenv("CSG_B200_SERIAL_SS");   // testing aid: loop over the samples in one lane
+        if (serial && serial[0] == '1') fp.sp_shift = 0;
+    }
+    // passes per ticket: 1 << sp_group; default: a warp tile in two tickets (measured best on the 8K x 16 spp config at 1..8 GPUs)
+    fp.sp_group = fp.sp_shift > 1 ? fp.sp_shift - 1 : 0;
+    {
+        const char* g = std::getenv("CSG_B200_SS_GROUP");   // tuning aid
+        if (g) fp.sp_group = std::min(std::max(std::atoi(g), 0), fp.sp_shift);
+    }
+    fp.n_local_warp_tiles = (int)((mine * 64) << (fp.sp_shift - fp.sp_group));
     fp.rm_magic = (fp.rm_w > 1 && fp.rm_w < 4096 && traced < (1ll << 20)) ? (unsigned int)((1ull << 32) / (unsigned long long)fp.rm_w + 1ull) : 0u;
     if (fp.rm_w == 0) fp.rm_w = 1;   // never divide by zero; n_local_warp_tiles is 0 anyway
 }
@@ -1155,7 +1200,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.width = fp.width; q.height = fp.height; q.macro_x = fp.macro_x;
             q.rm_x0 = fp.rm_x0; q.rm_y0 = fp.rm_y0; q.rm_w = fp.rm_w; q.rm_magic = fp.rm_magic;
             q.shard_rank = fp.shard_rank; q.shard_count = fp.shard_count;
-            q.n_tiles = c->prune ? fp.n_local_warp_tiles / 64 : 0;
+            q.n_tiles = c->prune ? (fp.n_local_warp_tiles >> (fp.sp_shift - fp.sp_group)) / 64 : 0;
             q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes; q.parent = s.d_parent;
             q.leaf_boxes = s.d_leaf_boxes; q.n_leaves = (int)(c->tree.leaf_boxes.size() / 8);
             q.mark_words = c->mark_words; q.marks_first = c->marks_first;

@@ -302,3 +302,19 @@ def test_camera_batch_equals_frame_by_frame(csg):
     assert ctx.last_frame_ms() > 0
     assert np.array_equal(ctx.render(cams[3], light).reshape(h, w, 4), single[3])   # the context is still usable frame by frame
     ctx.close()
+
+
+@pytest.mark.parametrize("k", [2, 4])
+def test_sample_parallel_supersampling_equals_the_serial_loop(k, csg, monkeypatch):
+    """4 / 16 rays per pixel spread over lanes (one ticket per 8 / 2 pixels) == the one-lane sample loop, bit for bit."""
+    txt = csg.Scene.generate_text(300, seed=3)
+    w, h = 200, 120           # partial tiles on both axes
+    cam, light = csg.Camera(pos=(0.0, 0.0, 5.0)), csg.Light()
+    out = {}
+    for serial in ("0", "1"):
+        monkeypatch.setenv("CSG_B200_SERIAL_SS", serial)
+        ctx = csg.Scene.parse(txt).upload(w, h).set_supersampling(k)
+        out[serial] = (ctx.render(cam, light).copy(), ctx.render_f32(cam, light).copy())
+        ctx.close()
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.array_equal(out["0"][1], out["1"][1])
