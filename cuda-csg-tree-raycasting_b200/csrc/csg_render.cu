@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         for (int m = gw * p.fill_stride + p.fill_first; m < total_macros; m += GW * p.fill_stride) {
             const int my = p.div_magic ? (int)__umulhi((unsigned int)m, p.div_magic) : m / p.macro_x;
             const int mx = m - my * p.macro_x;
+            if (my < p.band_m0 || my >= p.band_m1) continue;                                                   // another band of this frame
             if (mx >= p.rm_x0 && mx < p.rm_x0 + p.rm_w && my >= p.rm_y0 && my < p.rm_y0 + p.rm_h) continue;   // traced in phase 2
             const int x0 = mx * kMacroW, y0 = my * kMacroH;
             if (MODE == OUT_RGBA8 && (p.width & 3) == 0) {
@@ -976,6 +977,9 @@ struct csg_context {
     csg_context* twin = nullptr; // second frame slot (own stream, trees, framebuffer), created on first use
     cudaEvent_t ev_batch0 = nullptr, ev_batch1 = nullptr;
     int warp_tree_nodes = 0;     // per-warp shared-memory copy of the current tile's tree: capacity in records
+    int band_m0 = 0, band_m1 = 0;   // macro-tile rows the next enqueue covers (0, 0 = the whole frame)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_band[8] = {};
     bool external_target = false;   // csg_set_gather_target: pixels go to a buffer that is not rank 0's own framebuffer
     bool prune_alloc = false;    // tile slots were allocated at upload
     int last_rm[4] = {0, 0, 0, 0};   // traced macro-tile rectangle of the last frame (x0, y0, w, h)
@@ -1137,8 +1141,12 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
     fp.aspect = wf / hf;      // (width / height), :15
     screen_bound(c, cam, fp);
     // macro-tile rectangle touched by the bound; the ticket space of this frame covers only these
-    const int ax0 = std::max(fp.rect_x0, 0), ay0 = std::max(fp.rect_y0, 0);
-    const int ax1 = std::min(fp.rect_x1, c->width - 1), ay1 = std::min(fp.rect_y1, c->height - 1);
+    // a frame may be rendered in horizontal bands of macro-tile rows (csg_render to host memory: a band is copied out while
+    // the next one renders); this launch covers rows [band_m0, band_m1)
+    fp.band_m0 = c->band_m0;
+    fp.band_m1 = c->band_m1 > 0 ? c->band_m1 : c->macro_y;
+    const int ax0 = std::max(fp.rect_x0, 0), ay0 = std::max(std::max(fp.rect_y0, 0), fp.band_m0 * kMacroH);
+    const int ax1 = std::min(fp.rect_x1, c->width - 1), ay1 = std::min(std::min(fp.rect_y1, c->height - 1), fp.band_m1 * kMacroH - 1);
     if (ax0 > ax1 || ay0 > ay1) {
         fp.rm_x0 = fp.rm_y0 = 0; fp.rm_w = fp.rm_h = 0;
     } else {
@@ -1179,7 +1187,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
         c->cached_fov = cam->fov;
         c->launches++;
     }
-    CU(cudaEventRecord(root.ev_start, root.stream));
+    if (c->band_m0 == 0) CU(cudaEventRecord(root.ev_start, root.stream));   // later bands of a banded frame keep the first band's start mark
     for (size_t i = 1; i < c->shards.size(); ++i) {   // peers start after the root's start mark
         CU(cudaSetDevice(c->shards[i].device));
         CU(cudaStreamWaitEvent(c->shards[i].stream, root.ev_start, 0));
@@ -1585,6 +1593,11 @@ void csg_free_context(csg_context* c)
 {
     if (!c) return;
     if (c->twin) csg_free_context(c->twin);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+        for (cudaEvent_t e : c->ev_band) if (e) cudaEventDestroy(e);
+    }
     if (c->ev_batch0) cudaEventDestroy(c->ev_batch0);
     if (c->ev_batch1) cudaEventDestroy(c->ev_batch1);
     for (Shard& s : c->shards) {
@@ -1702,10 +1715,43 @@ int csg_render(csg_context* ctx, const csg_camera* cam, const csg_light* light, 
     csg_light_direction(light, ld);
     // multi-shard contexts always gather into the root framebuffer first
     const bool direct = dev && ctx->shards.size() == 1;
-    int rc = enqueue_frame(ctx, cam, ld, OUT_RGBA8, direct ? (void*)rgba8_out : nullptr);
-    if (rc) return rc;
     Shard& root = ctx->shards[0];
     const size_t bytes = (size_t)ctx->width * ctx->height * 4;
+    int n_bands = (!dev && ctx->shards.size() == 1 && ctx->shard_count == 1 && !ctx->external_target && ctx->macro_y >= 16) ? 4 : 1;
+    if (const char* nb = std::getenv("CSG_B200_BANDS")) n_bands = n_bands > 1 ? std::min(std::max(std::atoi(nb), 1), 8) : 1;   // tuning aid
+    if (n_bands > 1) {
+        // Host output on one GPU: the frame is rendered in 4 bands of macro-tile rows; band k travels over PCIe (the 33 MB copy
+        // is 3x the render time at 4K) while band k+1 renders.
+        CU(cudaSetDevice(root.device));
+        if (!ctx->copy_stream) {
+            CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (cudaEvent_t& e : ctx->ev_band) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        int rc = CSG_OK;
+        int rm[4] = {0, 0, 0, 0};   // union of the bands' traced rectangles, for csg_prune_stats
+        for (int b = 0; b < n_bands && !rc; ++b) {
+            ctx->band_m0 = ctx->macro_y * b / n_bands;
+            ctx->band_m1 = ctx->macro_y * (b + 1) / n_bands;
+            rc = enqueue_frame(ctx, cam, ld, OUT_RGBA8, nullptr);
+            if (rc) break;
+            if (ctx->last_rm[2] > 0 && ctx->last_rm[3] > 0) {
+                if (rm[3] == 0) { rm[0] = ctx->last_rm[0]; rm[1] = ctx->last_rm[1]; rm[2] = ctx->last_rm[2]; }
+                rm[3] = ctx->last_rm[1] + ctx->last_rm[3] - rm[1];
+            }
+            const size_t r0 = (size_t)ctx->band_m0 * kMacroH, r1 = std::min<size_t>((size_t)ctx->band_m1 * kMacroH, (size_t)ctx->height);
+            const size_t off = r0 * ctx->width * 4, len = (r1 - r0) * ctx->width * 4;
+            CU(cudaEventRecord(ctx->ev_band[b], root.stream));
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
+            CU(cudaMemcpyAsync(rgba8_out + off, ctx->d_fb + off, len, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        ctx->band_m0 = ctx->band_m1 = 0;
+        for (int i = 0; i < 4; ++i) ctx->last_rm[i] = rm[i];
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        return sync_frame(ctx);
+    }
+    int rc = enqueue_frame(ctx, cam, ld, OUT_RGBA8, direct ? (void*)rgba8_out : nullptr);
+    if (rc) return rc;
     if (!direct) {
         CU(cudaSetDevice(root.device));
         CU(cudaMemcpyAsync(rgba8_out, root.target, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, root.stream));
