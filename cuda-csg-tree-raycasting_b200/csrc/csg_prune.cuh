@@ -1,0 +1,373 @@
+// csg_prune.cuh — csg_prune_kernel: one pruned, origin-relative tree per 64x32-pixel macro tile, rebuilt every frame.
+// No counterpart in the reference (its per-frame work starts at RaycastKernel); see DESIGN.md 4.1 for why this cannot
+// change a result.  Included by csg_render.cu only.
+#pragma once
+#include "csg_kernel.cuh"
+#include "csg_frame.cuh"   // tile geometry constants
+
+namespace csgb {
+
+// ---- per-tile tree pruning ---------------------------------------------------------------------------------------------
+// One warp per traced macro tile builds the tile's own tree: a primitive whose culling box lies outside the tile's frustum
+// (the 64x32 pixels plus a margin of one pixel) is a Miss for every ray of the tile, whatever tmin; an operator with such an
+// operand behaves exactly like its other operand (Union: [x][M] -> RetL, [M][x] -> RetR; Difference: [x][M] -> RetL) or is a
+// Miss itself (Difference without its left operand, Intersection without either: all M* cells, RaycastingKernels.cu:666-677),
+// without ever looping — so dropping those primitives and collapsing those operators changes no result.  The surviving
+// nodes are written in preorder, origin-relative (the subtractions of isBVHNodeHit :724-729, cubeHit :389-394 and
+// sphereHit :139-143 are done here once per node and tile instead of once per ray: same single FADD, same bits), with
+// operator boxes recomputed over what is left.
+__device__ __forceinline__ void stage_record(const uint4 ua, const uint4 ub, float ox, float oy, float oz, uint4& oa, uint4& ob)
+{
+    float4 a = as_float4(ua), b = as_float4(ub);
+    if ((ub.w & 7u) == 3u) {
+        a.x = __fsub_rn(ox, a.x); a.y = __fsub_rn(oy, a.y); a.z = __fsub_rn(oz, a.z);
+    } else {
+        a.x = __fsub_rn(a.x, ox); a.y = __fsub_rn(a.y, oy); a.z = __fsub_rn(a.z, oz);
+        a.w = __fsub_rn(a.w, ox); b.x = __fsub_rn(b.x, oy); b.y = __fsub_rn(b.y, oz);
+    }
+    oa = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+    ob = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), ub.z, ub.w);
+}
+
+// culling box of a node relative to the origin: operators, cubes, cylinders carry it; spheres: centre +- r, padded like the host does
+__device__ __forceinline__ void rel_cull_box(const uint4 ua, const uint4 ub, float ox, float oy, float oz, float lo[3], float hi[3])
+{
+    const float4 a = as_float4(ua), b = as_float4(ub);
+    if ((ub.w & 7u) == 3u) {
+        const float r = fabsf(a.w);
+        const float c[3] = {a.x, a.y, a.z}, o[3] = {ox, oy, oz};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float pad = r * 1e-4f + fabsf(c[k]) * 4e-7f + 1e-30f;
+            lo[k] = (c[k] - r - pad) - o[k];
+            hi[k] = (c[k] + r + pad) - o[k];
+        }
+    } else {
+        lo[0] = a.x - ox; lo[1] = a.y - oy; lo[2] = a.z - oz;
+        hi[0] = a.w - ox; hi[1] = b.x - oy; hi[2] = b.y - oz;
+    }
+}
+
+constexpr int kPruneWarps = 4, kPruneThreads = kPruneWarps * 32;
+constexpr int kListMax = 512;     // nodes one tile may look at (alive nodes + their tested children)
+constexpr int kSlotMax = 256;     // records per tile slot
+constexpr int kLevelMax = 64;
+constexpr int kCostBuckets = 64;
+
+struct PruneWarpSmem {            // working set of one warp = one tile
+    int lnode[kListMax];          // node id, in breadth-first order of discovery
+    short lchild[kListMax];       // operators: list position of the left child (the right child follows it)
+    short lrep[kListMax];         // list position of the node standing for this subtree: itself, a descendant, or -1
+    short lsize[kListMax];        // survivors in the subtree (valid where lrep[p] == p)
+    short lidx[kListMax];         // preorder index among the survivors
+    unsigned char lkind[kListMax];   // kind | alive << 3 | reachable << 4
+    unsigned char flg[kListMax];  // bit0 pure, bit1 bounded
+    float box[kListMax][6];       // culling box, origin-relative (operators: recomputed over what survives)
+    short lvl[kLevelMax + 2];     // list position where each level starts
+};
+
+// One WARP per traced macro tile, top-down: only nodes whose parent is reachable from the tile are ever looked at, so the
+// cost follows the size of the tile's own tree, not of the scene.  Three passes over the levels of the visited part:
+// down (frustum tests), up (which operators survive, their boxes), down (preorder numbering and emission).
+__global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_constant__ PruneParams q)
+{
+    extern __shared__ __align__(16) unsigned char psm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float ox = q.cam_pos[0], oy = q.cam_pos[1], oz = q.cam_pos[2];
+    const int N = q.n_nodes, S = q.slot_nodes;
+    const int tile_ctas = (q.n_tiles + kPruneWarps - 1) / kPruneWarps;
+    cudaTriggerProgrammaticLaunchCompletion();   // the frame kernel may be scheduled now; it waits for this grid before it reads our output
+
+    if ((int)blockIdx.x >= tile_ctas) {
+        // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
+        const int nb = (int)gridDim.x - tile_ctas;
+        for (int i = ((int)blockIdx.x - tile_ctas) * kPruneThreads + tid; i < N; i += nb * kPruneThreads) {
+            uint4 oa, ob;
+            stage_record(__ldg(&q.nodes[2 * i]), __ldg(&q.nodes[2 * i + 1]), ox, oy, oz, oa, ob);
+            q.pool[2 * i] = oa;
+            q.pool[2 * i + 1] = ob;
+        }
+        return;
+    }
+    const int tile = (int)blockIdx.x * kPruneWarps + warp;
+    if (tile >= q.n_tiles) return;
+    {   // pull the tree into L2 in one go (the walk below touches it level by level, one dependent miss at a time otherwise)
+        const char* base = reinterpret_cast<const char*>(q.nodes);
+        const size_t bytes = (size_t)N * 32;
+        for (size_t off = ((size_t)(tile & 7) * 32 + lane) * 128; off < bytes && off < (size_t)(1 << 20); off += 8 * 32 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    }
+    PruneWarpSmem& w = reinterpret_cast<PruneWarpSmem*>(psm)[warp];
+    const unsigned int lt = (1u << lane) - 1u;
+
+    // ---- the tile and its frustum
+    const int j = tile * q.shard_count + q.shard_rank;
+    const int jy = q.rm_magic ? (int)__umulhi((unsigned int)j, q.rm_magic) : j / q.rm_w;
+    const int mx = q.rm_x0 + (j - jy * q.rm_w), my = q.rm_y0 + jy;
+    const int slot = (my * q.macro_x + mx) / q.shard_count;
+    float pn[5][3];   // inward plane normals: 4 sides through the origin + the camera plane
+    {
+        const float x0 = (float)(mx * kMacroW - 1) * q.ss, x1 = (float)(min(mx * kMacroW + kMacroW, q.width) + 1) * q.ss;
+        const float y0 = (float)(my * kMacroH - 1) * q.ss, y1 = (float)(min(my * kMacroH + kMacroH, q.height) + 1) * q.ss;
+        float d[4][3];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {   // corner rays (RaycastKernel :11-25, un-normalised), around the tile: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
+            const float fx = (c == 1 || c == 2) ? x1 : x0, fy = (c >= 2) ? y1 : y0;
+            const float u = fx / q.wm1, v = fy / q.hm1;
+            const float nx = q.aspect * (2.0f * u - 1.0f) * q.tan_half_fov, ny = (1.0f - 2.0f * v) * q.tan_half_fov;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) d[c][k] = q.forward[k] + q.right[k] * nx + q.up[k] * ny;
+        }
+        float dc[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dc[k] = d[0][k] + d[1][k] + d[2][k] + d[3][k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float* a = d[c];
+            const float* b = d[(c + 1) & 3];
+            float n0 = a[1] * b[2] - a[2] * b[1], n1 = a[2] * b[0] - a[0] * b[2], n2 = a[0] * b[1] - a[1] * b[0];
+            if (n0 * dc[0] + n1 * dc[1] + n2 * dc[2] < 0.0f) { n0 = -n0; n1 = -n1; n2 = -n2; }
+            pn[c][0] = n0; pn[c][1] = n1; pn[c][2] = n2;
+        }
+        pn[4][0] = q.forward[0]; pn[4][1] = q.forward[1]; pn[4][2] = q.forward[2];
+    }
+
+    // ---- A. breadth-first from the root, queueing the operands of live operators.  Two ways to decide "live":
+    //   pass 0 (frustum walk): test every visited node's box against the frustum.  Cost follows the number of boxes the
+    //          frustum touches — small when the tree is spatially coherent.
+    //   pass 1 (leaf marks; taken when pass 0 overflows its list, or first for small trees): test all primitives once, mark
+    //          the way from every reachable primitive up to the root (2 bits per node: left / right operand has something
+    //          below), then walk down along the marks only.  An operator with one marked side either stands for that side
+    //          (Union; Difference when it is the left one) or is gone (Difference without its left operand, Intersection) and
+    //          is skipped on the spot, so the list holds only operators with both sides marked, and primitives.
+    uint32_t* mk = reinterpret_cast<uint32_t*>(psm + kPruneWarps * sizeof(PruneWarpSmem)) + (size_t)warp * q.mark_words;
+    int total = 1, levels = 0;
+    bool overflow = true;
+    for (int pass = q.marks_first ? 1 : 0; pass < 2 && overflow; ++pass) {
+        if (pass == 1) {
+            if (q.mark_words == 0) break;           // tree too large for the marks
+            for (int i = lane; i < q.mark_words; i += 32) mk[i] = 0u;
+            __syncwarp();
+            // all primitives once, coalesced and several loads in flight: culling box (world space) + node number, 32 B each
+#pragma unroll 4
+            for (int k = lane; k < q.n_leaves; k += 32) {
+                const float4 la = __ldg(&q.leaf_boxes[2 * k]), lb4 = __ldg(&q.leaf_boxes[2 * k + 1]);
+                const float lo[3] = {la.x - ox, la.y - oy, la.z - oz}, hi[3] = {lb4.x - ox, lb4.y - oy, lb4.z - oz};
+                bool outside = false;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
+                                    fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
+                    outside = outside || (m < 0.0f);
+                }
+                if (outside) continue;
+                const int i = __float_as_int(la.w);
+                atomicOr(&mk[i >> 4], 1u << ((i & 15) * 2));
+                int c = i, par = __ldg(&q.parent[i]);
+                while (par >= 0) {                   // up to the root, or to a node somebody else already marked
+                    const int sh = (par & 15) * 2;
+                    const uint32_t old = atomicOr(&mk[par >> 4], (c == par + 1 ? 1u : 2u) << sh);
+                    if ((old >> sh) & 3u) break;
+                    c = par; par = __ldg(&q.parent[par]);
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) { w.lnode[0] = 0; w.lvl[0] = 0; }
+        __syncwarp();
+        int lb = 0, le = 1;
+        total = 1; levels = 0; overflow = false;
+        while (lb < le && !overflow) {
+            if (lane == 0) w.lvl[levels + 1] = (short)le;
+            int next_total = total;
+            for (int base = lb; base < le; base += 32) {
+                const int p = base + lane;
+                const bool have = p < le;
+                bool grow = false;
+                uint32_t meta = 0u;
+                int n = 0;
+                if (have) {
+                    n = w.lnode[p];
+                    bool outside = false;
+                    uint4 ua, ub;
+                    if (pass == 1) {
+                        for (;;) {
+                            meta = __ldg(&q.nodes[2 * n + 1]).w;
+                            const uint32_t kind = meta & 7u, m = (mk[n >> 4] >> ((n & 15) * 2)) & 3u;
+                            if (kind >= 3u) { outside = !(m & 1u); break; }
+                            if (m == 3u) break;
+                            if (m == 1u && kind != 2u) { n = n + 1; continue; }              // stands for its left operand
+                            if (m == 2u && kind == 0u) { n = (int)(meta >> 8); continue; }   // Union: stands for its right operand
+                            outside = true;
+                            break;
+                        }
+                        w.lnode[p] = n;
+                    }
+                    ua = __ldg(&q.nodes[2 * n]); ub = __ldg(&q.nodes[2 * n + 1]);
+                    meta = ub.w;
+                    float lo[3], hi[3];
+                    rel_cull_box(ua, ub, ox, oy, oz, lo, hi);
+                    if (pass == 0) {
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) {
+                            const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
+                                            fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
+                            outside = outside || (m < 0.0f);
+                        }
+                    }
+                    const uint32_t kind = meta & 7u;
+                    w.lkind[p] = (unsigned char)(kind | (outside ? 0u : 8u));
+                    w.lrep[p] = outside ? (short)-1 : (short)p;
+                    w.lsize[p] = 1;
+                    w.flg[p] = (unsigned char)(((kind == 3u || kind == 5u) ? 1u : 0u) | ((kind != 4u) ? 2u : 0u));
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { w.box[p][c] = lo[c]; w.box[p][3 + c] = hi[c]; }
+                    grow = !outside && kind < 3u;
+                }
+                const unsigned int mask = __ballot_sync(0xffffffffu, grow);
+                const int add = 2 * __popc(mask);
+                if (next_total + add > kListMax) { overflow = true; break; }
+                if (grow) {
+                    const int c = next_total + 2 * __popc(mask & lt);
+                    w.lnode[c] = n + 1;
+                    w.lnode[c + 1] = (int)(meta >> 8);
+                    w.lchild[p] = (short)c;
+                }
+                next_total += add;
+            }
+            __syncwarp();
+            lb = le; le = next_total; total = next_total;
+            if (++levels >= kLevelMax) overflow = true;
+        }
+    }
+    uint32_t kept = 0u, flags = 0u;
+    uint4* dst = q.pool + 2 * ((size_t)q.slots_off32 + (size_t)slot * S);
+    int r0 = -1;
+    if (!overflow) {
+        // ---- B. deepest level first: an operator stays (both operands matter: box over what is left, flags), collapses to
+        //         one operand, or goes
+        for (int d = levels - 1; d >= 0; --d) {
+            for (int p = w.lvl[d] + lane; p < w.lvl[d + 1]; p += 32) {
+                const uint32_t k = w.lkind[p];
+                if (!(k & 8u) || (k & 7u) >= 3u) continue;
+                const int c = w.lchild[p];
+                const int a = w.lrep[c], b = w.lrep[c + 1];
+                const uint32_t kind = k & 7u;
+                const int rp = kind == 0u ? (a < 0 ? b : (b < 0 ? a : p)) : kind == 1u ? (a < 0 ? -1 : (b < 0 ? a : p)) : ((a < 0 || b < 0) ? -1 : p);
+                w.lrep[p] = (short)rp;
+                if (rp != p) continue;
+                w.lsize[p] = (short)(1 + w.lsize[a] + w.lsize[b]);
+                const float* bl = w.box[a];
+                const float* br = w.box[b];
+                float* bo = w.box[p];
+                if (kind == 0u) {                   // Union: both operands
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; ++c2) { bo[c2] = fminf(bl[c2], br[c2]); bo[3 + c2] = fmaxf(bl[3 + c2], br[3 + c2]); }
+                } else if (kind == 1u) {            // Difference: a subset of the left operand
+#pragma unroll
+                    for (int c2 = 0; c2 < 6; ++c2) bo[c2] = bl[c2];
+                } else {                            // Intersection: a subset of both; the smaller box
+                    float vl = 1.f, vr = 1.f;
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; ++c2) { vl *= fmaxf(bl[3 + c2] - bl[c2], 0.f); vr *= fmaxf(br[3 + c2] - br[c2], 0.f); }
+                    const float* bs = vl <= vr ? bl : br;
+#pragma unroll
+                    for (int c2 = 0; c2 < 6; ++c2) bo[c2] = bs[c2];
+                }
+                const uint32_t fl = w.flg[a], fr = w.flg[b];
+                w.flg[p] = (unsigned char)(((kind == 0u) ? (fl & fr & 1u) : 0u) | (fl & fr & 2u));
+            }
+            __syncwarp();
+        }
+        r0 = w.lrep[0];
+        if (r0 >= 0) {
+            kept = (uint32_t)w.lsize[r0];
+            if (kept > (uint32_t)S) overflow = true;
+        }
+    }
+    if (!overflow && r0 >= 0) {
+        // ---- C. root first: preorder index of every survivor (left operand right after its operator, right operand after the
+        //         left subtree), and its record
+        if (lane == 0) { w.lidx[r0] = 0; w.lkind[r0] |= 16u; }
+        __syncwarp();
+        for (int d = 0; d < levels; ++d) {
+            for (int p = w.lvl[d] + lane; p < w.lvl[d + 1]; p += 32) {
+                const uint32_t k = w.lkind[p];
+                if (!(k & 16u)) continue;
+                const int i = w.lidx[p];
+                if ((k & 7u) >= 3u) {           // primitive: origin-relative record
+                    const int n = w.lnode[p];
+                    uint4 oa, ob;
+                    stage_record(__ldg(&q.nodes[2 * n]), __ldg(&q.nodes[2 * n + 1]), ox, oy, oz, oa, ob);
+                    dst[2 * i] = oa;
+                    dst[2 * i + 1] = ob;
+                    continue;
+                }
+                const int c = w.lchild[p];
+                const int ra = w.lrep[c], rb = w.lrep[c + 1];
+                const int r = i + 1 + w.lsize[ra];
+                w.lidx[ra] = (short)(i + 1);
+                w.lidx[rb] = (short)r;
+                w.lkind[ra] |= 16u;
+                w.lkind[rb] |= 16u;
+                const uint32_t f = w.flg[p];
+                const uint32_t meta = (k & 7u) | ((uint32_t)r << 8) | ((w.lkind[ra] & 7u) >= 3u ? kMetaLeftLeaf : 0u) |
+                                      ((w.lkind[rb] & 7u) >= 3u ? kMetaRightLeaf : 0u) | ((f & 2u) ? kMetaBounded : 0u) | ((f & 1u) ? kMetaPure : 0u);
+                const float* bo = w.box[p];
+                dst[2 * i] = make_uint4(__float_as_uint(bo[0]), __float_as_uint(bo[1]), __float_as_uint(bo[2]), __float_as_uint(bo[3]));
+                dst[2 * i + 1] = make_uint4(__float_as_uint(bo[4]), __float_as_uint(bo[5]), 0u, meta);
+            }
+            __syncwarp();
+        }
+        const uint32_t rk = w.lkind[r0] & 7u;
+        flags = (rk >= 3u ? kTileRootLeaf : 0u) | ((rk < 3u && (w.flg[r0] & 1u)) ? kTileRootPure : 0u);
+    }
+    // ---- descriptor; heavy tiles (more nodes) are handed out first by the frame kernel: bucket lists, then one ordered list
+    const uint32_t cost = overflow ? (uint32_t)min(N, 2 * kCostBuckets - 1) : kept;
+    const int bucket = (int)min(cost / 2u, (uint32_t)(kCostBuckets - 1));
+    if (lane == 0) {
+        q.desc[slot] = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
+                                : TileDesc{kept ? q.slots_off32 + (uint32_t)slot * (uint32_t)S : 0u, kept, flags, 0u};
+        if (q.order) {
+            const unsigned int rank = atomicAdd(&q.hist[bucket], 1u);
+            q.lists[(size_t)bucket * q.n_slots + rank] = (unsigned short)tile;
+            __threadfence();
+        }
+    }
+    if (!q.order) return;
+    unsigned int done = 0;
+    if (lane == 0) done = atomicAdd(q.done, 1u);
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done != (unsigned int)q.n_tiles - 1u) return;
+    // last warp of the grid: concatenate the bucket lists, heaviest bucket first, and reset the counters for the next frame
+    __threadfence();
+    static_assert(kCostBuckets == 64, "two buckets per lane");
+    unsigned int* start = reinterpret_cast<unsigned int*>(&w);   // the warp's own scratch is free now
+    {
+        // k = 63 - bucket: heaviest bucket first.  lane l owns k = l and k = 32 + l; start[k] = first position of bucket k in order[]
+        const unsigned int c0 = __ldcg(&q.hist[63 - lane]), c1 = __ldcg(&q.hist[31 - lane]);
+        unsigned int i0 = c0, i1 = c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+            if (lane >= o) { i0 += t0; i1 += t1; }
+        }
+        const unsigned int first_half = __shfl_sync(0xffffffffu, i0, 31);
+        start[lane] = i0 - c0;
+        start[32 + lane] = first_half + i1 - c1;
+    }
+    __syncwarp();
+    for (int b = lane; b < kCostBuckets; b += 32) q.hist[b] = 0u;
+    if (lane == 0) *q.done = 0u;
+    // every output position looks up its bucket (largest k with start[k] <= i): independent loads, several in flight per lane
+#pragma unroll 4
+    for (int i = lane; i < q.n_tiles; i += 32) {
+        int k = 0;
+#pragma unroll
+        for (int step = 32; step >= 1; step >>= 1)
+            if (k + step < kCostBuckets && start[k + step] <= (unsigned int)i) k += step;
+        q.order[i] = __ldcg(q.lists + (size_t)(63 - k) * q.n_slots + ((unsigned int)i - start[k]));
+    }
+}
+
+}  // namespace csgb

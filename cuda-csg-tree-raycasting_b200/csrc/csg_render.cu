@@ -1,4 +1,4 @@
-// csg_render.cu — frame kernel, launcher and the C ABI of libcsg_b200 (include/csg_b200.h).
+// csg_render.cu — launcher and the C ABI of libcsg_b200 (include/csg_b200.h); the kernels are in csg_frame.cuh / csg_prune.cuh.
 //
 // Replaces Raycaster::{ChangeSize,Raycast,CleanUp} (RayCasting/Raycaster.cu:3-45) and the two kernels it
 // launches (RayCasting/Kernels/RaycastingKernels.cu).  sm_100a only; there is no CPU path in this library.
@@ -16,889 +16,14 @@
 
 #include "../../include/csg_b200.h"
 #include "csg_kernel.cuh"
+#include "csg_frame.cuh"
+#include "csg_prune.cuh"
 #include "csg_scene.h"
 
 using namespace csgb;
 
 // =========================================================================================== device code
 namespace csgb {
-
-// CTA shapes the frame kernel is compiled for.  All three keep 24 warps per SM at <= 80 registers/thread
-// (768 threads x 80 registers x 1 CTA, 384 x 2, 256 x 3 all fill the 64K-register file); they differ in how many copies
-// of the staged tree and how much stack an SM holds.  The launcher picks the shape with the most resident warps for the
-// scene at hand, the largest CTA on ties (one tree copy per SM).
-constexpr int kShapes = 3;
-constexpr int kShapeThreads[kShapes] = {768, 384, 256};
-constexpr int min_blocks_for(int threads) { return threads >= 768 ? 1 : threads >= 384 ? 2 : 3; }
-constexpr int kWarpTileW = 8, kWarpTileH = 4;   // one warp = one 8x4 pixel tile (Raycaster.cuh:7-8 uses the same shape)
-constexpr int kMacroW = 64, kMacroH = 32;       // sharding unit: 8x8 warp tiles
-
-// Hit details + Phong (sphere/cylinder/cubeHitDetails :183-200/:338-372/:436-457 and LightningKernel :49-111).
-__device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const float4* __restrict__ prims, const FrameParams& p, const float* __restrict__ s_light)
-{
-    if (is_miss(res)) return make_float4(0.08f, 0.08f, 0.11f, 1.0f);   // :109
-    const uint32_t id = (res.m & H_META_MASK) >> H_ID_SHIFT;
-    const uint32_t kind = (res.m >> H_KIND_SHIFT) & 7u;
-    const float4 col = __ldg(&prims[id * 5 + 0]);
-    const float4 pc = __ldg(&prims[id * 5 + 1]);
-    const float t = res.t;
-    const float px = __fmaf_rn(t, r.dx, r.ox), py = __fmaf_rn(t, r.dy, r.oy), pz = __fmaf_rn(t, r.dz, r.oz);
-    float nx, ny, nz;
-    if (kind == 3u) {                                   // sphereHitDetails :189-195
-        nx = px - pc.x; ny = py - pc.y; nz = pz - pc.z;
-    } else if (kind == 5u) {                            // cubeHitDetails :446-451
-        const float bias = 1.00001f;
-        nx = (float)__float2int_rz(__fmul_rn(__fdiv_rn(px - pc.x, pc.w), bias));
-        ny = (float)__float2int_rz(__fmul_rn(__fdiv_rn(py - pc.y, pc.w), bias));
-        nz = (float)__float2int_rz(__fmul_rn(__fdiv_rn(pz - pc.z, pc.w), bias));
-    } else {                                            // cylinderHitDetails :345-365
-        const float4 pb = __ldg(&prims[id * 5 + 2]);
-        const float4 pv = __ldg(&prims[id * 5 + 3]);
-        if (res.m & H_FLAG1) { nx = -pv.x; ny = -pv.y; nz = -pv.z; }
-        else if (res.m & H_FLAG2) { nx = pv.x; ny = pv.y; nz = pv.z; }
-        else {
-            const float ocx = r.ox - pb.x, ocy = r.oy - pb.y, ocz = r.oz - pb.z;
-            const float dV = dot_ref(pv.x, pv.y, pv.z, r.dx, r.dy, r.dz);
-            const float ocv = dot_ref(pv.x, pv.y, pv.z, ocx, ocy, ocz);
-            const float m = __fmaf_rn(t, dV, ocv);
-            nx = __fmaf_rn(-pv.x, m, px - pb.x);
-            ny = __fmaf_rn(-pv.y, m, py - pb.y);
-            nz = __fmaf_rn(-pv.z, m, pz - pb.z);
-        }
-    }
-    if (!((res.m & (H_FLAG1 | H_FLAG2)) && kind == 4u)) {   // caps carry the unit axis as is; everything else is normalised
-        const float inv = __frcp_rn(__fsqrt_rn(dot_ref(nx, ny, nz, nx, ny, nz)));
-        nx *= inv; ny *= inv; nz *= inv;
-    }
-    if (res.m & H_FLIP) { nx = -nx; ny = -ny; nz = -nz; }
-    if ((res.m & H_CLS) == H_EXIT) { nx = -nx; ny = -ny; nz = -nz; }
-
-    // LightningKernel :78-103
-    const float Lx = s_light[0], Ly = s_light[1], Lz = s_light[2];   // normalize(lightDir), once per CTA
-    float vx = p.cam_pos[0] - px, vy = p.cam_pos[1] - py, vz = p.cam_pos[2] - pz;
-    const float iv = __frcp_rn(__fsqrt_rn(dot_ref(vx, vy, vz, vx, vy, vz)));
-    vx *= iv; vy *= iv; vz *= iv;
-    const float in = __frcp_rn(__fsqrt_rn(dot_ref(nx, ny, nz, nx, ny, nz)));   // reflect() re-normalises n
-    const float ux = nx * in, uy = ny * in, uz = nz * in;
-    const float dn = __fmaf_rn(-Lz, uz, __fmaf_rn(-Lx, ux, uy * -Ly));
-    const float two = dn + dn;
-    const float rx = __fmaf_rn(-ux, two, -Lx), ry = __fmaf_rn(-uy, two, -Ly), rz = __fmaf_rn(-uz, two, -Lz);
-    const float diff = fmaxf(dot_ref(nx, ny, nz, Lx, Ly, Lz), 0.0f);
-    const float sb = fmaxf(dot_ref(vx, vy, vz, rx, ry, rz), 0.0f);
-    const float spec = powf(sb, 30.0f);
-    const float k = __fmaf_rn(spec, 0.7f, __fmaf_rn(diff, 0.8f, 0.2f));
-    float4 o;
-    o.x = fminf(fmaxf(col.x * k, 0.0f), 1.0f);
-    o.y = fminf(fmaxf(col.y * k, 0.0f), 1.0f);
-    o.z = fminf(fmaxf(col.z * k, 0.0f), 1.0f);
-    o.w = 1.0f;
-    return o;
-}
-
-__device__ __forceinline__ uint32_t to_u8(float c)
-{  // Q12: (int)(clamp(c,0,1)*255 + 0.5)
-    return (uint32_t)__float2int_rz(__fadd_rn(__fmul_rn(fminf(fmaxf(c, 0.0f), 1.0f), 255.0f), 0.5f));
-}
-
-// CSGRayCast (RaycastingKernels.cu:459-512) re-expressed as an explicit-frame evaluation; equivalence with the
-// reference's GoTo/Compute/SaveLft action machine is argued in DESIGN.md §"State machine".
-//
-// One 16-byte frame per operator on the current path, in shared memory ([level][thread]):
-//   x = saved tmin (F_FIRST_*) or saved hit t (F_LOAD_*),  y = saved hit meta | return state,
-//   z = F_FIRST_*: lower bound of the pending sibling's hits (prune test),  w = byte offset of the operator's record.
-//
-// Additions over the reference's traversal order, all result-preserving (DESIGN.md §"Culling contract"):
-//   * a Union evaluates the child whose box the ray enters first; Difference/Intersection keep left-first;
-//   * when the first child returns a hit at t and the pending sibling's box starts beyond t, the sibling cannot change
-//     the outcome (Union: every cell with a farther Enter or a Miss on the other side returns this hit; Difference: same
-//     for the right operand) and is skipped;
-//   * nearest-Enter search (ST_SEARCH): a "pure" subtree (Unions over spheres/cubes only) whose box lies ahead of tmin is
-//     evaluated as a closest-hit BVH search with a shrinking limit instead of the frame machine.  With every leaf result an
-//     Enter or a Miss, each Union of the subtree returns the nearer Enter (EE lt/gt, EM, ME cells), i.e. the subtree returns
-//     its globally nearest Enter; the search aborts — and the subtree is re-evaluated by the frame machine — as soon as a
-//     leaf reports an Exit or two leaves tie for the nearest hit (the only inputs on which the cells differ from "min").
-//     The limit starts at the hit already known on the other side of the parent when every farther Enter (or a Miss) of
-//     this side gives the same parent outcome (Union either side, Difference right side): such results are equivalent, so
-//     subtrees beyond the limit need not be looked at.
-constexpr uint32_t kSearchMark = 0xfffffffeu;
-
-template <bool COUNT>
-__device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, const float4* __restrict__ prims,
-                                        const uint32_t* __restrict__ table, const uint32_t stack,
-                                        const uint32_t stack_stride, const Ray& r, const bool root_is_leaf, const bool root_pure, const bool root_gated, int& iters)
-{
-    enum { ST_ENTER = 0, ST_SEARCH = 1, ST_LOOPL = 2, ST_LOOPR = 3, ST_COMPUTE = 4, ST_RETURN = 5, ST_DONE = 6 };
-    Hit L = make_miss(), R = make_miss();      // ST_SEARCH: L = nearest Enter so far, R.t = limit
-    float tmin = 0.0f;                        // :466
-    if (root_is_leaf) {
-        // The scene's root is a primitive: GoTo's leaf branch on the virtual root, no box test (:582-594, Q7).
-        // A pruned tile tree that collapsed to one primitive (root_gated): the primitive is still reached through its
-        // operators in the reference, so a cylinder keeps its gating box (Q6).
-        bool go;
-        float tn;
-        uint32_t cm;
-        eval_child(tree, prims, 0u, r, tmin, root_gated, L, go, tn, cm);
-        return L;
-    }
-    uint32_t n = 0u;                           // byte offset of the current operator's record
-    uint32_t sp = stack;                       // next free frame (shared-memory address; stack_stride = bytes between levels)
-    sts128(sp, make_uint4(0u, 0u, 0u, 0xffffffffu)); // sentinel frame: popping it ends the traversal (no base pointer to keep)
-    sp += stack_stride;
-    int st = ST_ENTER;
-    if (root_pure) {                           // the whole scene is one pure subtree
-        sts128(sp, make_uint4(0u, 0u, 0u, kSearchMark));
-        sp += stack_stride;
-        R.t = INFINITY;
-        st = ST_SEARCH;
-    }
-    while (st != ST_DONE) {
-        if (COUNT) iters += (st == ST_SEARCH) ? (1 << 20) : (st == ST_ENTER) ? (1 << 10) : 1;   // packed: search visits | frame-machine visits | other iterations
-        if (st <= ST_LOOPR) {
-            const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
-            const uint32_t op = meta & 7u;
-            const uint32_t cl = n + 32u, cr = (meta >> 8) << 5;
-            Hit a = make_miss(), b = make_miss();
-            bool goA = false, goB = false;
-            float tnA = -INFINITY, tnB = -INFINITY;
-            uint32_t mA = 0u, mB = 0u;
-            if (st != ST_LOOPR) eval_child(tree, prims, cl, r, tmin, st <= ST_SEARCH, a, goA, tnA, mA);
-            if (st == ST_ENTER && op != 0u && !goA && is_miss(a)) {
-                // left operand of a Difference/Intersection already missed: the node's result is Miss whatever the right
-                // operand does (all M* cells of both tables, :670-677) — skip the right subtree (Q8)
-                L = a; R = a;
-                st = ST_RETURN;
-            } else {
-                if (st != ST_LOOPL) eval_child(tree, prims, cr, r, tmin, st <= ST_SEARCH, b, goB, tnB, mB);
-                if (st == ST_LOOPL) { L = a; st = ST_COMPUTE; }
-                else if (st == ST_LOOPR) { R = b; st = ST_COMPUTE; }
-                else if (st == ST_SEARCH) {
-                    // leaf results are candidates; an Exit or a tie for the nearest hit ends the search
-                    bool abort = false;
-                    float lim = R.t;
-                    if (!is_miss(a)) {
-                        if ((a.m & H_CLS) == H_EXIT) abort = true;
-                        else if (a.t < lim) { L = a; lim = a.t; }
-                        else if (a.t == lim) { if (is_miss(L)) L = a; else abort = true; }
-                    }
-                    if (!is_miss(b)) {
-                        if ((b.m & H_CLS) == H_EXIT) abort = true;
-                        else if (b.t < lim) { L = b; lim = b.t; }
-                        else if (b.t == lim) { if (is_miss(L)) L = b; else abort = true; }
-                    }
-                    R.t = lim;
-                    if (abort) {                 // back to the subtree's root, this time through the frame machine
-                        uint4 f;
-                        do { sp -= stack_stride; f = lds128(sp); } while (f.w != kSearchMark);
-                        n = f.z; st = ST_ENTER;
-                    } else {
-                        goA = goA && !(tnA > lim);
-                        goB = goB && !(tnB > lim);
-                        if (goA && goB) {
-                            const bool right_first = tnB < tnA;
-                            sts128(sp, make_uint4(__float_as_uint(right_first ? tnA : tnB), 0u, 0u, right_first ? cl : cr));
-                            sp += stack_stride; n = right_first ? cr : cl;
-                        } else if (goA) { n = cl; }
-                        else if (goB) { n = cr; }
-                        else {
-                            for (;;) {
-                                sp -= stack_stride;
-                                const uint4 f = lds128(sp);
-                                if (f.w == kSearchMark) { R = L; st = ST_RETURN; break; }   // the subtree's result: nearest Enter or Miss
-                                if (!(__uint_as_float(f.x) > lim)) { n = f.w; break; }
-                            }
-                        }
-                    }
-                } else {
-                    L = a; R = b;
-                    // sibling pruning against a leaf hit that is already known
-                    if (op != 2u) {
-                        if (goB && !goA && !is_miss(L) && tnB > L.t) goB = false;
-                        if (op == 0u && goA && !goB && !is_miss(R) && tnA > R.t) goA = false;
-                    }
-                    if (!goA && !goB) {
-                        st = ST_COMPUTE;                                                   // :578
-                    } else {
-                        uint32_t first, fm;   // subtree to descend into now, and its meta word
-                        float ftn, lim = INFINITY;
-                        if (!goA) {                                                        // :556-561
-                            sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n));
-                            first = cr; fm = mB; ftn = tnB;
-                            if (op != 2u && !is_miss(L)) lim = L.t;
-                        } else if (!goB) {                                                 // :562-567
-                            sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n));
-                            first = cl; fm = mA; ftn = tnA;
-                            if (op == 0u && !is_miss(R)) lim = R.t;
-                        } else {                                                           // :568-574
-                            const bool right_first = (op == 0u) && (tnB < tnA);
-                            const uint32_t pend_pure = ((right_first ? mA : mB) >> 6) & 1u;
-                            sts128(sp, make_uint4(__float_as_uint(tmin), (right_first ? F_FIRST_RGH : F_FIRST_LFT) | pend_pure,
-                                             __float_as_uint(right_first ? tnA : tnB), n));
-                            first = right_first ? cr : cl; fm = right_first ? mB : mA; ftn = right_first ? tnB : tnA;
-                        }
-                        sp += stack_stride; n = first;
-                        if ((fm & kMetaPure) && ftn > tmin) {   // pure subtree ahead of tmin: nearest-Enter search
-                            sts128(sp, make_uint4(0u, 0u, first, kSearchMark));
-                            sp += stack_stride;
-                            L = make_miss(); R.t = lim; st = ST_SEARCH;
-                        }
-                    }
-                }
-            }
-        }
-        if (st == ST_COMPUTE) {                                                        // Compute :597-661
-            const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
-            const uint32_t op = meta & 7u;
-            const uint32_t e = table[op * 9u + (L.m & H_CLS) * 3u + (R.m & H_CLS)];
-            const uint32_t o = (L.t < R.t) ? (e & 7u) : (L.t > R.t) ? ((e >> 3) & 7u) : ((e >> 6) & 7u);
-            if (o == O_RETL) { R = L; st = ST_RETURN; }
-            else if (o == O_RETR || o == O_RETR_FLIP) {
-                if (o == O_RETR_FLIP) R.m ^= (H_FLIP | 1u);                            // :629-635 toggles Flip and Enter<->Exit
-                L = R; st = ST_RETURN;
-            } else if (o == O_LOOPL) {                                                 // :640-646
-                tmin = L.t;
-                if (meta & kMetaLeftLeaf) st = ST_LOOPL;
-                else { sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride; n = n + 32u; st = ST_ENTER; }
-            } else if (o == O_LOOPR) {                                                 // :647-653
-                tmin = R.t;
-                if (meta & kMetaRightLeaf) st = ST_LOOPR;
-                else { sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride; n = (meta >> 8) << 5; st = ST_ENTER; }
-            } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
-        }
-        if (st == ST_RETURN) {                  // action = actionStack.pop(); node = GetParent() (:624-625 etc.); L == R == result
-            sp -= stack_stride;
-            const uint4 f = lds128(sp);
-            if (f.w == 0xffffffffu) { st = ST_DONE; }
-            else {
-                n = f.w;
-                const uint32_t ret = f.y & F_RET_MASK;
-                if (ret == F_LOAD_LFT) {        // :611-614
-                    L.t = __uint_as_float(f.x); L.m = f.y & H_META_MASK; st = ST_COMPUTE;
-                } else if (ret == F_LOAD_RGH) { // :615-618
-                    R.t = __uint_as_float(f.x); R.m = f.y & H_META_MASK; st = ST_COMPUTE;
-                } else {                        // SaveLft :476-481: restore tmin, keep the first result, evaluate the sibling
-                    tmin = __uint_as_float(f.x);
-                    const uint32_t pm = *reinterpret_cast<const uint32_t*>(tree + n + 28);
-                    const uint32_t pop = pm & 7u;
-                    const bool miss = is_miss(L);
-                    const float ptn = __uint_as_float(f.z);     // entry distance of the pending sibling's box (-inf: not a bound)
-                    if (miss ? (pop != 0u) : (pop != 2u && ptn > L.t)) {
-                        // Difference/Intersection whose left operand missed -> Miss; or the sibling lies beyond this hit -> this hit.
-                        // Either way the node's result is what L == R already hold; stay in ST_RETURN.
-                    } else {
-                        uint32_t sib;
-                        if (ret == F_FIRST_LFT) {
-                            sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n));
-                            sib = (pm >> 8) << 5;
-                        } else {
-                            sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n));
-                            sib = n + 32u;
-                        }
-                        sp += stack_stride; n = sib; st = ST_ENTER;
-                        if ((f.y & 1u) && ptn > tmin) {
-                            const float lim = (pop != 2u && !miss) ? L.t : INFINITY;
-                            sts128(sp, make_uint4(0u, 0u, sib, kSearchMark));
-                            sp += stack_stride;
-                            L = make_miss(); R.t = lim; st = ST_SEARCH;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    return L;                                   // :511
-}
-
-template <int MODE, int kThreads, bool kSuper>   // kSuper: more than one ray per pixel (keeps the sample loop and its accumulators out of the common case)
-__global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_kernel(const __grid_constant__ FrameParams p)
-{
-    // shared memory: [outcome table 128 B][stack: (levels+2) x kThreads x 16 B][per-warp tree copy: warp_tree_nodes x 32 B].
-    // Every 64x32-pixel macro tile has its own pruned, origin-relative tree (csg_prune_kernel), a few hundred bytes to a few
-    // KB; a warp copies the tree of its current tile into shared memory when it fits, and reads it through L1 otherwise.
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* s_table = reinterpret_cast<uint32_t*>(smem_raw);
-    uint4* s_stack = reinterpret_cast<uint4*>(smem_raw + 128);
-
-    const int tid = threadIdx.x, lane = tid & 31;
-    const float ox = p.cam_pos[0], oy = p.cam_pos[1], oz = p.cam_pos[2];
-
-    if (tid < 27) s_table[tid] = kOutcomeTable[tid];
-    if (tid == 27) {   // L = normalize(lightDir), LightningKernel :78: the same for every pixel of the frame
-        const float il = __frcp_rn(__fsqrt_rn(dot_ref(p.light[0], p.light[1], p.light[2], p.light[0], p.light[1], p.light[2])));
-        float* s_light = reinterpret_cast<float*>(s_table + 28);
-        s_light[0] = p.light[0] * il; s_light[1] = p.light[1] * il; s_light[2] = p.light[2] * il;
-    }
-    __syncthreads();
-    const uint32_t my_stack = (uint32_t)__cvta_generic_to_shared(s_stack + tid);   // frames are addressed in the shared window: 32-bit
-    // per-warp copy of the current tile's tree (when it fits): traversal then reads shared memory instead of L1/L2
-    const uint32_t my_tree_off = 128u + 16u * (uint32_t)((p.stack_levels + 2) * kThreads + (tid >> 5) * (2 * p.warp_tree_nodes));   // bytes from smem_raw
-    const float* s_light = reinterpret_cast<const float*>(s_table + 28);
-
-    // per-frame constants of ray generation, RaycastKernel :11-16
-    // Per-frame constants of ray generation (RaycastKernel :11-16) arrive precomputed in the parameter block (wm1 = w-1,
-    // hm1 = h-1, aspect = w/h: single IEEE operations, identical on the host; tan(fov/2) from the device, see csg_tan_kernel).
-    // With supersampling (ss samples per axis) they describe the virtual (width*ss) x (height*ss) grid: sub-sample (sx,sy)
-    // of pixel (x,y) is virtual pixel (x*ss+sx, y*ss+sy), SURVEY.md §8(d) row 5.
-    const int ss = kSuper ? p.ss : 1;
-
-    // ---- phase 1: macro tiles entirely outside the screen-space bound of the scene are Miss everywhere (:109): fill them
-    // with the background, statically partitioned over the warps of this shard (no traversal, no tickets).
-    {
-        const int warps_per_cta = kThreads / 32;
-        const int gw = blockIdx.x * warps_per_cta + (tid >> 5), GW = gridDim.x * warps_per_cta;
-        const int total_macros = p.macro_x * p.macro_y;
-        // fill_stride/fill_first: a single GPU or the root of a sharded frame fills every background tile itself (local
-        // stores); the other shards fill none — only traced pixels cross NVLink
-        for (int m = gw * p.fill_stride + p.fill_first; m < total_macros; m += GW * p.fill_stride) {
-            const int my = p.div_magic ? (int)__umulhi((unsigned int)m, p.div_magic) : m / p.macro_x;
-            const int mx = m - my * p.macro_x;
-            if (my < p.band_m0 || my >= p.band_m1) continue;                                                   // another band of this frame
-            if (mx >= p.rm_x0 && mx < p.rm_x0 + p.rm_w && my >= p.rm_y0 && my < p.rm_y0 + p.rm_h) continue;   // traced in phase 2
-            const int x0 = mx * kMacroW, y0 = my * kMacroH;
-            if (MODE == OUT_RGBA8 && (p.width & 3) == 0) {
-                const uint32_t bg = 20u | (20u << 8) | (28u << 16) | 0xFF000000u;   // (0.08,0.08,0.11,1) quantised per Q12
-                const int x = x0 + (lane & 15) * 4;
-#pragma unroll 4
-                for (int r = lane >> 4; r < kMacroH; r += 2) {
-                    const int y = y0 + r;
-                    if (x < p.width && y < p.height) reinterpret_cast<uint4*>(p.out)[((size_t)y * p.width + x) >> 2] = make_uint4(bg, bg, bg, bg);
-                }
-            } else {
-                for (int r = 0; r < kMacroH; ++r) {
-                    const int y = y0 + r;
-                    if (y >= p.height) break;
-                    for (int cx = lane; cx < kMacroW; cx += 32) {
-                        const int x = x0 + cx;
-                        if (x >= p.width) continue;
-                        const size_t pix = (size_t)y * p.width + x;
-                        if (MODE == OUT_RGBA8) reinterpret_cast<uint32_t*>(p.out)[pix] = 20u | (20u << 8) | (28u << 16) | 0xFF000000u;
-                        else if (MODE == OUT_F32) reinterpret_cast<float4*>(p.out)[pix] = make_float4(0.08f, 0.08f, 0.11f, 1.0f);
-                        else {
-                            if (p.aov_hit) p.aov_hit[pix] = 0;
-                            if (p.aov_prim) p.aov_prim[pix] = -1;
-                            if (p.aov_t) p.aov_t[pix] = -1.0f;
-                            if (p.aov_iters) p.aov_iters[pix] = 0;
-                        }
-                    }
-                }
-            }
-        }
-    }
-
-    // everything below reads what csg_prune_kernel wrote (tile descriptors, pruned trees, hand-out order)
-    cudaGridDependencySynchronize();
-
-    // ---- phase 2: dynamic tile scheduling over the macro tiles that touch the bound: one ticket per warp tile; the next
-    // ticket is requested before the current tile is rendered so the atomic's round trip hides behind the traversal.
-    // Ticket t -> macro tile number (t >> 6) * shard_count + shard_rank of the rm_w x rm_h macro rectangle, warp tile t & 63.
-    unsigned int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u) - p.counter_base;
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    // Supersampling with 4 or 16 rays per pixel (sp = log2 of that): the samples of a pixel sit in neighbouring lanes instead
-    // of being looped over by one lane: a warp pass covers 8 / 2 pixels of one row with one ray per lane, and a warp tile is
-    // 4 / 16 such passes, handed out in tickets of 1 << gp passes each — so a heavy pixel does not serialise 16 traversals in
-    // one warp, and the per-ticket set-up (descriptor, tree copy) is still shared by a few passes.
-    const int sp = kSuper ? p.sp_shift : 0, gp = kSuper ? p.sp_group : 0;
-    while (ticket < (unsigned int)p.n_local_warp_tiles) {
-        const unsigned int cur = ticket >> (sp - gp);
-        const int pass0 = (int)(ticket & ((1u << (sp - gp)) - 1u)) << gp;
-        unsigned int next = 0;
-        if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
-        const int k = (int)(cur & 63u);
-        // traced tiles are handed out heaviest first (order[] from csg_prune_kernel: tiles whose pruned tree is larger come
-        // first, so that the expensive tiles are not the ones still running when the ticket counter runs dry)
-        const int tile_no = p.order ? (int)__ldg(p.order + (cur >> 6)) : (int)(cur >> 6);
-        const int j = tile_no * p.shard_count + p.shard_rank;
-        // j / rm_w by multiply-high with a host-computed reciprocal (exact for the ranges the host enables it for)
-        const int jy = p.rm_magic ? (int)__umulhi((unsigned int)j, p.rm_magic) : j / p.rm_w;
-        const int mx = p.rm_x0 + (j - jy * p.rm_w), my = p.rm_y0 + jy;
-        const int kx = (k & 1) | ((k >> 1) & 2) | ((k >> 2) & 4);        // Morton order inside the macro tile
-        const int ky = ((k >> 1) & 1) | ((k >> 2) & 2) | ((k >> 3) & 4);
-        const int tx0 = mx * kMacroW + kx * kWarpTileW, ty0 = my * kMacroH + ky * kWarpTileH;   // the warp tile's corner
-        ticket = 0xffffffffu;   // placeholder; the real value is broadcast at the end of the iteration
-        if (tx0 >= p.width || ty0 >= p.height) { ticket = __shfl_sync(0xffffffffu, next, 0); continue; }
-
-        // this macro tile's pruned tree (csg_prune_kernel): only the primitives its rays can reach, operators whose other
-        // operand cannot be reached collapsed away.  n_nodes == 0: every ray of the tile is a Miss.
-        const int slot = p.shard_shift >= 0 ? (my * p.macro_x + mx) >> p.shard_shift : (my * p.macro_x + mx) / p.shard_count;
-        const uint4 td = p.desc ? __ldg(reinterpret_cast<const uint4*>(p.desc) + slot) : make_uint4(0u, (uint32_t)p.n_nodes, p.full_flags, 0u);
-        const unsigned char* tree = reinterpret_cast<const unsigned char*>(p.pool + 2 * (size_t)td.x);
-        if (td.y != 0u && td.y <= (uint32_t)p.warp_tree_nodes) {
-            uint4* my_tree = reinterpret_cast<uint4*>(smem_raw + my_tree_off);
-            __syncwarp();   // everybody is done with the previous tile's copy
-            for (uint32_t i = lane; i < 2u * td.y; i += 32u) my_tree[i] = __ldg(p.pool + 2 * (size_t)td.x + i);
-            __syncwarp();
-            tree = reinterpret_cast<const unsigned char*>(my_tree);
-        }
-        // whole warp tile outside the screen-space bound of the root box: every ray is a Miss (:109 background colour)
-        const bool tile_empty = td.y == 0u || tx0 > p.rect_x1 || tx0 + (kWarpTileW - 1) < p.rect_x0 || ty0 > p.rect_y1 || ty0 + (kWarpTileH - 1) < p.rect_y0;
-
-#pragma unroll 1
-        for (int pass = pass0; pass < pass0 + (1 << gp); ++pass) {
-            int x = tx0, y = ty0;   // this lane's pixel
-            if (sp == 0) { x += lane & 7; y += lane >> 3; }
-            else {   // 32 >> sp pixels of one row per pass, 1 << sp lanes per pixel
-                const int ppw = 32 >> sp, lg = sp > 2 ? sp - 2 : 0;   // 8 / ppw = 1 << lg passes per row of the warp tile
-                x += (pass & ((1 << lg) - 1)) * ppw + (lane >> sp);
-                y += pass >> lg;
-            }
-            const bool active = x < p.width && y < p.height;
-            const uint32_t pix = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;   // :33 (csg_upload keeps width*height below 2^31)
-            if (__ballot_sync(0xffffffffu, active) == 0u) continue;
-
-            Hit res = make_miss();
-            int iters = 0;
-            Ray r;
-            r.ox = ox; r.oy = oy; r.oz = oz;
-            float accx = 0.f, accy = 0.f, accz = 0.f;
-            if (tile_empty) {
-                const float w = (float)(ss * ss);
-                accx = 0.08f * w; accy = 0.08f * w; accz = 0.11f * w;
-            } else if (active) {
-                const int n_samples = sp ? 1 : ss * ss;
-#pragma unroll 1
-                for (int s = 0, sx = sp ? ((lane & ((1 << sp) - 1)) & (ss - 1)) : 0, sy = sp ? ((lane & ((1 << sp) - 1)) >> (sp >> 1)) : 0; s < n_samples; ++s) {
-                    const int vx = x * ss + sx, vy = y * ss + sy;
-                    if (++sx == ss) { sx = 0; ++sy; }
-                    // RaycastKernel :11-27 + Ray ctor (Ray.cuh:12-18)
-                    const float u = __fdiv_rn(__fadd_rn((float)vx, 0.5f), p.wm1);
-                    const float v = __fdiv_rn(__fadd_rn((float)vy, 0.5f), p.hm1);
-                    const float nx = __fmul_rn(__fmul_rn(p.aspect, __fmaf_rn(u, 2.0f, -1.0f)), p.tan_half_fov);
-                    const float ny = __fmul_rn(__fsub_rn(1.0f, __fadd_rn(v, v)), p.tan_half_fov);
-                    float cx = __fadd_rn(p.forward[0], __fmaf_rn(p.right[0], nx, __fmul_rn(p.up[0], ny)));
-                    float cy = __fadd_rn(p.forward[1], __fmaf_rn(p.right[1], nx, __fmul_rn(p.up[1], ny)));
-                    float cz = __fadd_rn(p.forward[2], __fmaf_rn(p.right[2], nx, __fmul_rn(p.up[2], ny)));
-#pragma unroll
-                    for (int rep = 0; rep < 2; ++rep) {   // normalize() then the Ray ctor normalises again (Q3)
-                        const float inv = __frcp_rn(__fsqrt_rn(dot_ref(cx, cy, cz, cx, cy, cz)));
-                        cx = __fmul_rn(inv, cx); cy = __fmul_rn(inv, cy); cz = __fmul_rn(inv, cz);
-                    }
-                    r.dx = cx; r.dy = cy; r.dz = cz;
-                    r.ix = rcp_approx(cx); r.iy = rcp_approx(cy); r.iz = rcp_approx(cz);   // culling boxes only: they carry 1e-5 of slack
-                    res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u,
-                                                    (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
-                    if (MODE != OUT_AOV) {
-                        const float4 c = shade_pixel(res, r, p.prims, p, s_light);
-                        accx += c.x; accy += c.y; accz += c.z;
-                    }
-                }
-            }
-
-            if (MODE == OUT_AOV) {
-                if (active) {
-                    const bool hit = !is_miss(res);
-                    if (p.aov_hit) p.aov_hit[pix] = hit ? 1 : 0;
-                    if (p.aov_prim) p.aov_prim[pix] = hit ? (int32_t)((res.m & H_META_MASK) >> H_ID_SHIFT) : -1;
-                    if (p.aov_t) p.aov_t[pix] = hit ? res.t : -1.0f;
-                    if (p.aov_iters) p.aov_iters[pix] = iters;
-                }
-            } else {
-                if (kSuper && sp && !tile_empty) {
-                    // sum the pixel's samples in sample order (the order of the one-lane loop), in every lane of the pixel
-                    const int base = lane & ~((1 << sp) - 1);
-                    float sxr = 0.f, syr = 0.f, szr = 0.f;
-                    for (int s = 0; s < (1 << sp); ++s) {
-                        sxr += __shfl_sync(0xffffffffu, accx, base + s);
-                        syr += __shfl_sync(0xffffffffu, accy, base + s);
-                        szr += __shfl_sync(0xffffffffu, accz, base + s);
-                    }
-                    accx = sxr; accy = syr; accz = szr;
-                }
-                float4 c = make_float4(accx, accy, accz, 1.0f);
-                if (ss > 1) {   // box filter of the linear colour
-                    const float w = __frcp_rn((float)(ss * ss));
-                    c.x *= w; c.y *= w; c.z *= w;
-                }
-                if (kSuper && sp) {   // one lane per pixel stores
-                    if (active && (lane & ((1 << sp) - 1)) == 0) {
-                        if (MODE == OUT_F32) reinterpret_cast<float4*>(p.out)[pix] = c;
-                        else reinterpret_cast<uint32_t*>(p.out)[pix] = to_u8(c.x) | (to_u8(c.y) << 8) | (to_u8(c.z) << 16) | 0xFF000000u;
-                    }
-                } else if (MODE == OUT_F32) {
-                    if (active) reinterpret_cast<float4*>(p.out)[pix] = c;
-                } else {
-                    const uint32_t px8 = to_u8(c.x) | (to_u8(c.y) << 8) | (to_u8(c.z) << 16) | 0xFF000000u;
-                    // four horizontally adjacent pixels -> one 16-byte store
-                    const uint32_t p1 = __shfl_down_sync(0xffffffffu, px8, 1);
-                    const uint32_t p2 = __shfl_down_sync(0xffffffffu, px8, 2);
-                    const uint32_t p3 = __shfl_down_sync(0xffffffffu, px8, 3);
-                    if ((p.width & 3) == 0) {
-                        if (active && (lane & 3) == 0) reinterpret_cast<uint4*>(p.out)[pix >> 2] = make_uint4(px8, p1, p2, p3);
-                    } else if (active) {
-                        reinterpret_cast<uint32_t*>(p.out)[pix] = px8;
-                    }
-                }
-            }
-        }
-        ticket = __shfl_sync(0xffffffffu, next, 0);
-    }
-}
-
-// tan(cam.fov / 2.0f) of RaycastKernel :15-16, evaluated with the device tanf once per field of view (kept out of
-// the frame kernel: tanf's large-argument path needs a local-memory scratch array).
-__global__ void csg_tan_kernel(float fov, float* out) { *out = tanf(__fmul_rn(fov, 0.5f)); }
-
-// ---- per-tile tree pruning ---------------------------------------------------------------------------------------------
-// One CTA per traced macro tile builds the tile's own tree: a primitive whose culling box lies outside the tile's frustum
-// (the 64x32 pixels plus a margin of one pixel) is a Miss for every ray of the tile, whatever tmin; an operator with such an
-// operand behaves exactly like its other operand (Union: [x][M] -> RetL, [M][x] -> RetR; Difference: [x][M] -> RetL) or is a
-// Miss itself (Difference without its left operand, Intersection without either: all M* cells, RaycastingKernels.cu:666-677),
-// without ever looping — so dropping those primitives and collapsing those operators changes no result.  The surviving
-// nodes are written in preorder, origin-relative (the subtractions of isBVHNodeHit :724-729, cubeHit :389-394 and
-// sphereHit :139-143 are done here once per node and tile instead of once per ray: same single FADD, same bits), with
-// operator boxes recomputed over what is left.
-__device__ __forceinline__ void stage_record(const uint4 ua, const uint4 ub, float ox, float oy, float oz, uint4& oa, uint4& ob)
-{
-    float4 a = as_float4(ua), b = as_float4(ub);
-    if ((ub.w & 7u) == 3u) {
-        a.x = __fsub_rn(ox, a.x); a.y = __fsub_rn(oy, a.y); a.z = __fsub_rn(oz, a.z);
-    } else {
-        a.x = __fsub_rn(a.x, ox); a.y = __fsub_rn(a.y, oy); a.z = __fsub_rn(a.z, oz);
-        a.w = __fsub_rn(a.w, ox); b.x = __fsub_rn(b.x, oy); b.y = __fsub_rn(b.y, oz);
-    }
-    oa = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
-    ob = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), ub.z, ub.w);
-}
-
-// culling box of a node relative to the origin: operators, cubes, cylinders carry it; spheres: centre +- r, padded like the host does
-__device__ __forceinline__ void rel_cull_box(const uint4 ua, const uint4 ub, float ox, float oy, float oz, float lo[3], float hi[3])
-{
-    const float4 a = as_float4(ua), b = as_float4(ub);
-    if ((ub.w & 7u) == 3u) {
-        const float r = fabsf(a.w);
-        const float c[3] = {a.x, a.y, a.z}, o[3] = {ox, oy, oz};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float pad = r * 1e-4f + fabsf(c[k]) * 4e-7f + 1e-30f;
-            lo[k] = (c[k] - r - pad) - o[k];
-            hi[k] = (c[k] + r + pad) - o[k];
-        }
-    } else {
-        lo[0] = a.x - ox; lo[1] = a.y - oy; lo[2] = a.z - oz;
-        hi[0] = a.w - ox; hi[1] = b.x - oy; hi[2] = b.y - oz;
-    }
-}
-
-constexpr int kPruneWarps = 4, kPruneThreads = kPruneWarps * 32;
-constexpr int kListMax = 512;     // nodes one tile may look at (alive nodes + their tested children)
-constexpr int kSlotMax = 256;     // records per tile slot
-constexpr int kLevelMax = 64;
-constexpr int kCostBuckets = 64;
-
-struct PruneWarpSmem {            // working set of one warp = one tile
-    int lnode[kListMax];          // node id, in breadth-first order of discovery
-    short lchild[kListMax];       // operators: list position of the left child (the right child follows it)
-    short lrep[kListMax];         // list position of the node standing for this subtree: itself, a descendant, or -1
-    short lsize[kListMax];        // survivors in the subtree (valid where lrep[p] == p)
-    short lidx[kListMax];         // preorder index among the survivors
-    unsigned char lkind[kListMax];   // kind | alive << 3 | reachable << 4
-    unsigned char flg[kListMax];  // bit0 pure, bit1 bounded
-    float box[kListMax][6];       // culling box, origin-relative (operators: recomputed over what survives)
-    short lvl[kLevelMax + 2];     // list position where each level starts
-};
-
-// One WARP per traced macro tile, top-down: only nodes whose parent is reachable from the tile are ever looked at, so the
-// cost follows the size of the tile's own tree, not of the scene.  Three passes over the levels of the visited part:
-// down (frustum tests), up (which operators survive, their boxes), down (preorder numbering and emission).
-__global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_constant__ PruneParams q)
-{
-    extern __shared__ __align__(16) unsigned char psm[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float ox = q.cam_pos[0], oy = q.cam_pos[1], oz = q.cam_pos[2];
-    const int N = q.n_nodes, S = q.slot_nodes;
-    const int tile_ctas = (q.n_tiles + kPruneWarps - 1) / kPruneWarps;
-    cudaTriggerProgrammaticLaunchCompletion();   // the frame kernel may be scheduled now; it waits for this grid before it reads our output
-
-    if ((int)blockIdx.x >= tile_ctas) {
-        // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
-        const int nb = (int)gridDim.x - tile_ctas;
-        for (int i = ((int)blockIdx.x - tile_ctas) * kPruneThreads + tid; i < N; i += nb * kPruneThreads) {
-            uint4 oa, ob;
-            stage_record(__ldg(&q.nodes[2 * i]), __ldg(&q.nodes[2 * i + 1]), ox, oy, oz, oa, ob);
-            q.pool[2 * i] = oa;
-            q.pool[2 * i + 1] = ob;
-        }
-        return;
-    }
-    const int tile = (int)blockIdx.x * kPruneWarps + warp;
-    if (tile >= q.n_tiles) return;
-    {   // pull the tree into L2 in one go (the walk below touches it level by level, one dependent miss at a time otherwise)
-        const char* base = reinterpret_cast<const char*>(q.nodes);
-        const size_t bytes = (size_t)N * 32;
-        for (size_t off = ((size_t)(tile & 7) * 32 + lane) * 128; off < bytes && off < (size_t)(1 << 20); off += 8 * 32 * 128)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
-    }
-    PruneWarpSmem& w = reinterpret_cast<PruneWarpSmem*>(psm)[warp];
-    const unsigned int lt = (1u << lane) - 1u;
-
-    // ---- the tile and its frustum
-    const int j = tile * q.shard_count + q.shard_rank;
-    const int jy = q.rm_magic ? (int)__umulhi((unsigned int)j, q.rm_magic) : j / q.rm_w;
-    const int mx = q.rm_x0 + (j - jy * q.rm_w), my = q.rm_y0 + jy;
-    const int slot = (my * q.macro_x + mx) / q.shard_count;
-    float pn[5][3];   // inward plane normals: 4 sides through the origin + the camera plane
-    {
-        const float x0 = (float)(mx * kMacroW - 1) * q.ss, x1 = (float)(min(mx * kMacroW + kMacroW, q.width) + 1) * q.ss;
-        const float y0 = (float)(my * kMacroH - 1) * q.ss, y1 = (float)(min(my * kMacroH + kMacroH, q.height) + 1) * q.ss;
-        float d[4][3];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {   // corner rays (RaycastKernel :11-25, un-normalised), around the tile: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
-            const float fx = (c == 1 || c == 2) ? x1 : x0, fy = (c >= 2) ? y1 : y0;
-            const float u = fx / q.wm1, v = fy / q.hm1;
-            const float nx = q.aspect * (2.0f * u - 1.0f) * q.tan_half_fov, ny = (1.0f - 2.0f * v) * q.tan_half_fov;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) d[c][k] = q.forward[k] + q.right[k] * nx + q.up[k] * ny;
-        }
-        float dc[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) dc[k] = d[0][k] + d[1][k] + d[2][k] + d[3][k];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float* a = d[c];
-            const float* b = d[(c + 1) & 3];
-            float n0 = a[1] * b[2] - a[2] * b[1], n1 = a[2] * b[0] - a[0] * b[2], n2 = a[0] * b[1] - a[1] * b[0];
-            if (n0 * dc[0] + n1 * dc[1] + n2 * dc[2] < 0.0f) { n0 = -n0; n1 = -n1; n2 = -n2; }
-            pn[c][0] = n0; pn[c][1] = n1; pn[c][2] = n2;
-        }
-        pn[4][0] = q.forward[0]; pn[4][1] = q.forward[1]; pn[4][2] = q.forward[2];
-    }
-
-    // ---- A. breadth-first from the root, queueing the operands of live operators.  Two ways to decide "live":
-    //   pass 0 (frustum walk): test every visited node's box against the frustum.  Cost follows the number of boxes the
-    //          frustum touches — small when the tree is spatially coherent.
-    //   pass 1 (leaf marks; taken when pass 0 overflows its list, or first for small trees): test all primitives once, mark
-    //          the way from every reachable primitive up to the root (2 bits per node: left / right operand has something
-    //          below), then walk down along the marks only.  An operator with one marked side either stands for that side
-    //          (Union; Difference when it is the left one) or is gone (Difference without its left operand, Intersection) and
-    //          is skipped on the spot, so the list holds only operators with both sides marked, and primitives.
-    uint32_t* mk = reinterpret_cast<uint32_t*>(psm + kPruneWarps * sizeof(PruneWarpSmem)) + (size_t)warp * q.mark_words;
-    int total = 1, levels = 0;
-    bool overflow = true;
-    for (int pass = q.marks_first ? 1 : 0; pass < 2 && overflow; ++pass) {
-        if (pass == 1) {
-            if (q.mark_words == 0) break;           // tree too large for the marks
-            for (int i = lane; i < q.mark_words; i += 32) mk[i] = 0u;
-            __syncwarp();
-            // all primitives once, coalesced and several loads in flight: culling box (world space) + node number, 32 B each
-#pragma unroll 4
-            for (int k = lane; k < q.n_leaves; k += 32) {
-                const float4 la = __ldg(&q.leaf_boxes[2 * k]), lb4 = __ldg(&q.leaf_boxes[2 * k + 1]);
-                const float lo[3] = {la.x - ox, la.y - oy, la.z - oz}, hi[3] = {lb4.x - ox, lb4.y - oy, lb4.z - oz};
-                bool outside = false;
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
-                                    fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
-                    outside = outside || (m < 0.0f);
-                }
-                if (outside) continue;
-                const int i = __float_as_int(la.w);
-                atomicOr(&mk[i >> 4], 1u << ((i & 15) * 2));
-                int c = i, par = __ldg(&q.parent[i]);
-                while (par >= 0) {                   // up to the root, or to a node somebody else already marked
-                    const int sh = (par & 15) * 2;
-                    const uint32_t old = atomicOr(&mk[par >> 4], (c == par + 1 ? 1u : 2u) << sh);
-                    if ((old >> sh) & 3u) break;
-                    c = par; par = __ldg(&q.parent[par]);
-                }
-            }
-            __syncwarp();
-        }
-        if (lane == 0) { w.lnode[0] = 0; w.lvl[0] = 0; }
-        __syncwarp();
-        int lb = 0, le = 1;
-        total = 1; levels = 0; overflow = false;
-        while (lb < le && !overflow) {
-            if (lane == 0) w.lvl[levels + 1] = (short)le;
-            int next_total = total;
-            for (int base = lb; base < le; base += 32) {
-                const int p = base + lane;
-                const bool have = p < le;
-                bool grow = false;
-                uint32_t meta = 0u;
-                int n = 0;
-                if (have) {
-                    n = w.lnode[p];
-                    bool outside = false;
-                    uint4 ua, ub;
-                    if (pass == 1) {
-                        for (;;) {
-                            meta = __ldg(&q.nodes[2 * n + 1]).w;
-                            const uint32_t kind = meta & 7u, m = (mk[n >> 4] >> ((n & 15) * 2)) & 3u;
-                            if (kind >= 3u) { outside = !(m & 1u); break; }
-                            if (m == 3u) break;
-                            if (m == 1u && kind != 2u) { n = n + 1; continue; }              // stands for its left operand
-                            if (m == 2u && kind == 0u) { n = (int)(meta >> 8); continue; }   // Union: stands for its right operand
-                            outside = true;
-                            break;
-                        }
-                        w.lnode[p] = n;
-                    }
-                    ua = __ldg(&q.nodes[2 * n]); ub = __ldg(&q.nodes[2 * n + 1]);
-                    meta = ub.w;
-                    float lo[3], hi[3];
-                    rel_cull_box(ua, ub, ox, oy, oz, lo, hi);
-                    if (pass == 0) {
-#pragma unroll
-                        for (int c = 0; c < 5; ++c) {
-                            const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
-                                            fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
-                            outside = outside || (m < 0.0f);
-                        }
-                    }
-                    const uint32_t kind = meta & 7u;
-                    w.lkind[p] = (unsigned char)(kind | (outside ? 0u : 8u));
-                    w.lrep[p] = outside ? (short)-1 : (short)p;
-                    w.lsize[p] = 1;
-                    w.flg[p] = (unsigned char)(((kind == 3u || kind == 5u) ? 1u : 0u) | ((kind != 4u) ? 2u : 0u));
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) { w.box[p][c] = lo[c]; w.box[p][3 + c] = hi[c]; }
-                    grow = !outside && kind < 3u;
-                }
-                const unsigned int mask = __ballot_sync(0xffffffffu, grow);
-                const int add = 2 * __popc(mask);
-                if (next_total + add > kListMax) { overflow = true; break; }
-                if (grow) {
-                    const int c = next_total + 2 * __popc(mask & lt);
-                    w.lnode[c] = n + 1;
-                    w.lnode[c + 1] = (int)(meta >> 8);
-                    w.lchild[p] = (short)c;
-                }
-                next_total += add;
-            }
-            __syncwarp();
-            lb = le; le = next_total; total = next_total;
-            if (++levels >= kLevelMax) overflow = true;
-        }
-    }
-    uint32_t kept = 0u, flags = 0u;
-    uint4* dst = q.pool + 2 * ((size_t)q.slots_off32 + (size_t)slot * S);
-    int r0 = -1;
-    if (!overflow) {
-        // ---- B. deepest level first: an operator stays (both operands matter: box over what is left, flags), collapses to
-        //         one operand, or goes
-        for (int d = levels - 1; d >= 0; --d) {
-            for (int p = w.lvl[d] + lane; p < w.lvl[d + 1]; p += 32) {
-                const uint32_t k = w.lkind[p];
-                if (!(k & 8u) || (k & 7u) >= 3u) continue;
-                const int c = w.lchild[p];
-                const int a = w.lrep[c], b = w.lrep[c + 1];
-                const uint32_t kind = k & 7u;
-                const int rp = kind == 0u ? (a < 0 ? b : (b < 0 ? a : p)) : kind == 1u ? (a < 0 ? -1 : (b < 0 ? a : p)) : ((a < 0 || b < 0) ? -1 : p);
-                w.lrep[p] = (short)rp;
-                if (rp != p) continue;
-                w.lsize[p] = (short)(1 + w.lsize[a] + w.lsize[b]);
-                const float* bl = w.box[a];
-                const float* br = w.box[b];
-                float* bo = w.box[p];
-                if (kind == 0u) {                   // Union: both operands
-#pragma unroll
-                    for (int c2 = 0; c2 < 3; ++c2) { bo[c2] = fminf(bl[c2], br[c2]); bo[3 + c2] = fmaxf(bl[3 + c2], br[3 + c2]); }
-                } else if (kind == 1u) {            // Difference: a subset of the left operand
-#pragma unroll
-                    for (int c2 = 0; c2 < 6; ++c2) bo[c2] = bl[c2];
-                } else {                            // Intersection: a subset of both; the smaller box
-                    float vl = 1.f, vr = 1.f;
-#pragma unroll
-                    for (int c2 = 0; c2 < 3; ++c2) { vl *= fmaxf(bl[3 + c2] - bl[c2], 0.f); vr *= fmaxf(br[3 + c2] - br[c2], 0.f); }
-                    const float* bs = vl <= vr ? bl : br;
-#pragma unroll
-                    for (int c2 = 0; c2 < 6; ++c2) bo[c2] = bs[c2];
-                }
-                const uint32_t fl = w.flg[a], fr = w.flg[b];
-                w.flg[p] = (unsigned char)(((kind == 0u) ? (fl & fr & 1u) : 0u) | (fl & fr & 2u));
-            }
-            __syncwarp();
-        }
-        r0 = w.lrep[0];
-        if (r0 >= 0) {
-            kept = (uint32_t)w.lsize[r0];
-            if (kept > (uint32_t)S) overflow = true;
-        }
-    }
-    if (!overflow && r0 >= 0) {
-        // ---- C. root first: preorder index of every survivor (left operand right after its operator, right operand after the
-        //         left subtree), and its record
-        if (lane == 0) { w.lidx[r0] = 0; w.lkind[r0] |= 16u; }
-        __syncwarp();
-        for (int d = 0; d < levels; ++d) {
-            for (int p = w.lvl[d] + lane; p < w.lvl[d + 1]; p += 32) {
-                const uint32_t k = w.lkind[p];
-                if (!(k & 16u)) continue;
-                const int i = w.lidx[p];
-                if ((k & 7u) >= 3u) {           // primitive: origin-relative record
-                    const int n = w.lnode[p];
-                    uint4 oa, ob;
-                    stage_record(__ldg(&q.nodes[2 * n]), __ldg(&q.nodes[2 * n + 1]), ox, oy, oz, oa, ob);
-                    dst[2 * i] = oa;
-                    dst[2 * i + 1] = ob;
-                    continue;
-                }
-                const int c = w.lchild[p];
-                const int ra = w.lrep[c], rb = w.lrep[c + 1];
-                const int r = i + 1 + w.lsize[ra];
-                w.lidx[ra] = (short)(i + 1);
-                w.lidx[rb] = (short)r;
-                w.lkind[ra] |= 16u;
-                w.lkind[rb] |= 16u;
-                const uint32_t f = w.flg[p];
-                const uint32_t meta = (k & 7u) | ((uint32_t)r << 8) | ((w.lkind[ra] & 7u) >= 3u ? kMetaLeftLeaf : 0u) |
-                                      ((w.lkind[rb] & 7u) >= 3u ? kMetaRightLeaf : 0u) | ((f & 2u) ? kMetaBounded : 0u) | ((f & 1u) ? kMetaPure : 0u);
-                const float* bo = w.box[p];
-                dst[2 * i] = make_uint4(__float_as_uint(bo[0]), __float_as_uint(bo[1]), __float_as_uint(bo[2]), __float_as_uint(bo[3]));
-                dst[2 * i + 1] = make_uint4(__float_as_uint(bo[4]), __float_as_uint(bo[5]), 0u, meta);
-            }
-            __syncwarp();
-        }
-        const uint32_t rk = w.lkind[r0] & 7u;
-        flags = (rk >= 3u ? kTileRootLeaf : 0u) | ((rk < 3u && (w.flg[r0] & 1u)) ? kTileRootPure : 0u);
-    }
-    // ---- descriptor; heavy tiles (more nodes) are handed out first by the frame kernel: bucket lists, then one ordered list
-    const uint32_t cost = overflow ? (uint32_t)min(N, 2 * kCostBuckets - 1) : kept;
-    const int bucket = (int)min(cost / 2u, (uint32_t)(kCostBuckets - 1));
-    if (lane == 0) {
-        q.desc[slot] = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
-                                : TileDesc{kept ? q.slots_off32 + (uint32_t)slot * (uint32_t)S : 0u, kept, flags, 0u};
-        if (q.order) {
-            const unsigned int rank = atomicAdd(&q.hist[bucket], 1u);
-            q.lists[(size_t)bucket * q.n_slots + rank] = (unsigned short)tile;
-            __threadfence();
-        }
-    }
-    if (!q.order) return;
-    unsigned int done = 0;
-    if (lane == 0) done = atomicAdd(q.done, 1u);
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != (unsigned int)q.n_tiles - 1u) return;
-    // last warp of the grid: concatenate the bucket lists, heaviest bucket first, and reset the counters for the next frame
-    __threadfence();
-    static_assert(kCostBuckets == 64, "two buckets per lane");
-    unsigned int* start = reinterpret_cast<unsigned int*>(&w);   // the warp's own scratch is free now
-    {
-        // k = 63 - bucket: heaviest bucket first.  lane l owns k = l and k = 32 + l; start[k] = first position of bucket k in order[]
-        const unsigned int c0 = __ldcg(&q.hist[63 - lane]), c1 = __ldcg(&q.hist[31 - lane]);
-        unsigned int i0 = c0, i1 = c1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-            if (lane >= o) { i0 += t0; i1 += t1; }
-        }
-        const unsigned int first_half = __shfl_sync(0xffffffffu, i0, 31);
-        start[lane] = i0 - c0;
-        start[32 + lane] = first_half + i1 - c1;
-    }
-    __syncwarp();
-    for (int b = lane; b < kCostBuckets; b += 32) q.hist[b] = 0u;
-    if (lane == 0) *q.done = 0u;
-    // every output position looks up its bucket (largest k with start[k] <= i): independent loads, several in flight per lane
-#pragma unroll 4
-    for (int i = lane; i < q.n_tiles; i += 32) {
-        int k = 0;
-#pragma unroll
-        for (int step = 32; step >= 1; step >>= 1)
-            if (k + step < kCostBuckets && start[k + step] <= (unsigned int)i) k += step;
-        q.order[i] = __ldcg(q.lists + (size_t)(63 - k) * q.n_slots + ((unsigned int)i - start[k]));
-    }
-}
 
 // FP32 roofline probe: 8 independent FFMA chains per thread, nothing else.
 __global__ void __launch_bounds__(256) csg_ffma_probe_kernel(float* out, int iters, float a, float b)
