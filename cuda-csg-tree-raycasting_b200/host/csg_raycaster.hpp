@@ -15,6 +15,8 @@
 #include <stdexcept>
 #include <string>
 
+#include <vector>
+
 #include "../../include/csg_b200.h"
 
 namespace csg_b200 {
@@ -118,6 +120,15 @@ class Raycaster {
     {  // idempotent, like the reference's `alloced` guard (Raycaster.cu:36-45)
         csg_free_context(ctx_);
         ctx_ = nullptr;
+    }
+    // A camera path in one call (the application's frame loop over a moving camera, Application.cpp:39-57): n frames of
+    // RGBA8, frame k at rgba8 + k*width*height*4 (host or device pointer), pipelined over two frame slots.
+    void RaycastBatch(const Camera* cams, int n, const DirectionalLight& light, uint8_t* rgba8)
+    {
+        std::vector<csg_camera> cs(static_cast<size_t>(n));
+        for (int k = 0; k < n; ++k) cs[static_cast<size_t>(k)] = cams[k].store();
+        csg_light l{light.polar, light.azimuth};
+        if (csg_render_batch(ctx_, cs.data(), n, &l, rgba8) != CSG_OK) throw std::runtime_error(csg_last_error());
     }
     csg_context* context() { return ctx_; }
 

@@ -117,8 +117,9 @@ int csg_render_batch(csg_context* ctx, const csg_camera* cams, int n_frames, con
  * I.e. the result equals the reference kernel run at k times the resolution and averaged k x k.  Default 1. */
 int csg_set_supersampling(csg_context* ctx, int samples_per_axis);
 
-/* Work statistics: traversal loop iterations per pixel of THIS implementation (the reference algorithm's counts come from
- * the instrumented oracle).  Host pointer, width*height int32. */
+/* Work statistics of THIS implementation (the reference algorithm's counts come from the instrumented oracle): per pixel, the
+ * traversal loop iterations packed as search_visits << 20 | frame_machine_visits << 10 | other_iterations (nearest-Enter
+ * search visits, operator visits of the frame machine, Compute/Return/leaf-loop rounds).  Host pointer, width*height int32. */
 int csg_render_stats(csg_context* ctx, const csg_camera* cam, int32_t* iterations);
 
 /* Per-tile tree pruning (on by default): before each frame every 64x32-pixel tile gets its own copy of the tree holding only
