@@ -20,7 +20,7 @@ CSG_OK, CSG_ERR_PARSE, CSG_ERR_IO, CSG_ERR_CUDA, CSG_ERR_ARG, CSG_ERR_NO_DEVICE,
 
 # every symbol include/csg_b200.h declares
 EXPORTS = [
-    "csg_load_scene", "csg_parse_scene", "csg_free_scene", "csg_scene_counts", "csg_scene_dump", "csg_scene_write",
+    "csg_load_scene", "csg_parse_scene", "csg_free_scene", "csg_scene_counts", "csg_scene_dump", "csg_scene_flatten", "csg_scene_write",
     "csg_generate_scene", "csg_camera_default", "csg_camera_set", "csg_camera_set_fov_degrees", "csg_light_default",
     "csg_light_direction", "csg_upload", "csg_upload_shard", "csg_free_context", "csg_scene_set_optimize",
     "csg_render", "csg_render_batch", "csg_render_f32", "csg_render_aov", "csg_render_stats", "csg_set_supersampling", "csg_set_pruning", "csg_prune_stats", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
@@ -59,6 +59,7 @@ def _load():
         "csg_free_scene": (None, [vp]),
         "csg_scene_counts": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
         "csg_scene_dump": (i, [vp, vp, vp]),
+        "csg_scene_flatten": (i, [vp, vp, vp, C.POINTER(i), C.POINTER(i)]),
         "csg_scene_write": (C.c_size_t, [vp, C.c_char_p, C.c_size_t]),
         "csg_generate_scene": (C.c_size_t, [i, C.c_uint64, C.c_char_p, C.c_size_t]),
         "csg_camera_default": (None, [C.POINTER(CCamera)]),
@@ -212,6 +213,15 @@ class Scene:
         prims = np.zeros((npr, 48), np.uint8)
         _check(lib.csg_scene_dump(self.h, _ptr(nodes), _ptr(prims)))
         return nodes, prims
+
+    def flatten(self):
+        """The GPU layout: (records as uint32[n, 8] — view as float32 for the first 6 words — , parents int32[n], depth)."""
+        n, d = C.c_int(), C.c_int()
+        _check(lib.csg_scene_flatten(self.h, None, None, C.byref(n), C.byref(d)))
+        rec = np.zeros((n.value, 8), np.uint32)
+        par = np.zeros(n.value, np.int32)
+        _check(lib.csg_scene_flatten(self.h, _ptr(rec), _ptr(par), C.byref(n), C.byref(d)))
+        return rec, par, d.value
 
     def write(self):
         n = lib.csg_scene_write(self.h, None, 0)

@@ -604,6 +604,18 @@ int csg_scene_dump(const csg_scene* scene, void* nodes44, void* prims48)
     return CSG_OK;
 }
 
+int csg_scene_flatten(const csg_scene* scene, void* nodes32, int32_t* parents, int* n_nodes, int* depth)
+{
+    if (!scene) return fail(CSG_ERR_ARG, "null scene");
+    FlatTree t;
+    flatten(scene->scene, scene->scene.optimize, t);
+    if (nodes32) std::memcpy(nodes32, t.nodes.data(), t.nodes.size() * sizeof(NodeRec));
+    if (parents) std::memcpy(parents, t.parent.data(), t.parent.size() * sizeof(int32_t));
+    if (n_nodes) *n_nodes = (int)t.nodes.size();
+    if (depth) *depth = t.depth;
+    return CSG_OK;
+}
+
 size_t csg_scene_write(const csg_scene* scene, char* buf, size_t buflen)
 {
     if (!scene) return 0;

@@ -64,6 +64,10 @@ int csg_scene_counts(const csg_scene* scene, int* n_nodes, int* n_prims, int* de
 /* Copies the tree in the reference's own layouts: n_nodes*44 bytes of CSGNode (CSGTree.cuh:15-34,
  * with the reference's AABBs of BVHNode.cuh:17-77) and n_prims*48 bytes of Primitive (Primitives.h:29-41). */
 int csg_scene_dump(const csg_scene* scene, void* nodes44, void* prims48);
+/* The GPU layout csg_upload builds from the scene at its current optimisation level (host side only, no device needed;
+ * for tests and tools): *n_nodes 32-byte records in preorder (layout: cuda-csg-tree-raycasting_b200/csrc/csg_scene.h),
+ * the parent of every record (-1 at the root) and the operator depth.  nodes32 / parents may be NULL to query the count. */
+int csg_scene_flatten(const csg_scene* scene, void* nodes32, int32_t* parents, int* n_nodes, int* depth);
 /* Writes the scene back out in the text format. Returns bytes needed (excluding NUL). */
 size_t csg_scene_write(const csg_scene* scene, char* buf, size_t buflen);
 /* Synthetic balanced tree in the scene text format (BASELINE.json configs[4]).
