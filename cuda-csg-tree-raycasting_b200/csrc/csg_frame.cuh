@@ -68,7 +68,7 @@ __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const flo
     const float rx = __fmaf_rn(-ux, two, -Lx), ry = __fmaf_rn(-uy, two, -Ly), rz = __fmaf_rn(-uz, two, -Lz);
     const float diff = fmaxf(dot_ref(nx, ny, nz, Lx, Ly, Lz), 0.0f);
     const float sb = fmaxf(dot_ref(vx, vy, vz, rx, ry, rz), 0.0f);
-    const float spec = powf(sb, 30.0f);
+    const float spec = sb > 0.0f ? powf(sb, 30.0f) : 0.0f;   // powf(+0, 30) is exactly +0: skip the call for pixels facing away from the highlight
     const float k = __fmaf_rn(spec, 0.7f, __fmaf_rn(diff, 0.8f, 0.2f));
     float4 o;
     o.x = fminf(fmaxf(col.x * k, 0.0f), 1.0f);
