@@ -23,7 +23,7 @@ EXPORTS = [
     "csg_load_scene", "csg_parse_scene", "csg_free_scene", "csg_scene_counts", "csg_scene_dump", "csg_scene_flatten", "csg_scene_write",
     "csg_generate_scene", "csg_camera_default", "csg_camera_set", "csg_camera_set_fov_degrees", "csg_light_default",
     "csg_light_direction", "csg_upload", "csg_upload_shard", "csg_free_context", "csg_scene_set_optimize",
-    "csg_render", "csg_render_batch", "csg_render_f32", "csg_render_aov", "csg_render_stats", "csg_set_supersampling", "csg_set_pruning", "csg_prune_stats", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
+    "csg_render", "csg_render_batch", "csg_render_f32", "csg_render_aov", "csg_render_stats", "csg_set_supersampling", "csg_set_pruning", "csg_set_view_cache", "csg_prune_stats", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
     "csg_launch_count", "csg_framebuffer", "csg_framebuffer_ipc_handle", "csg_set_gather_target_ipc",
     "csg_set_gather_target", "csg_read_framebuffer", "csg_device_tan_half_fov", "csg_fp32_peak_tflops", "csg_context_info",
     "csg_last_error", "csg_version",
@@ -78,6 +78,7 @@ def _load():
         "csg_render_stats": (i, [vp, C.POINTER(CCamera), vp]),
         "csg_set_supersampling": (i, [vp, i]),
         "csg_set_pruning": (i, [vp, i]),
+        "csg_set_view_cache": (i, [vp, i]),
         "csg_prune_stats": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(C.c_longlong)]),
         "csg_render_enqueue": (i, [vp, C.POINTER(CCamera), C.POINTER(CLight), vp]),
         "csg_sync": (i, [vp]),
@@ -294,6 +295,10 @@ class Context:
 
     def set_pruning(self, enabled):
         _check(lib.csg_set_pruning(self.h, int(bool(enabled))))
+        return self
+
+    def set_view_cache(self, enabled):
+        _check(lib.csg_set_view_cache(self.h, int(bool(enabled))))
         return self
 
     def prune_stats(self):

@@ -66,6 +66,8 @@ struct Shard {  // one GPU's share of the frame
     int rank = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+    PruneParams last_q;          // what the tile pool currently holds (view cache)
+    bool last_q_valid = false;
     uint4* d_nodes = nullptr;
     uint4* d_pool = nullptr;     // [staged whole tree][one slot of slot_nodes records per macro tile of this shard]
     TileDesc* d_desc = nullptr;  // per macro tile of this shard
@@ -105,6 +107,7 @@ struct csg_context {
     int band_m0 = 0, band_m1 = 0;   // macro-tile rows the next enqueue covers (0, 0 = the whole frame)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_band[8] = {};
+    bool view_cache = false;     // csg_set_view_cache
     bool external_target = false;   // csg_set_gather_target: pixels go to a buffer that is not rank 0's own framebuffer
     bool prune_alloc = false;    // tile slots were allocated at upload
     int last_rm[4] = {0, 0, 0, 0};   // traced macro-tile rectangle of the last frame (x0, y0, w, h)
@@ -341,11 +344,15 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.lists = s.d_lists; q.order = s.d_order;
             q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes;
             q.slots_off32 = (uint32_t)fp.n_nodes; q.full_flags = c->full_flags;
+            // view cache (opt-in): same camera, size, sampling and tile set as the trees this shard already holds -> keep them
+            const bool cached = c->view_cache && s.last_q_valid && std::memcmp(&q, &s.last_q, sizeof q) == 0;
+            s.last_q = q;
+            s.last_q_valid = true;
             const int stage_ctas = std::max(1, std::min(64, (fp.n_nodes + kPruneThreads - 1) / kPruneThreads));
-            csg_prune_kernel<<<(q.n_tiles + kPruneWarps - 1) / kPruneWarps + stage_ctas, kPruneThreads, c->prune_smem, s.stream>>>(q);
+            if (!cached) csg_prune_kernel<<<(q.n_tiles + kPruneWarps - 1) / kPruneWarps + stage_ctas, kPruneThreads, c->prune_smem, s.stream>>>(q);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("prune kernel launch: ") + cudaGetErrorString(e));
-            c->launches++;
+            if (!cached) c->launches++;
         }
         int rc = CSG_OK;
         if (mode == OUT_RGBA8) {
@@ -1000,6 +1007,14 @@ int csg_render_aov(csg_context* ctx, const csg_camera* cam, uint8_t* hit, int32_
     if (hit) CU(cudaMemcpy(hit, ctx->d_aov_hit, n, cudaMemcpyDeviceToHost));
     if (prim_id) CU(cudaMemcpy(prim_id, ctx->d_aov_prim, n * 4, cudaMemcpyDeviceToHost));
     if (t) CU(cudaMemcpy(t, ctx->d_aov_t, n * 4, cudaMemcpyDeviceToHost));
+    return CSG_OK;
+}
+
+int csg_set_view_cache(csg_context* ctx, int enabled)
+{
+    if (!ctx) return fail(CSG_ERR_ARG, "null context");
+    ctx->view_cache = enabled != 0;
+    for (Shard& s : ctx->shards) s.last_q_valid = false;
     return CSG_OK;
 }
 

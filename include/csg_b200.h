@@ -132,6 +132,10 @@ int csg_render_stats(csg_context* ctx, const csg_camera* cam, int32_t* iteration
  * csg_prune_stats reports the last frame of shard 0: traced tiles, tiles no primitive reaches, tiles whose tree did not fit
  * its slot (they read the whole tree), and the total number of nodes over all pruned trees. */
 int csg_set_pruning(csg_context* ctx, int enabled);
+/* View cache (off by default): the per-tile trees depend on the camera, the frame size and the sampling only — not on the
+ * light.  With the cache on, a frame whose view equals the previous frame's reuses the trees instead of rebuilding them
+ * (the reference application's static camera with a moving light: one kernel per frame instead of two). */
+int csg_set_view_cache(csg_context* ctx, int enabled);
 int csg_prune_stats(csg_context* ctx, int* traced_tiles, int* empty_tiles, int* fallback_tiles, long long* pruned_nodes);
 
 /* ---- asynchronous / device-resident form (benchmarks, interop viewers, multi-process gather) */

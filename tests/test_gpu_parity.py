@@ -318,3 +318,24 @@ def test_sample_parallel_supersampling_equals_the_serial_loop(k, csg, monkeypatc
         ctx.close()
     assert np.array_equal(out["0"][0], out["1"][0])
     assert np.array_equal(out["0"][1], out["1"][1])
+
+
+def test_view_cache_reuses_the_trees_of_an_unchanged_view(csg):
+    """csg_set_view_cache: same camera, moving light -> the pruning kernel is skipped, the frames are what they would be anyway."""
+    txt = scenes.INLINE["nested"]
+    w, h = 256, 144
+    sc = csg.Scene.parse(txt)
+    ctx = sc.upload(w, h)
+    v = orbit_view(w, h, 5, radius=4.0)
+    cam, cam2 = cam_of(csg, v), cam_of(csg, orbit_view(w, h, 6, radius=4.0))
+    lights = [csg.Light(), csg.Light(0.7, 2.0), csg.Light(-0.3, 1.0)]
+    plain = [ctx.render(cam, l).copy() for l in lights] + [ctx.render(cam2, lights[0]).copy()]
+    ctx.set_view_cache(True)
+    n0 = ctx.launch_count()
+    cached = [ctx.render(cam, l).copy() for l in lights]
+    assert ctx.launch_count() - n0 == 2 + 1 + 1          # prune + frame, then frame only
+    cached.append(ctx.render(cam2, lights[0]).copy())     # the view changed: trees rebuilt
+    assert ctx.launch_count() - n0 == 6
+    for a, b in zip(plain, cached):
+        assert np.array_equal(a, b)
+    ctx.close()
