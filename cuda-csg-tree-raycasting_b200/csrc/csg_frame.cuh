@@ -40,13 +40,17 @@ __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const flo
         if (res.m & H_FLAG1) { nx = -pv.x; ny = -pv.y; nz = -pv.z; }
         else if (res.m & H_FLAG2) { nx = pv.x; ny = pv.y; nz = pv.z; }
         else {
-            const float ocx = r.ox - pb.x, ocy = r.oy - pb.y, ocz = r.oz - pb.z;
+            // Here the reference's kernel forms C = centre - (h/2)V with one rounding (FFMA -V, h/2, centre in its SASS), unlike
+            // cylinderHit, whose C is the two-rounding base point of the primitive record
+            const float hh = __fmul_rn(pb.w, 0.5f);
+            const float cx = __fmaf_rn(-pv.x, hh, pc.x), cy = __fmaf_rn(-pv.y, hh, pc.y), cz = __fmaf_rn(-pv.z, hh, pc.z);
+            const float ocx = r.ox - cx, ocy = r.oy - cy, ocz = r.oz - cz;
             const float dV = dot_ref(pv.x, pv.y, pv.z, r.dx, r.dy, r.dz);
             const float ocv = dot_ref(pv.x, pv.y, pv.z, ocx, ocy, ocz);
             const float m = __fmaf_rn(t, dV, ocv);
-            nx = __fmaf_rn(-pv.x, m, px - pb.x);
-            ny = __fmaf_rn(-pv.y, m, py - pb.y);
-            nz = __fmaf_rn(-pv.z, m, pz - pb.z);
+            nx = __fmaf_rn(-pv.x, m, px - cx);
+            ny = __fmaf_rn(-pv.y, m, py - cy);
+            nz = __fmaf_rn(-pv.z, m, pz - cz);
         }
     }
     if (!((res.m & (H_FLAG1 | H_FLAG2)) && kind == 4u)) {   // caps carry the unit axis as is; everything else is normalised
@@ -63,7 +67,9 @@ __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const flo
     vx *= iv; vy *= iv; vz *= iv;
     const float in = __frcp_rn(__fsqrt_rn(dot_ref(nx, ny, nz, nx, ny, nz)));   // reflect() re-normalises n
     const float ux = nx * in, uy = ny * in, uz = nz * in;
-    const float dn = __fmaf_rn(-Lz, uz, __fmaf_rn(-Lx, ux, uy * -Ly));
+    // dot(-L, n) of reflect(): the reference's SASS rounds the x product first here (FMUL Lx*nx; FFMA -Ly,ny,-that; FFMA -Lz,nz,.),
+    // not the y product as in every other dot of the path
+    const float dn = __fmaf_rn(-Lz, uz, __fmaf_rn(-Ly, uy, -__fmul_rn(Lx, ux)));
     const float two = dn + dn;
     const float rx = __fmaf_rn(-ux, two, -Lx), ry = __fmaf_rn(-uy, two, -Ly), rz = __fmaf_rn(-uz, two, -Lz);
     const float diff = fmaxf(dot_ref(nx, ny, nz, Lx, Ly, Lz), 0.0f);

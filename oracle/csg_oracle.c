@@ -754,7 +754,8 @@ static rayhit hit_details(const orc_scene* s, const ray_t* ray, const hitmin* h)
     } else {
         const f3 V = {p->p[2], p->p[3], p->p[4]};
         const float hh = p->p[1] * 0.5f;
-        const f3 Cb = {p->x - V.x * hh, p->y - V.y * hh, p->z - V.z * hh}; /* :347 */
+        /* :347 — in this function the reference kernel's SASS forms C with one rounding (FFMA -V, h/2, centre) */
+        const f3 Cb = {fmaf(-V.x, hh, p->x), fmaf(-V.y, hh, p->y), fmaf(-V.z, hh, p->z)};
         const f3 OC = sub3(ray->origin, Cb);
         if (h->hit & R_FLAG1) d.normal = neg3(V);       /* :351-355 */
         else if (h->hit & R_FLAG2) d.normal = V;        /* :356-360 */
@@ -783,7 +784,8 @@ static void shade(const orc_scene* s, const orc_camera* cam, const rayhit* hi, c
     f3 Vv = normalize3(sub3(eye, hi->position));        /* :79 */
     /* reflect(-L, normal), Float3Utils.cuh:39-44: n = normalize(b); a - 2*dot(a,n)*n */
     f3 n = normalize3(hi->normal);
-    float dn = fmaf(-L.z, n.z, fmaf(-L.x, n.x, n.y * -L.y));
+    /* SASS of LightningKernel: FMUL Lx*nx; FFMA -Ly,ny,-that; FFMA -Lz,nz,. (the x product is the one rounded first here) */
+    float dn = fmaf(-L.z, n.z, fmaf(-L.y, n.y, -(L.x * n.x)));
     float two = dn + dn;
     f3 R = {fmaf(-n.x, two, -L.x), fmaf(-n.y, two, -L.y), fmaf(-n.z, two, -L.z)};
     float diff = fmaxf(dot3(hi->normal, L), 0.0f);      /* :86 */

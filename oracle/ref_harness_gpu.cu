@@ -96,6 +96,47 @@ void refgpu_light_dir(const ref_view* v, float* out3)
 // Timing (any may be NULL): iters >= 1 timed repetitions after `warmup` untimed ones;
 //   ms_kernels[iters]  = CUDA-event time of RaycastKernel+LightningKernel launched back to back,
 //   ms_shipped[iters]  = CUDA-event time around Raycaster::Raycast as shipped.
+/* Diagnostic: RayHit.position and RayHit.normal (Ray.cuh:24-34) of every pixel as the reference's RaycastKernel stores them
+ * (6 floats per pixel; untouched where the ray misses). */
+int refgpu_render_details(const char* text, const ref_view* v, float* pos_normal, char* err, int errlen)
+{
+    CSGTree tree;
+    try {
+        tree = CSGTree::Parse(text);
+    } catch (const std::exception& e) {
+        fill_err(err, errlen, e.what());
+        return 1;
+    }
+    const int w = v->width, h = v->height;
+    const size_t npx = (size_t)w * h;
+    Camera cam = make_camera(v);
+    CudaCSGTree ct;
+    RayHit* dHits = nullptr;
+    CK(cudaMalloc(&ct.nodes, tree.nodes.size() * sizeof(CSGNode)));
+    CK(cudaMalloc(&ct.primitives, tree.primitives.primitives.size() * sizeof(Primitive)));
+    CK(cudaMemcpy(ct.nodes, tree.nodes.data(), tree.nodes.size() * sizeof(CSGNode), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ct.primitives, tree.primitives.primitives.data(),
+                  tree.primitives.primitives.size() * sizeof(Primitive), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&dHits, npx * sizeof(RayHit)));
+    CK(cudaMemset(dHits, 0, npx * sizeof(RayHit)));
+    dim3 block(BLOCKXSIZE, BLOCKYSIZE);
+    dim3 grid((w + block.x - 1) / block.x, (h + block.y - 1) / block.y);
+    RaycastKernel<<<grid, block>>>(cam, ct, dHits, (float)w, (float)h);
+    CK(cudaDeviceSynchronize());
+    std::vector<RayHit> hh(npx);
+    CK(cudaMemcpy((void*)hh.data(), dHits, npx * sizeof(RayHit), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < npx; ++i) {
+        if (!hh[i].hit) continue;
+        float* o = pos_normal + 6 * i;
+        o[0] = hh[i].position.x; o[1] = hh[i].position.y; o[2] = hh[i].position.z;
+        o[3] = hh[i].normal.x; o[4] = hh[i].normal.y; o[5] = hh[i].normal.z;
+    }
+    cudaFree(ct.nodes);
+    cudaFree(ct.primitives);
+    cudaFree(dHits);
+    return 0;
+}
+
 int refgpu_render(const char* text, const ref_view* v,
                   uint8_t* hit, int32_t* prim, float* t, float* rgba,
                   int warmup, int iters, float* ms_kernels, float* ms_shipped,

@@ -23,7 +23,7 @@ def light_of(v):
 
 
 def compare(name, v, ref, optimize, timing_iters=0):
-    txt = scene_text(name)
+    txt = g.Scene.generate_text(int(name.split(":")[1]), 1234) if name.startswith("synthetic:") else scene_text(name)
     fr = ref.render(txt, v, warmup=1 if timing_iters else 0, iters=max(1, timing_iters), shipped=bool(timing_iters))
     sc = g.Scene.parse(txt, optimize=optimize)
     ctx = sc.upload(v.width, v.height)
@@ -77,7 +77,7 @@ def main():
                 print(json.dumps(r), flush=True)
     for name, v in [("testWikipedia", View(1920, 1080)), ("testSphereCutByCubesAndCylinder", orbit_view(3840, 2160, 9)),
                     ("testCheese256", View(3840, 2160)), ("testCheese512", View(3840, 2160)),
-                    ("testCheese512", oblique_view(3840, 2160))]:
+                    ("testCheese512", oblique_view(3840, 2160)), ("synthetic:4096", View(3840, 2160))]:
         for opt in (0, 1):
             r = compare(name, v, ref, opt, timing_iters=10)
             res.append(r)
