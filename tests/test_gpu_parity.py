@@ -339,3 +339,23 @@ def test_view_cache_reuses_the_trees_of_an_unchanged_view(csg):
     for a, b in zip(plain, cached):
         assert np.array_equal(a, b)
     ctx.close()
+
+
+@pytest.mark.parametrize("scene_id", ["synthetic:1500", "corpus:testCubeCutEdges", "corpus:testCylinderSpheres2", "corpus:testCheese256"])
+def test_float_colour_is_bit_identical_to_the_reference_kernel(scene_id, csg, ref_gpu):
+    """The linear float4 colour (what the reference writes into its PBO), every bit — stricter than the 1-LSB RGBA8 contract.
+    Pins the FFMA placement of hit details and Phong (arithmetic contract)."""
+    if scene_id.startswith("corpus:") and scene_id[7:] not in scenes.corpus_names():
+        pytest.skip("scene corpus not staged")
+    txt = csg.Scene.generate_text(1500, seed=99) if scene_id.startswith("synthetic:") else scenes.text_of(scene_id)
+    w, h = 960, 540
+    for v in (View(w, h), orbit_view(w, h, 23, radius=7.0, pitch_deg=-35.0) if not scene_id.startswith("synthetic:") else
+              View(w, h, pos=(25.0, 12.0, -8.0), pitch=-0.25, yaw=1.1, polar=0.9, azimuth=2.2)):
+        ref = ref_gpu.render(txt, v)
+        sc = csg.Scene.parse(txt)
+        ctx = sc.upload(w, h)
+        f32 = ctx.render_f32(cam_of(csg, v), light_of(csg, v)).reshape(-1, 4)
+        ctx.close()
+        want = ref.rgba.reshape(-1, 4)
+        differ = (f32.view(np.uint32) != want.view(np.uint32)).any(axis=1)
+        assert not differ.any(), f"{scene_id}: {int(differ.sum())} of {differ.size} pixels differ in float colour"
