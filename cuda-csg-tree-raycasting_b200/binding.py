@@ -294,7 +294,8 @@ class Context:
         return ret
 
     def set_pruning(self, enabled):
-        _check(lib.csg_set_pruning(self.h, int(bool(enabled))))
+        """False/0: every tile reads the whole tree; True/1: per-tile trees (default kernel); 2: per-tile trees by the tree-walking kernel."""
+        _check(lib.csg_set_pruning(self.h, int(enabled)))
         return self
 
     def set_view_cache(self, enabled):

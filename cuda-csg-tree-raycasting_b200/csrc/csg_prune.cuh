@@ -48,6 +48,57 @@ __device__ __forceinline__ void rel_cull_box(const uint4 ua, const uint4 ub, flo
     }
 }
 
+// Traced macro tile number `tile` of this shard -> macro tile coordinates.
+__device__ __forceinline__ void tile_of(const PruneParams& q, int tile, int& mx, int& my)
+{
+    const int j = tile * q.shard_count + q.shard_rank;
+    const int jy = q.rm_magic ? (int)__umulhi((unsigned int)j, q.rm_magic) : j / q.rm_w;
+    mx = q.rm_x0 + (j - jy * q.rm_w);
+    my = q.rm_y0 + jy;
+}
+
+// Frustum of a macro tile: its pixels plus a margin of one pixel.  Inward plane normals: 4 sides through the camera position
+// (cross products of the un-normalised corner rays of RaycastKernel :11-25) + the camera plane.
+__device__ __forceinline__ void tile_frustum(const PruneParams& q, int mx, int my, float pn[5][3])
+{
+    const float x0 = (float)(mx * kMacroW - 1) * q.ss, x1 = (float)(min(mx * kMacroW + kMacroW, q.width) + 1) * q.ss;
+    const float y0 = (float)(my * kMacroH - 1) * q.ss, y1 = (float)(min(my * kMacroH + kMacroH, q.height) + 1) * q.ss;
+    float d[4][3];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {   // corner rays around the tile: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
+        const float fx = (c == 1 || c == 2) ? x1 : x0, fy = (c >= 2) ? y1 : y0;
+        const float u = fx / q.wm1, v = fy / q.hm1;
+        const float nx = q.aspect * (2.0f * u - 1.0f) * q.tan_half_fov, ny = (1.0f - 2.0f * v) * q.tan_half_fov;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[c][k] = q.forward[k] + q.right[k] * nx + q.up[k] * ny;
+    }
+    float dc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dc[k] = d[0][k] + d[1][k] + d[2][k] + d[3][k];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float* a = d[c];
+        const float* b = d[(c + 1) & 3];
+        float n0 = a[1] * b[2] - a[2] * b[1], n1 = a[2] * b[0] - a[0] * b[2], n2 = a[0] * b[1] - a[1] * b[0];
+        if (n0 * dc[0] + n1 * dc[1] + n2 * dc[2] < 0.0f) { n0 = -n0; n1 = -n1; n2 = -n2; }
+        pn[c][0] = n0; pn[c][1] = n1; pn[c][2] = n2;
+    }
+    pn[4][0] = q.forward[0]; pn[4][1] = q.forward[1]; pn[4][2] = q.forward[2];
+}
+
+// box [lo, hi] (relative to the camera position) entirely behind one of the five planes?
+__device__ __forceinline__ bool box_outside(const float pn[5][3], const float lo[3], const float hi[3])
+{
+    bool outside = false;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
+                        fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
+        outside = outside || (m < 0.0f);
+    }
+    return outside;
+}
+
 constexpr int kPruneWarps = 4, kPruneThreads = kPruneWarps * 32;
 constexpr int kListMax = 512;     // nodes one tile may look at (alive nodes + their tested children)
 constexpr int kSlotMax = 256;     // records per tile slot
@@ -101,36 +152,11 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
     const unsigned int lt = (1u << lane) - 1u;
 
     // ---- the tile and its frustum
-    const int j = tile * q.shard_count + q.shard_rank;
-    const int jy = q.rm_magic ? (int)__umulhi((unsigned int)j, q.rm_magic) : j / q.rm_w;
-    const int mx = q.rm_x0 + (j - jy * q.rm_w), my = q.rm_y0 + jy;
+    int mx, my;
+    tile_of(q, tile, mx, my);
     const int slot = (my * q.macro_x + mx) / q.shard_count;
     float pn[5][3];   // inward plane normals: 4 sides through the origin + the camera plane
-    {
-        const float x0 = (float)(mx * kMacroW - 1) * q.ss, x1 = (float)(min(mx * kMacroW + kMacroW, q.width) + 1) * q.ss;
-        const float y0 = (float)(my * kMacroH - 1) * q.ss, y1 = (float)(min(my * kMacroH + kMacroH, q.height) + 1) * q.ss;
-        float d[4][3];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {   // corner rays (RaycastKernel :11-25, un-normalised), around the tile: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
-            const float fx = (c == 1 || c == 2) ? x1 : x0, fy = (c >= 2) ? y1 : y0;
-            const float u = fx / q.wm1, v = fy / q.hm1;
-            const float nx = q.aspect * (2.0f * u - 1.0f) * q.tan_half_fov, ny = (1.0f - 2.0f * v) * q.tan_half_fov;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) d[c][k] = q.forward[k] + q.right[k] * nx + q.up[k] * ny;
-        }
-        float dc[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) dc[k] = d[0][k] + d[1][k] + d[2][k] + d[3][k];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float* a = d[c];
-            const float* b = d[(c + 1) & 3];
-            float n0 = a[1] * b[2] - a[2] * b[1], n1 = a[2] * b[0] - a[0] * b[2], n2 = a[0] * b[1] - a[1] * b[0];
-            if (n0 * dc[0] + n1 * dc[1] + n2 * dc[2] < 0.0f) { n0 = -n0; n1 = -n1; n2 = -n2; }
-            pn[c][0] = n0; pn[c][1] = n1; pn[c][2] = n2;
-        }
-        pn[4][0] = q.forward[0]; pn[4][1] = q.forward[1]; pn[4][2] = q.forward[2];
-    }
+    tile_frustum(q, mx, my, pn);
 
     // ---- A. breadth-first from the root, queueing the operands of live operators.  Two ways to decide "live":
     //   pass 0 (frustum walk): test every visited node's box against the frustum.  Cost follows the number of boxes the
@@ -153,14 +179,7 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
             for (int k = lane; k < q.n_leaves; k += 32) {
                 const float4 la = __ldg(&q.leaf_boxes[2 * k]), lb4 = __ldg(&q.leaf_boxes[2 * k + 1]);
                 const float lo[3] = {la.x - ox, la.y - oy, la.z - oz}, hi[3] = {lb4.x - ox, lb4.y - oy, lb4.z - oz};
-                bool outside = false;
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
-                                    fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
-                    outside = outside || (m < 0.0f);
-                }
-                if (outside) continue;
+                if (box_outside(pn, lo, hi)) continue;
                 const int i = __float_as_int(la.w);
                 atomicOr(&mk[i >> 4], 1u << ((i & 15) * 2));
                 int c = i, par = __ldg(&q.parent[i]);
@@ -207,14 +226,7 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
                     meta = ub.w;
                     float lo[3], hi[3];
                     rel_cull_box(ua, ub, ox, oy, oz, lo, hi);
-                    if (pass == 0) {
-#pragma unroll
-                        for (int c = 0; c < 5; ++c) {
-                            const float m = fmaxf(pn[c][0] * lo[0], pn[c][0] * hi[0]) + fmaxf(pn[c][1] * lo[1], pn[c][1] * hi[1]) +
-                                            fmaxf(pn[c][2] * lo[2], pn[c][2] * hi[2]);
-                            outside = outside || (m < 0.0f);
-                        }
-                    }
+                    if (pass == 0) outside = box_outside(pn, lo, hi);
                     const uint32_t kind = meta & 7u;
                     w.lkind[p] = (unsigned char)(kind | (outside ? 0u : 8u));
                     w.lrep[p] = outside ? (short)-1 : (short)p;
@@ -367,6 +379,301 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
         for (int step = 32; step >= 1; step >>= 1)
             if (k + step < kCostBuckets && start[k + step] <= (unsigned int)i) k += step;
         q.order[i] = __ldcg(q.lists + (size_t)(63 - k) * q.n_slots + ((unsigned int)i - start[k]));
+    }
+}
+
+// ---- the same pruned trees, without walking the tree ----------------------------------------------------------------------
+// csg_prune_kernel follows the tree level by level: ~12 dependent levels x 3 passes per tile, one warp per tile, every level a
+// round trip to L2 — 14 us per tile however little work there is, which is the fixed part of a frame once it is spread over
+// several GPUs.  csg_prune_flat_kernel (the default for trees of up to kFlatMaxNodes nodes) gets the same tree out of the
+// PREORDER layout with prefix sums, one CTA per tile and no pointer chasing:
+//   1. every primitive's culling box against the tile's frustum, in parallel (coalesced 32-byte box records)     -> alive[n]
+//   2. A = inclusive prefix sum of alive over the preorder positions.  A subtree is a contiguous range [n, end[n]), so the
+//      number of reachable primitives below the left / right operand of operator n is A[right-1] - A[n] / A[end-1] - A[right-1].
+//   3. an operator survives when both sides have some; with one side empty it stands for the other side (Union; Difference whose
+//      right side is empty) or is gone with everything below it (Difference without its left operand, Intersection with one
+//      side: all M* cells, RaycastingKernels.cu:666-677).  The latter takes reachable primitives away from its ancestors:
+//      clear them and repeat 2-3 (rare: needs an Intersection / a Difference that lost its left operand inside the tile).
+//   4. S = inclusive prefix sum of the survivor flags = preorder numbering of the tile's tree: survivor n becomes record
+//      S[n]-1, its left operand is the next record, its right operand record S[right[n]-1] (survivors before the right subtree).
+//   5. primitives are emitted origin-relative (stage_record); operator boxes and the pure / bounded flags come from a bottom-up
+//      refit of the tile's (small) tree in shared memory, with the same box rules as csg_prune_kernel (Union: both operands;
+//      Difference: the left one; Intersection: the smaller).
+// The trees differ from csg_prune_kernel's only where that one drops a whole operator by its box before looking at the
+// primitives (never the other way round), and frames are byte-identical with either (tests/test_gpu_parity.py).
+constexpr int kFlatThreads = 128;
+constexpr int kFlatMaxNodes = 32768;   // 2 x 16-bit prefix sums per node in shared memory (128 KB at the limit)
+
+struct FlatTileSmem {                  // followed by uint16_t A[n_pad], S[n_pad]
+    float box[kSlotMax][6];            // culling box of every record of the tile's tree, origin-relative
+    uint32_t meta[kSlotMax];           // kind | right operand (record index) << 8
+    unsigned char flg[kSlotMax];       // bit0 pure, bit1 bounded
+    unsigned char done[kSlotMax];      // box and flags are final
+    unsigned int wsum[kFlatThreads / 32];
+    unsigned int start[kCostBuckets];  // ordering tail
+    unsigned int last;
+};
+
+// Inclusive prefix sum of v[0, n) in place by the whole CTA; every thread owns `chunk` consecutive elements (odd: the
+// strided accesses then fall into distinct banks).  Ends with a barrier.
+__device__ __forceinline__ void cta_scan_u16(unsigned short* v, int n, int chunk, unsigned int* wsum)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = min(tid * chunk, n), e = min(b + chunk, n);
+    unsigned int s = 0;
+    for (int i = b; i < e; ++i) s += v[i];
+    unsigned int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned int run = inc - s;
+    for (int k = 0; k < warp; ++k) run += wsum[k];
+    for (int i = b; i < e; ++i) { run += v[i]; v[i] = (unsigned short)run; }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFlatThreads) csg_prune_flat_kernel(const __grid_constant__ PruneParams q)
+{
+    extern __shared__ __align__(16) unsigned char psm[];
+    constexpr int T = kFlatThreads;
+    const int tid = threadIdx.x;
+    const float ox = q.cam_pos[0], oy = q.cam_pos[1], oz = q.cam_pos[2];
+    const int N = q.n_nodes, S = q.slot_nodes;
+    cudaTriggerProgrammaticLaunchCompletion();   // the frame kernel may be scheduled now; it waits for this grid before it reads our output
+
+    if ((int)blockIdx.x >= q.n_tiles) {
+        // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
+        const int nb = (int)gridDim.x - q.n_tiles;
+        for (int i = ((int)blockIdx.x - q.n_tiles) * T + tid; i < N; i += nb * T) {
+            uint4 oa, ob;
+            stage_record(__ldg(&q.nodes[2 * i]), __ldg(&q.nodes[2 * i + 1]), ox, oy, oz, oa, ob);
+            q.pool[2 * i] = oa;
+            q.pool[2 * i + 1] = ob;
+        }
+        return;
+    }
+    const int tile = (int)blockIdx.x;
+    FlatTileSmem& w = *reinterpret_cast<FlatTileSmem*>(psm);
+    const int n_pad = (N + 7) & ~7;
+    unsigned short* A = reinterpret_cast<unsigned short*>(psm + sizeof(FlatTileSmem));
+    unsigned short* Sv = A + n_pad;
+
+    int mx, my;
+    tile_of(q, tile, mx, my);
+    const int slot = (my * q.macro_x + mx) / q.shard_count;
+    float pn[5][3];
+    tile_frustum(q, mx, my, pn);
+
+    // ---- 1. reachable primitives
+    for (int i = tid; i < N; i += T) A[i] = 0;
+    __syncthreads();
+    for (int k0 = tid; k0 < q.n_leaves; k0 += 4 * T) {   // batches of four: all eight loads of a batch in flight together
+        float4 la[4], lb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = min(k0 + j * T, q.n_leaves - 1);
+            la[j] = __ldg(&q.leaf_boxes[2 * k]);
+            lb[j] = __ldg(&q.leaf_boxes[2 * k + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float lo[3] = {la[j].x - ox, la[j].y - oy, la[j].z - oz}, hi[3] = {lb[j].x - ox, lb[j].y - oy, lb[j].z - oz};
+            if (k0 + j * T < q.n_leaves && !box_outside(pn, lo, hi)) A[__float_as_int(la[j].w)] = 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- 2./3. reachable primitives per subtree, survivors; primitives below an operator that is gone are taken away
+    for (;;) {
+        cta_scan_u16(A, N, q.flat_chunk, w.wsum);
+        bool gone = false;
+        for (int n0 = tid; n0 < N; n0 += 8 * T) {   // batches of eight: the topology loads of a batch are in flight together
+            uint2 tp[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tp[j] = __ldg(&q.topo[min(n0 + j * T, N - 1)]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = n0 + j * T;
+                if (n >= N) break;
+                const uint32_t kind = tp[j].x & 7u;
+                const unsigned int an = A[n];
+                unsigned int surv;
+                if (kind >= 3u) {
+                    surv = an - (n ? (unsigned int)A[n - 1] : 0u);
+                } else {
+                    const unsigned int ar = A[(tp[j].x >> 8) - 1u], ae = A[tp[j].y - 1u];
+                    const bool hl = ar != an, hr = ae != ar;   // something reachable below the left / right operand
+                    surv = (hl && hr) ? 1u : 0u;
+                    if (kind == 1u ? (!hl && hr) : (kind == 2u && hl != hr)) gone = true;
+                }
+                Sv[n] = (unsigned short)surv;
+            }
+        }
+        if (!__syncthreads_or(gone ? 1 : 0)) break;
+        // Sv holds the alive flag of every primitive: clear those below the operators that are gone, rebuild A from the flags
+        for (int n = tid; n < N; n += T) {
+            const uint2 tp = __ldg(&q.topo[n]);
+            const uint32_t kind = tp.x & 7u;
+            if (kind >= 3u) continue;
+            const unsigned int an = A[n], ar = A[(tp.x >> 8) - 1u], ae = A[tp.y - 1u];
+            const bool hl = ar != an, hr = ae != ar;
+            if (kind == 1u ? (!hl && hr) : (kind == 2u && hl != hr))   // atomics: operators that are gone may be nested
+                for (unsigned int m = (unsigned int)n + 1u; m < tp.y; ++m)
+                    atomicAnd(reinterpret_cast<unsigned int*>(Sv) + (m >> 1), (m & 1u) ? 0x0000ffffu : 0xffff0000u);
+        }
+        __syncthreads();
+        for (int n = tid; n < N; n += T) A[n] = ((__ldg(&q.topo[n]).x & 7u) >= 3u) ? Sv[n] : (unsigned short)0;
+        __syncthreads();
+    }
+
+    // ---- 4. preorder numbering of the survivors
+    cta_scan_u16(Sv, N, q.flat_chunk, w.wsum);
+    const uint32_t kept = Sv[N - 1];
+    const bool overflow = kept > (uint32_t)S;
+    // heavy tiles (more nodes) are handed out first by the frame kernel: bucket lists now (the round trips of the atomic and
+    // the list entry overlap the emission below), one ordered list at the end
+    if (tid == 0 && q.order) {
+        const uint32_t cost = overflow ? (uint32_t)min(N, 2 * kCostBuckets - 1) : kept;
+        const int bucket = (int)min(cost / 2u, (uint32_t)(kCostBuckets - 1));
+        const unsigned int rank = atomicAdd(&q.hist[bucket], 1u);
+        q.lists[(size_t)bucket * q.n_slots + rank] = (unsigned short)tile;
+    }
+    uint4* dst = q.pool + 2 * ((size_t)q.slots_off32 + (size_t)slot * S);
+    uint32_t flags = 0u;
+    if (!overflow && kept) {
+        // ---- 5. records of the primitives, shape of the tile's tree
+        for (int n = tid; n < N; n += T) {
+            const uint32_t sn = Sv[n], sp = n ? (uint32_t)Sv[n - 1] : 0u;
+            if (sn == sp) continue;
+            const uint32_t i = sp;   // this survivor's record
+            const uint2 tp = __ldg(&q.topo[n]);
+            const uint32_t kind = tp.x & 7u;
+            if (kind >= 3u) {
+                const uint4 ua = __ldg(&q.nodes[2 * n]), ub = __ldg(&q.nodes[2 * n + 1]);
+                uint4 oa, ob;
+                stage_record(ua, ub, ox, oy, oz, oa, ob);
+                dst[2 * i] = oa;
+                dst[2 * i + 1] = ob;
+                float lo[3], hi[3];
+                rel_cull_box(ua, ub, ox, oy, oz, lo, hi);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { w.box[i][c] = lo[c]; w.box[i][3 + c] = hi[c]; }
+                w.meta[i] = kind;
+                w.flg[i] = (unsigned char)(((kind == 3u || kind == 5u) ? 1u : 0u) | ((kind != 4u) ? 2u : 0u));
+                w.done[i] = 1;
+            } else {
+                const uint32_t ri = Sv[(tp.x >> 8) - 1u];   // survivors before the right subtree = record of the right operand
+                w.meta[i] = kind | (ri << 8);
+                w.done[i] = 0;
+            }
+        }
+        __syncthreads();
+        // ---- bottom-up refit in rounds: an operator whose operands are both done computes its box and flags; rounds = height of
+        //      the tile's tree (a handful), two barriers each, shared memory only
+        for (;;) {
+            unsigned int now = 0u;
+            int pending = 0;
+            for (int i = tid, k = 0; i < (int)kept; i += T, ++k) {
+                const uint32_t m = w.meta[i], kind = m & 7u;
+                if (kind >= 3u || w.done[i]) continue;
+                const int a = i + 1, b = (int)(m >> 8);
+                if (!(w.done[a] && w.done[b])) { pending = 1; continue; }
+                const float* bl = w.box[a];
+                const float* br = w.box[b];
+                float* bo = w.box[i];
+                if (kind == 0u) {                   // Union: both operands
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { bo[c] = fminf(bl[c], br[c]); bo[3 + c] = fmaxf(bl[3 + c], br[3 + c]); }
+                } else if (kind == 1u) {            // Difference: a subset of the left operand
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) bo[c] = bl[c];
+                } else {                            // Intersection: a subset of both; the smaller box
+                    float vl = 1.f, vr = 1.f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { vl *= fmaxf(bl[3 + c] - bl[c], 0.f); vr *= fmaxf(br[3 + c] - br[c], 0.f); }
+                    const float* bs = vl <= vr ? bl : br;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) bo[c] = bs[c];
+                }
+                const uint32_t fl = w.flg[a], fr = w.flg[b];
+                w.flg[i] = (unsigned char)(((kind == 0u) ? (fl & fr & 1u) : 0u) | (fl & fr & 2u));
+                now |= 1u << k;
+            }
+            __syncthreads();
+            for (int i = tid, k = 0; i < (int)kept; i += T, ++k)
+                if ((now >> k) & 1u) w.done[i] = 1;
+            if (!__syncthreads_or(pending)) break;
+        }
+        // ---- records of the operators
+        for (int i = tid; i < (int)kept; i += T) {
+            const uint32_t m = w.meta[i], kind = m & 7u;
+            if (kind >= 3u) continue;
+            const uint32_t ri = m >> 8, f = w.flg[i];
+            const uint32_t meta = kind | (ri << 8) | ((w.meta[i + 1] & 7u) >= 3u ? kMetaLeftLeaf : 0u) | ((w.meta[ri] & 7u) >= 3u ? kMetaRightLeaf : 0u) |
+                                  ((f & 2u) ? kMetaBounded : 0u) | ((f & 1u) ? kMetaPure : 0u);
+            const float* bo = w.box[i];
+            dst[2 * i] = make_uint4(__float_as_uint(bo[0]), __float_as_uint(bo[1]), __float_as_uint(bo[2]), __float_as_uint(bo[3]));
+            dst[2 * i + 1] = make_uint4(__float_as_uint(bo[4]), __float_as_uint(bo[5]), 0u, meta);
+        }
+        const uint32_t rk = w.meta[0] & 7u;
+        flags = (rk >= 3u ? kTileRootLeaf : 0u) | ((rk < 3u && (w.flg[0] & 1u)) ? kTileRootPure : 0u);
+    }
+
+    // ---- descriptor, and the count of finished tiles (release: this tile's list entry; acquire: everybody else's)
+    if (tid == 0) {
+        q.desc[slot] = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
+                                : TileDesc{kept ? q.slots_off32 + (uint32_t)slot * (uint32_t)S : 0u, kept, flags, 0u};
+        unsigned int last = 0u;
+        if (q.order) {
+            unsigned int before;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(before) : "l"(q.done) : "memory");
+            last = before == (unsigned int)q.n_tiles - 1u ? 1u : 0u;
+        }
+        w.last = last;
+    }
+    __syncthreads();
+    if (!w.last) return;
+    // last CTA of the grid: concatenate the bucket lists, heaviest bucket first, and reset the counters for the next frame
+    static_assert(kCostBuckets == 64, "two buckets per lane");
+    if (tid < 32) {
+        // k = 63 - bucket: heaviest bucket first.  lane l owns k = l and k = 32 + l; start[k] = first position of bucket k in order[]
+        const int lane = tid;
+        const unsigned int c0 = __ldcg(&q.hist[63 - lane]), c1 = __ldcg(&q.hist[31 - lane]);
+        unsigned int i0 = c0, i1 = c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+            if (lane >= o) { i0 += t0; i1 += t1; }
+        }
+        const unsigned int first_half = __shfl_sync(0xffffffffu, i0, 31);
+        w.start[lane] = i0 - c0;
+        w.start[32 + lane] = first_half + i1 - c1;
+    }
+    __syncthreads();
+    for (int b = tid; b < kCostBuckets; b += T) q.hist[b] = 0u;
+    if (tid == 0) *q.done = 0u;
+    // every output position looks up its bucket (largest k with start[k] <= i); batches of four loads in flight per thread
+    for (int i0 = tid; i0 < q.n_tiles; i0 += 4 * T) {
+        const unsigned short* src[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned int i = (unsigned int)min(i0 + j * T, q.n_tiles - 1);
+            int k = 0;
+#pragma unroll
+            for (int step = 32; step >= 1; step >>= 1)
+                if (k + step < kCostBuckets && w.start[k + step] <= i) k += step;
+            src[j] = q.lists + (size_t)(63 - k) * q.n_slots + (i - w.start[k]);
+        }
+        unsigned short v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldcg(src[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j * T < q.n_tiles) q.order[i0 + j * T] = v[j];
     }
 }
 

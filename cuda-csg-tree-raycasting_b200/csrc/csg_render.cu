@@ -72,6 +72,7 @@ struct Shard {  // one GPU's share of the frame
     uint4* d_pool = nullptr;     // [staged whole tree][one slot of slot_nodes records per macro tile of this shard]
     TileDesc* d_desc = nullptr;  // per macro tile of this shard
     int* d_parent = nullptr;
+    uint2* d_topo = nullptr;             // per node: meta word, end of its subtree (csg_prune_flat_kernel)
     float4* d_leaf_boxes = nullptr;      // per primitive: culling box (world space) + node number, 2 x float4
     unsigned int* d_hist = nullptr;      // kCostBuckets counters + 1 "done" counter
     unsigned short* d_lists = nullptr;   // kCostBuckets x n_slots
@@ -95,7 +96,11 @@ struct csg_context {
     int shard_count = 1;
     bool multi_process = false;
     FlatTree tree;
-    bool prune = true;           // per-tile pruned trees (csg_prune_kernel); off for trees too large for its shared memory
+    bool prune = true;           // per-tile pruned trees, rebuilt every frame
+    bool prune_flat = true;      // by csg_prune_flat_kernel (prefix sums over the preorder layout); false: csg_prune_kernel (tree walk)
+    bool flat_ok = false;        // the tree is small enough for csg_prune_flat_kernel
+    size_t flat_smem = 0;
+    int flat_chunk = 1;
     int slot_nodes = 0;          // records per tile slot
     size_t prune_smem = 0;
     uint32_t full_flags = 0;
@@ -340,6 +345,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes; q.parent = s.d_parent;
             q.leaf_boxes = s.d_leaf_boxes; q.n_leaves = (int)(c->tree.leaf_boxes.size() / 8);
             q.mark_words = c->mark_words; q.marks_first = c->marks_first;
+            q.topo = s.d_topo; q.flat_chunk = c->flat_chunk;
             q.n_slots = s.n_slots; q.hist = s.d_hist; q.done = s.d_hist ? s.d_hist + kCostBuckets : nullptr;
             q.lists = s.d_lists; q.order = s.d_order;
             q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes;
@@ -349,7 +355,10 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             s.last_q = q;
             s.last_q_valid = true;
             const int stage_ctas = std::max(1, std::min(64, (fp.n_nodes + kPruneThreads - 1) / kPruneThreads));
-            if (!cached) csg_prune_kernel<<<(q.n_tiles + kPruneWarps - 1) / kPruneWarps + stage_ctas, kPruneThreads, c->prune_smem, s.stream>>>(q);
+            if (!cached) {
+                if (c->prune_flat && c->flat_ok) csg_prune_flat_kernel<<<q.n_tiles + stage_ctas, kFlatThreads, c->flat_smem, s.stream>>>(q);
+                else csg_prune_kernel<<<(q.n_tiles + kPruneWarps - 1) / kPruneWarps + stage_ctas, kPruneThreads, c->prune_smem, s.stream>>>(q);
+            }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("prune kernel launch: ") + cudaGetErrorString(e));
             if (!cached) c->launches++;
@@ -453,8 +462,16 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         c->marks_first = mf ? (mf[0] == '1') : 0;   // the frustum walk first; the marks when it overflows
         c->prune_smem = kPruneWarps * (sizeof(PruneWarpSmem) + (size_t)c->mark_words * 4);
         const char* off = std::getenv("CSG_B200_NO_PRUNE");   // tuning aid
-        c->prune = !(off && off[0] == '1');
+        // A scene that is a single primitive has nothing to prune, and its root is intersected without the gating box (Q7):
+        // dropping a root cylinder by that (non-conservative, Q6) box would lose pixels the reference draws.
+        c->prune = !(off && off[0] == '1') && !c->tree.root_is_leaf;
         c->prune_alloc = c->prune;
+        // csg_prune_flat_kernel: two 16-bit prefix sums per node behind the fixed part of its shared memory
+        c->flat_ok = n <= (size_t)kFlatMaxNodes;
+        c->flat_chunk = (int)((n + kFlatThreads - 1) / kFlatThreads) | 1;
+        c->flat_smem = sizeof(FlatTileSmem) + 2 * ((n + 7) & ~(size_t)7) * sizeof(unsigned short);
+        const char* walk = std::getenv("CSG_B200_PRUNE_WALK");   // tuning aid: the tree-walking kernel instead
+        c->prune_flat = !(walk && walk[0] == '1');
     }
     {
         // resident warps per SM for every (shape, tree placement); +1 KB per CTA is what the driver reserves
@@ -502,6 +519,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         const int my_macros = (total_macros - s.rank + shard_count - 1) / shard_count;
         s.n_local_warp_tiles = my_macros * 64;
         const int want = (s.n_local_warp_tiles + (c->threads / 32) - 1) / (c->threads / 32);
+        if (const char* cap = std::getenv("CSG_B200_CTAS_PER_SM")) bps = std::max(1, std::min(bps, std::atoi(cap)));   // tuning aid
         s.grid = std::max(1, std::min(dev_sms * bps, want));   // persistent CTAs: a multiple of the SM count
         CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&s.ev_start));
@@ -526,6 +544,14 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
             }
             if (c->prune_smem > 48 * 1024)
                 CU(cudaFuncSetAttribute(csg_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->prune_smem));
+            if (c->flat_ok) {
+                std::vector<uint2> topo(c->tree.nodes.size());
+                for (size_t k = 0; k < topo.size(); ++k) topo[k] = make_uint2(c->tree.nodes[k].meta, c->tree.subtree_end[k]);
+                CU(cudaMalloc(&s.d_topo, std::max<size_t>(topo.size(), 1) * sizeof(uint2)));
+                CU(cudaMemcpy(s.d_topo, topo.data(), topo.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+                if (c->flat_smem > 48 * 1024)
+                    CU(cudaFuncSetAttribute(csg_prune_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
+            }
         }
         const size_t prim_bytes = c->tree.prims.size() * sizeof(PrimRec);
         CU(cudaMalloc(&s.d_prims, std::max<size_t>(prim_bytes, 80)));
@@ -752,6 +778,7 @@ void csg_free_context(csg_context* c)
         cudaFree(s.d_pool);
         cudaFree(s.d_desc);
         cudaFree(s.d_parent);
+        cudaFree(s.d_topo);
         cudaFree(s.d_leaf_boxes);
         cudaFree(s.d_hist);
         cudaFree(s.d_lists);
@@ -920,6 +947,7 @@ int csg_render_batch(csg_context* ctx, const csg_camera* cams, int n_frames, con
     csg_context* slot[2] = {ctx, ctx->twin};
     ctx->twin->ss = ctx->ss;
     ctx->twin->prune = ctx->prune;
+    ctx->twin->prune_flat = ctx->prune_flat;
     const bool dev = is_device_pointer(rgba8_out);
     const size_t bytes = (size_t)ctx->width * ctx->height * 4;
     float ld[3];
@@ -1022,6 +1050,8 @@ int csg_set_pruning(csg_context* ctx, int enabled)
 {
     if (!ctx) return fail(CSG_ERR_ARG, "null context");
     ctx->prune = enabled != 0 && ctx->prune_alloc;
+    ctx->prune_flat = enabled != 2;   // 2: the tree-walking csg_prune_kernel
+    for (Shard& s : ctx->shards) s.last_q_valid = false;
     return CSG_OK;
 }
 

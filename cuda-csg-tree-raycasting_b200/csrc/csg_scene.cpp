@@ -430,6 +430,7 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
     out.root_pure = false;
     out.parent.clear();
     out.leaf_boxes.clear();
+    out.subtree_end.clear();
     if (s.nodes.empty()) return;
     Builder b(s);
     int root = optimize >= 1 ? b.build_optimized(0) : b.copy(0);
@@ -474,6 +475,7 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
         const int me = (int)out.nodes.size();
         index[id] = me;
         out.parent.push_back(parent);
+        out.subtree_end.push_back((uint32_t)me + 1u);
         out.nodes.push_back(NodeRec{});
         NodeRec& r = out.nodes[me];
         std::memset(&r, 0, sizeof r);
@@ -505,6 +507,7 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
         emit(n.left, me, depth + 1);
         const int right = (int)out.nodes.size();
         emit(n.right, me, depth + 1);
+        out.subtree_end[me] = (uint32_t)out.nodes.size();
         uint32_t meta = (uint32_t)n.type | ((uint32_t)right << 8);
         if (b.w[n.left].prim != -1) meta |= kMetaLeftLeaf;
         if (b.w[n.right].prim != -1) meta |= kMetaRightLeaf;

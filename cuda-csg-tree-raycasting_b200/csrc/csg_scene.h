@@ -61,6 +61,7 @@ struct FlatTree {
     bool root_pure = false;
     std::vector<int> parent;   // parent node of every record (-1 at the root), for the pruning kernel's upward marking
     std::vector<float> leaf_boxes;   // per primitive record, 8 floats: culling box min.xyz, node number (int bits), max.xyz, 0
+    std::vector<uint32_t> subtree_end;   // per record: one past the last record of its subtree (preorder), for csg_prune_flat_kernel
     // Box outside which every ray is a Miss (the root's culling box; for a root primitive its true bounds, since a root leaf
     // is intersected without the reference's gating box, Q7).  Used for the per-frame screen-space bound.
     bool root_box_valid = false;

@@ -128,10 +128,12 @@ int csg_render_stats(csg_context* ctx, const csg_camera* cam, int32_t* iteration
 
 /* Per-tile tree pruning (on by default): before each frame every 64x32-pixel tile gets its own copy of the tree holding only
  * the primitives its rays can reach (operators left with one operand collapse to it).  Results are identical with and
- * without it; csg_set_pruning(ctx, 0) makes every tile read the whole tree.
+ * without it.  mode 0: every tile reads the whole tree; 1 (default): per-tile trees, built by csg_prune_flat_kernel (prefix
+ * sums over the preorder layout; trees of up to 32768 nodes, larger ones use the walk); 2: per-tile trees built by the
+ * tree-walking csg_prune_kernel.
  * csg_prune_stats reports the last frame of shard 0: traced tiles, tiles no primitive reaches, tiles whose tree did not fit
  * its slot (they read the whole tree), and the total number of nodes over all pruned trees. */
-int csg_set_pruning(csg_context* ctx, int enabled);
+int csg_set_pruning(csg_context* ctx, int mode);
 /* View cache (off by default): the per-tile trees depend on the camera, the frame size and the sampling only — not on the
  * light.  With the cache on, a frame whose view equals the previous frame's reuses the trees instead of rebuilding them
  * (the reference application's static camera with a moving light: one kernel per frame instead of two). */

@@ -185,3 +185,103 @@ def test_pruned_tile_tree_gives_the_same_pixels(scene_id, csg, oracle):
                 assert np.array_equal(fp[m], np.array(ids, np.int32)[pp[m]])                 # same primitive (ids renumbered)
                 assert np.array_equal(full.rgba8().reshape(h, w, 4)[sl], part.rgba8().reshape(h, w, 4)[sl])
         assert pruned_somewhere
+
+
+# ---- csg_prune_flat_kernel's arithmetic: the tile's tree out of prefix sums over the preorder layout ---------------------
+def subtree_ends(kind, meta):
+    n = len(kind)
+    end = np.zeros(n, np.int64)
+
+    def walk(i):
+        if kind[i] >= 3:
+            end[i] = i + 1
+        else:
+            walk(i + 1)
+            end[i] = walk(int(meta[i] >> 8))
+        return int(end[i])
+    assert walk(0) == n
+    return end
+
+
+def collapse_flat(kind, meta, alive):
+    """Recursive definition: returns the surviving nodes as a nested tuple, or None."""
+    def rec(i):
+        k = int(kind[i])
+        if k >= 3:
+            return (i,) if alive[i] else None
+        a, b = rec(i + 1), rec(int(meta[i] >> 8))
+        if k == K_UNION:
+            return (i, a, b) if a and b else (a or b)
+        if k == K_DIFF:
+            return None if not a else ((i, a, b) if b else a)
+        return (i, a, b) if a and b else None
+    return rec(0)
+
+
+def preorder_records(tree):
+    """[(node, right operand's record index or -1)] in preorder."""
+    out = []
+
+    def rec(t):
+        me = len(out)
+        out.append([t[0], -1])
+        if len(t) == 3:
+            rec(t[1])
+            out[me][1] = len(out)
+            rec(t[2])
+    if tree:
+        rec(tree)
+    return [tuple(x) for x in out]
+
+
+def prune_by_prefix_sums(kind, meta, end, alive):
+    """What csg_prune_flat_kernel does, step for step, in numpy."""
+    n = len(kind)
+    is_leaf = kind >= 3
+    right = (meta >> 8).astype(np.int64)
+    flags = np.where(is_leaf, alive, 0).astype(np.int64)
+    rounds = 0
+    while True:
+        rounds += 1
+        A = np.cumsum(flags)
+        ops = np.nonzero(~is_leaf)[0]
+        hl = np.zeros(n, bool)
+        hr = np.zeros(n, bool)
+        hl[ops] = A[right[ops] - 1] != A[ops]
+        hr[ops] = A[end[ops] - 1] != A[right[ops] - 1]
+        surv = np.where(is_leaf, flags, (hl & hr).astype(np.int64))
+        gone = (~is_leaf) & (((kind == K_DIFF) & ~hl & hr) | ((kind == K_INTER) & (hl != hr)))
+        if not gone.any():
+            break
+        for i in np.nonzero(gone)[0]:
+            flags[i + 1:end[i]] = 0
+    S = np.cumsum(surv)
+    recs = []
+    for i in np.nonzero(surv)[0]:
+        recs.append((int(i), -1 if is_leaf[i] else int(S[right[i] - 1])))
+    return recs, rounds
+
+
+@pytest.mark.parametrize("optimize", [0, 1])
+@pytest.mark.parametrize("scene_id", scenes.all_scene_ids() + ["synthetic:300"])
+def test_prefix_sum_pruning_equals_the_recursive_collapse(scene_id, optimize, csg):
+    txt = csg.Scene.generate_text(300, seed=3) if scene_id.startswith("synthetic:") else scenes.text_of(scene_id)
+    rec, par, depth, nn, npr = flat(csg, txt, optimize)
+    meta = rec[:, 7].astype(np.int64)
+    kind = meta & 7
+    end = subtree_ends(kind, meta)
+    rng = np.random.default_rng(17)
+    saw_rounds = 0
+    for trial in range(40):
+        p = [0.0, 0.1, 0.5, 0.9, 1.0][trial % 5] if trial < 10 else rng.uniform(0.02, 0.98)
+        alive = rng.uniform(size=len(kind)) < p
+        want = preorder_records(collapse_flat(kind, meta, alive))
+        got, rounds = prune_by_prefix_sums(kind, meta, end, alive)
+        assert got == want
+        saw_rounds = max(saw_rounds, rounds)
+        # record i+1 is the left operand of operator record i; a record's subtree is contiguous
+        for i, (node, ri) in enumerate(got):
+            if ri >= 0:
+                assert i + 1 < ri < len(got)
+    if scene_id == "inline:nested":
+        assert saw_rounds >= 2    # an Intersection / Difference that went away took primitives from its ancestors

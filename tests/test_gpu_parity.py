@@ -234,8 +234,9 @@ def _frames(csg, ctx, cam, light):
 @pytest.mark.parametrize("scene_id", ["inline:nested", "inline:deep_left_chain", "inline:rotated_cylinder_union", "inline:duplicate_spheres",
                                       "inline:single_cylinder", "corpus:testCheese256", "corpus:testCubeCutEdges", "synthetic:600"])
 def test_per_tile_pruning_changes_nothing(scene_id, csg, monkeypatch):
-    """csg_prune_kernel: every tile's own tree (unreachable primitives dropped, one-operand operators collapsed) gives the
-    frame of the whole tree, byte for byte — through the frustum walk and through the leaf-mark path."""
+    """Every tile's own tree (unreachable primitives dropped, one-operand operators collapsed) gives the frame of the whole tree,
+    byte for byte — built by csg_prune_flat_kernel (prefix sums over the preorder layout, the default) and by csg_prune_kernel
+    (tree walk), the latter through the frustum walk and through the leaf-mark path."""
     if scene_id.startswith("corpus:") and scene_id[7:] not in scenes.corpus_names():
         pytest.skip("scene corpus not staged")
     txt = csg.Scene.generate_text(600, seed=7) if scene_id.startswith("synthetic:") else scenes.text_of(scene_id)
@@ -243,23 +244,62 @@ def test_per_tile_pruning_changes_nothing(scene_id, csg, monkeypatch):
     vs = [View(w, h), orbit_view(w, h, 13, pitch_deg=25.0, radius=6.0), View(w, h, pos=(0.3, 0.2, -0.4), pitch=0.2, yaw=2.5)]
     if "Cheese" in scene_id:
         vs = [View(w, h), oblique_view(w, h), View(w, h, pos=(0.5, 1.0, -19.0), pitch=0.3, yaw=2.0)]
-    for marks_first in ("0", "1"):
+    for mode, marks_first in ((1, "0"), (2, "0"), (2, "1")):
         monkeypatch.setenv("CSG_B200_MARKS_FIRST", marks_first)
         for optimize in (0, 1):
             sc = csg.Scene.parse(txt, optimize=optimize)
             ctx = sc.upload(w, h)
             for v in vs:
                 cam, light = cam_of(csg, v), light_of(csg, v)
-                ctx.set_pruning(True)
+                ctx.set_pruning(mode)
                 a = _frames(csg, ctx, cam, light)
                 st = ctx.prune_stats()
                 ctx.set_pruning(False)
                 b = _frames(csg, ctx, cam, light)
                 for x, y in zip(a, b):
-                    assert np.array_equal(x, y), f"{scene_id} opt={optimize} marks_first={marks_first}"
+                    assert np.array_equal(x, y), f"{scene_id} opt={optimize} mode={mode} marks_first={marks_first}"
                 assert st["fallback_tiles"] == 0 and st["traced_tiles"] >= st["empty_tiles"]
             ctx.close()
             sc.close()
+
+
+def test_flat_and_walking_pruning_kernels_agree_on_the_tile_trees(csg):
+    """The two kernels decide "reachable" slightly differently (the walk also tests operator boxes on its way down, the prefix-sum
+    kernel tests primitives only), so a tile's tree may differ by a node here and there — the frames may not, and the totals
+    stay close."""
+    if "testCheese512" not in scenes.corpus_names():
+        pytest.skip("scene corpus not staged")
+    txt = scenes.text_of("corpus:testCheese512")
+    sc = csg.Scene.parse(txt)
+    ctx = sc.upload(1920, 1080)
+    cam, light = csg.Camera(), csg.Light()
+    out = {}
+    for mode in (1, 2):
+        ctx.set_pruning(mode)
+        img = ctx.render(cam, light).copy()
+        out[mode] = (img, ctx.prune_stats())
+    assert np.array_equal(out[1][0], out[2][0])
+    a, b = out[1][1], out[2][1]
+    assert a["traced_tiles"] == b["traced_tiles"] and a["fallback_tiles"] == b["fallback_tiles"] == 0
+    assert abs(a["empty_tiles"] - b["empty_tiles"]) <= 0.05 * a["traced_tiles"]
+    assert abs(a["pruned_nodes"] - b["pruned_nodes"]) <= 0.05 * b["pruned_nodes"]
+    ctx.close()
+
+
+def test_root_primitive_is_not_pruned_by_its_gating_box(csg, oracle):
+    """Q7: a scene that is one primitive is intersected without the (non-conservative, Q6) cylinder box; tiles that see only the
+    part of a rotated cylinder that sticks out of that box must still draw it."""
+    txt = "Cylinder 0 0 0 00FF00 1 5 30 30 0\n"
+    w, h = 1280, 720
+    v = View(w, h, pos=(0.0, 2.6, 8.0))
+    sc = csg.Scene.parse(txt)
+    ctx = sc.upload(w, h)
+    cam, light = cam_of(csg, v), light_of(csg, v)
+    hit, prim, t = ctx.render_aov(cam)
+    rgba8 = ctx.render(cam, light)
+    ref = oracle.render(txt, v, tan_half_fov=ctx.device_tan_half_fov(cam.c.fov))
+    check(csg, hit, prim, t, rgba8, ref, "root cylinder", exact=True)
+    ctx.close()
 
 
 def test_pruning_statistics_and_slot_overflow(csg):
