@@ -26,7 +26,7 @@ EXPORTS = [
     "csg_render", "csg_render_batch", "csg_render_f32", "csg_render_aov", "csg_render_stats", "csg_set_supersampling", "csg_set_pruning", "csg_set_view_cache", "csg_prune_stats", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
     "csg_launch_count", "csg_framebuffer", "csg_framebuffer_ipc_handle", "csg_set_gather_target_ipc",
     "csg_set_gather_target", "csg_read_framebuffer", "csg_device_tan_half_fov", "csg_fp32_peak_tflops", "csg_context_info",
-    "csg_last_error", "csg_version",
+    "csg_last_error", "csg_version", "csg_cube_normal_threshold",
 ]
 
 
@@ -94,6 +94,7 @@ def _load():
         "csg_context_info": (C.c_char_p, [vp]),
         "csg_last_error": (C.c_char_p, []),
         "csg_version": (C.c_char_p, []),
+        "csg_cube_normal_threshold": (f, [f, f]),
     }
     for name in EXPORTS:
         fn = getattr(lib, name)  # AttributeError here = the library does not export what the header declares
@@ -120,6 +121,10 @@ def _ptr(a):
 
 def version():
     return lib.csg_version().decode()
+
+
+def cube_normal_threshold(half_size, level):
+    return float(lib.csg_cube_normal_threshold(float(half_size), float(level)))
 
 
 def fp32_peak_tflops(device=0):

@@ -30,10 +30,10 @@ __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const flo
     if (kind == 3u) {                                   // sphereHitDetails :189-195
         nx = px - pc.x; ny = py - pc.y; nz = pz - pc.z;
     } else if (kind == 5u) {                            // cubeHitDetails :446-451
-        const float bias = 1.00001f;
-        nx = (float)__float2int_rz(__fmul_rn(__fdiv_rn(px - pc.x, pc.w), bias));
-        ny = (float)__float2int_rz(__fmul_rn(__fdiv_rn(py - pc.y, pc.w), bias));
-        nz = (float)__float2int_rz(__fmul_rn(__fdiv_rn(pz - pc.z, pc.w), bias));
+        const float4 th = __ldg(&prims[id * 5 + 2]);
+        nx = cube_normal_component(__fsub_rn(px, pc.x), pc.w, th.x, th.y);
+        ny = cube_normal_component(__fsub_rn(py, pc.y), pc.w, th.x, th.y);
+        nz = cube_normal_component(__fsub_rn(pz, pc.z), pc.w, th.x, th.y);
     } else {                                            // cylinderHitDetails :345-365
         const float4 pb = __ldg(&prims[id * 5 + 2]);
         const float4 pv = __ldg(&prims[id * 5 + 3]);

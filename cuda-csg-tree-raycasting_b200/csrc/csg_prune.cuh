@@ -401,7 +401,13 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
 //      Difference: the left one; Intersection: the smaller).
 // The trees differ from csg_prune_kernel's only where that one drops a whole operator by its box before looking at the
 // primitives (never the other way round), and frames are byte-identical with either (tests/test_gpu_parity.py).
-constexpr int kFlatThreads = 128;
+#ifdef CSG_PRUNE_PROBE   // one-off instrumented build (tools/gpu_prune_probe.py): globaltimer at the phase boundaries of every tile CTA
+__device__ unsigned long long g_prune_probe[4096][16];
+#define PROBE(k) do { if (threadIdx.x == 0 && blockIdx.x < 4096) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_prune_probe[blockIdx.x][k] = t_; } } while (0)
+#else
+#define PROBE(k) do { } while (0)
+#endif
+constexpr int kFlatThreadsMax = 512;   // CTA sizes: 128 (many tiles: throughput), 256, 512 (few tiles: the per-tile latency is the frame's fixed cost)
 constexpr int kFlatMaxNodes = 32768;   // 2 x 16-bit prefix sums per node in shared memory (128 KB at the limit)
 
 struct FlatTileSmem {                  // followed by uint16_t A[n_pad], S[n_pad]
@@ -409,13 +415,15 @@ struct FlatTileSmem {                  // followed by uint16_t A[n_pad], S[n_pad
     uint32_t meta[kSlotMax];           // kind | right operand (record index) << 8
     unsigned char flg[kSlotMax];       // bit0 pure, bit1 bounded
     unsigned char done[kSlotMax];      // box and flags are final
-    unsigned int wsum[kFlatThreads / 32];
+    unsigned int wsum[kFlatThreadsMax / 32];
+    float plane[5][4];                 // the tile's frustum
     unsigned int start[kCostBuckets];  // ordering tail
     unsigned int last;
 };
 
 // Inclusive prefix sum of v[0, n) in place by the whole CTA; every thread owns `chunk` consecutive elements (odd: the
 // strided accesses then fall into distinct banks).  Ends with a barrier.
+template <int T>
 __device__ __forceinline__ void cta_scan_u16(unsigned short* v, int n, int chunk, unsigned int* wsum)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -431,15 +439,16 @@ __device__ __forceinline__ void cta_scan_u16(unsigned short* v, int n, int chunk
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
     unsigned int run = inc - s;
-    for (int k = 0; k < warp; ++k) run += wsum[k];
+#pragma unroll
+    for (int k = 0; k < T / 32; ++k) run += k < warp ? wsum[k] : 0u;
     for (int i = b; i < e; ++i) { run += v[i]; v[i] = (unsigned short)run; }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kFlatThreads) csg_prune_flat_kernel(const __grid_constant__ PruneParams q)
+template <int T>
+__global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant__ PruneParams q)
 {
     extern __shared__ __align__(16) unsigned char psm[];
-    constexpr int T = kFlatThreads;
     const int tid = threadIdx.x;
     const float ox = q.cam_pos[0], oy = q.cam_pos[1], oz = q.cam_pos[2];
     const int N = q.n_nodes, S = q.slot_nodes;
@@ -457,6 +466,7 @@ __global__ void __launch_bounds__(kFlatThreads) csg_prune_flat_kernel(const __gr
         return;
     }
     const int tile = (int)blockIdx.x;
+    PROBE(0);
     FlatTileSmem& w = *reinterpret_cast<FlatTileSmem*>(psm);
     const int n_pad = (N + 7) & ~7;
     unsigned short* A = reinterpret_cast<unsigned short*>(psm + sizeof(FlatTileSmem));
@@ -465,12 +475,25 @@ __global__ void __launch_bounds__(kFlatThreads) csg_prune_flat_kernel(const __gr
     int mx, my;
     tile_of(q, tile, mx, my);
     const int slot = (my * q.macro_x + mx) / q.shard_count;
-    float pn[5][3];
-    tile_frustum(q, mx, my, pn);
-
-    // ---- 1. reachable primitives
+    const int chunk = ((N + T - 1) / T) | 1;
+    // the frustum is worked out by the first warp only (divisions, cross products: ~150 dependent instructions), while the
+    // other warps clear the flags; everybody then keeps the five planes in registers, with the absolute values of the
+    // normals: box [c - e, c + e] is outside plane n when n.c + |n|.e < 0
+    if (tid < 32) {
+        float pn0[5][3];
+        tile_frustum(q, mx, my, pn0);
+        if (tid < 5) { w.plane[tid][0] = pn0[tid][0]; w.plane[tid][1] = pn0[tid][1]; w.plane[tid][2] = pn0[tid][2]; }
+    }
     for (int i = tid; i < N; i += T) A[i] = 0;
     __syncthreads();
+    float pn[5][3], pa[5][3];
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { pn[c][k] = w.plane[c][k]; pa[c][k] = fabsf(pn[c][k]); }
+    PROBE(1);
+
+    // ---- 1. reachable primitives
     for (int k0 = tid; k0 < q.n_leaves; k0 += 4 * T) {   // batches of four: all eight loads of a batch in flight together
         float4 la[4], lb[4];
 #pragma unroll
@@ -481,15 +504,24 @@ __global__ void __launch_bounds__(kFlatThreads) csg_prune_flat_kernel(const __gr
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float lo[3] = {la[j].x - ox, la[j].y - oy, la[j].z - oz}, hi[3] = {lb[j].x - ox, lb[j].y - oy, lb[j].z - oz};
-            if (k0 + j * T < q.n_leaves && !box_outside(pn, lo, hi)) A[__float_as_int(la[j].w)] = 1;
+            // centre (relative to the camera) and half extent of the culling box
+            const float ex = 0.5f * (lb[j].x - la[j].x), ey = 0.5f * (lb[j].y - la[j].y), ez = 0.5f * (lb[j].z - la[j].z);
+            const float cx = (la[j].x - ox) + ex, cy = (la[j].y - oy) + ey, cz = (la[j].z - oz) + ez;
+            bool outside = false;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const float m = fmaf(pn[c][0], cx, fmaf(pn[c][1], cy, pn[c][2] * cz)) + fmaf(pa[c][0], ex, fmaf(pa[c][1], ey, pa[c][2] * ez));
+                outside = outside || (m < 0.0f);
+            }
+            if (k0 + j * T < q.n_leaves && !outside) A[__float_as_int(la[j].w)] = 1;
         }
     }
     __syncthreads();
 
+    PROBE(2);
     // ---- 2./3. reachable primitives per subtree, survivors; primitives below an operator that is gone are taken away
     for (;;) {
-        cta_scan_u16(A, N, q.flat_chunk, w.wsum);
+        cta_scan_u16<T>(A, N, chunk, w.wsum);
         bool gone = false;
         for (int n0 = tid; n0 < N; n0 += 8 * T) {   // batches of eight: the topology loads of a batch are in flight together
             uint2 tp[8];
@@ -530,8 +562,10 @@ __global__ void __launch_bounds__(kFlatThreads) csg_prune_flat_kernel(const __gr
         __syncthreads();
     }
 
+    PROBE(3);
     // ---- 4. preorder numbering of the survivors
-    cta_scan_u16(Sv, N, q.flat_chunk, w.wsum);
+    cta_scan_u16<T>(Sv, N, chunk, w.wsum);
+    PROBE(4);
     const uint32_t kept = Sv[N - 1];
     const bool overflow = kept > (uint32_t)S;
     // heavy tiles (more nodes) are handed out first by the frame kernel: bucket lists now (the round trips of the atomic and
@@ -572,42 +606,48 @@ __global__ void __launch_bounds__(kFlatThreads) csg_prune_flat_kernel(const __gr
             }
         }
         __syncthreads();
-        // ---- bottom-up refit in rounds: an operator whose operands are both done computes its box and flags; rounds = height of
-        //      the tile's tree (a handful), two barriers each, shared memory only
-        for (;;) {
-            unsigned int now = 0u;
-            int pending = 0;
-            for (int i = tid, k = 0; i < (int)kept; i += T, ++k) {
-                const uint32_t m = w.meta[i], kind = m & 7u;
-                if (kind >= 3u || w.done[i]) continue;
-                const int a = i + 1, b = (int)(m >> 8);
-                if (!(w.done[a] && w.done[b])) { pending = 1; continue; }
-                const float* bl = w.box[a];
-                const float* br = w.box[b];
-                float* bo = w.box[i];
-                if (kind == 0u) {                   // Union: both operands
+        PROBE(5);
+        // ---- bottom-up refit in rounds, by one warp (warp barriers only): an operator whose operands are both done computes
+        //      its box and flags; rounds = height of the tile's tree (a handful), shared memory only
+        if (tid < 32) {
+            for (;;) {
+                unsigned int now = 0u;
+                bool pending = false;
+                for (int i = tid, k = 0; i < (int)kept; i += 32, ++k) {
+                    const uint32_t m = w.meta[i], kind = m & 7u;
+                    if (kind >= 3u || w.done[i]) continue;
+                    const int a = i + 1, b = (int)(m >> 8);
+                    if (!(w.done[a] && w.done[b])) { pending = true; continue; }
+                    const float* bl = w.box[a];
+                    const float* br = w.box[b];
+                    float* bo = w.box[i];
+                    if (kind == 0u) {                   // Union: both operands
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) { bo[c] = fminf(bl[c], br[c]); bo[3 + c] = fmaxf(bl[3 + c], br[3 + c]); }
-                } else if (kind == 1u) {            // Difference: a subset of the left operand
+                        for (int c = 0; c < 3; ++c) { bo[c] = fminf(bl[c], br[c]); bo[3 + c] = fmaxf(bl[3 + c], br[3 + c]); }
+                    } else if (kind == 1u) {            // Difference: a subset of the left operand
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) bo[c] = bl[c];
-                } else {                            // Intersection: a subset of both; the smaller box
-                    float vl = 1.f, vr = 1.f;
+                        for (int c = 0; c < 6; ++c) bo[c] = bl[c];
+                    } else {                            // Intersection: a subset of both; the smaller box
+                        float vl = 1.f, vr = 1.f;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) { vl *= fmaxf(bl[3 + c] - bl[c], 0.f); vr *= fmaxf(br[3 + c] - br[c], 0.f); }
-                    const float* bs = vl <= vr ? bl : br;
+                        for (int c = 0; c < 3; ++c) { vl *= fmaxf(bl[3 + c] - bl[c], 0.f); vr *= fmaxf(br[3 + c] - br[c], 0.f); }
+                        const float* bs = vl <= vr ? bl : br;
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) bo[c] = bs[c];
+                        for (int c = 0; c < 6; ++c) bo[c] = bs[c];
+                    }
+                    const uint32_t fl = w.flg[a], fr = w.flg[b];
+                    w.flg[i] = (unsigned char)(((kind == 0u) ? (fl & fr & 1u) : 0u) | (fl & fr & 2u));
+                    now |= 1u << k;
                 }
-                const uint32_t fl = w.flg[a], fr = w.flg[b];
-                w.flg[i] = (unsigned char)(((kind == 0u) ? (fl & fr & 1u) : 0u) | (fl & fr & 2u));
-                now |= 1u << k;
+                __syncwarp();
+                for (int i = tid, k = 0; i < (int)kept; i += 32, ++k)
+                    if ((now >> k) & 1u) w.done[i] = 1;
+                __syncwarp();
+                if (!__any_sync(0xffffffffu, pending)) break;
             }
-            __syncthreads();
-            for (int i = tid, k = 0; i < (int)kept; i += T, ++k)
-                if ((now >> k) & 1u) w.done[i] = 1;
-            if (!__syncthreads_or(pending)) break;
         }
+        __syncthreads();
+        PROBE(6);
         // ---- records of the operators
         for (int i = tid; i < (int)kept; i += T) {
             const uint32_t m = w.meta[i], kind = m & 7u;
@@ -623,6 +663,7 @@ __global__ void __launch_bounds__(kFlatThreads) csg_prune_flat_kernel(const __gr
         flags = (rk >= 3u ? kTileRootLeaf : 0u) | ((rk < 3u && (w.flg[0] & 1u)) ? kTileRootPure : 0u);
     }
 
+    PROBE(7);
     // ---- descriptor, and the count of finished tiles (release: this tile's list entry; acquire: everybody else's)
     if (tid == 0) {
         q.desc[slot] = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
@@ -636,6 +677,7 @@ __global__ void __launch_bounds__(kFlatThreads) csg_prune_flat_kernel(const __gr
         w.last = last;
     }
     __syncthreads();
+    PROBE(8);
     if (!w.last) return;
     // last CTA of the grid: concatenate the bucket lists, heaviest bucket first, and reset the counters for the next frame
     static_assert(kCostBuckets == 64, "two buckets per lane");
@@ -675,6 +717,7 @@ __global__ void __launch_bounds__(kFlatThreads) csg_prune_flat_kernel(const __gr
         for (int j = 0; j < 4; ++j)
             if (i0 + j * T < q.n_tiles) q.order[i0 + j * T] = v[j];
     }
+    PROBE(9);
 }
 
 }  // namespace csgb

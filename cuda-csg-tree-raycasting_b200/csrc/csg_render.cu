@@ -100,7 +100,6 @@ struct csg_context {
     bool prune_flat = true;      // by csg_prune_flat_kernel (prefix sums over the preorder layout); false: csg_prune_kernel (tree walk)
     bool flat_ok = false;        // the tree is small enough for csg_prune_flat_kernel
     size_t flat_smem = 0;
-    int flat_chunk = 1;
     int slot_nodes = 0;          // records per tile slot
     size_t prune_smem = 0;
     uint32_t full_flags = 0;
@@ -345,7 +344,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes; q.parent = s.d_parent;
             q.leaf_boxes = s.d_leaf_boxes; q.n_leaves = (int)(c->tree.leaf_boxes.size() / 8);
             q.mark_words = c->mark_words; q.marks_first = c->marks_first;
-            q.topo = s.d_topo; q.flat_chunk = c->flat_chunk;
+            q.topo = s.d_topo;
             q.n_slots = s.n_slots; q.hist = s.d_hist; q.done = s.d_hist ? s.d_hist + kCostBuckets : nullptr;
             q.lists = s.d_lists; q.order = s.d_order;
             q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes;
@@ -356,7 +355,17 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             s.last_q_valid = true;
             const int stage_ctas = std::max(1, std::min(64, (fp.n_nodes + kPruneThreads - 1) / kPruneThreads));
             if (!cached) {
-                if (c->prune_flat && c->flat_ok) csg_prune_flat_kernel<<<q.n_tiles + stage_ctas, kFlatThreads, c->flat_smem, s.stream>>>(q);
+                if (c->prune_flat && c->flat_ok) {
+                    // CTA size by the number of tiles: with few tiles per SM the per-tile latency is what the frame waits for
+                    int sms = 148;
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.device);
+                    int ft = q.n_tiles <= sms ? 512 : q.n_tiles <= 3 * sms ? 256 : 128;
+                    if (const char* e = std::getenv("CSG_B200_FLAT_THREADS")) ft = std::atoi(e);   // tuning aid
+                    const unsigned grid = (unsigned)(q.n_tiles + stage_ctas);
+                    if (ft == 512) csg_prune_flat_kernel<512><<<grid, 512, c->flat_smem, s.stream>>>(q);
+                    else if (ft == 256) csg_prune_flat_kernel<256><<<grid, 256, c->flat_smem, s.stream>>>(q);
+                    else csg_prune_flat_kernel<128><<<grid, 128, c->flat_smem, s.stream>>>(q);
+                }
                 else csg_prune_kernel<<<(q.n_tiles + kPruneWarps - 1) / kPruneWarps + stage_ctas, kPruneThreads, c->prune_smem, s.stream>>>(q);
             }
             cudaError_t e = cudaGetLastError();
@@ -468,7 +477,6 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         c->prune_alloc = c->prune;
         // csg_prune_flat_kernel: two 16-bit prefix sums per node behind the fixed part of its shared memory
         c->flat_ok = n <= (size_t)kFlatMaxNodes;
-        c->flat_chunk = (int)((n + kFlatThreads - 1) / kFlatThreads) | 1;
         c->flat_smem = sizeof(FlatTileSmem) + 2 * ((n + 7) & ~(size_t)7) * sizeof(unsigned short);
         const char* walk = std::getenv("CSG_B200_PRUNE_WALK");   // tuning aid: the tree-walking kernel instead
         c->prune_flat = !(walk && walk[0] == '1');
@@ -549,8 +557,11 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
                 for (size_t k = 0; k < topo.size(); ++k) topo[k] = make_uint2(c->tree.nodes[k].meta, c->tree.subtree_end[k]);
                 CU(cudaMalloc(&s.d_topo, std::max<size_t>(topo.size(), 1) * sizeof(uint2)));
                 CU(cudaMemcpy(s.d_topo, topo.data(), topo.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-                if (c->flat_smem > 48 * 1024)
-                    CU(cudaFuncSetAttribute(csg_prune_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
+                if (c->flat_smem > 48 * 1024) {
+                    CU(cudaFuncSetAttribute(csg_prune_flat_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
+                    CU(cudaFuncSetAttribute(csg_prune_flat_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
+                    CU(cudaFuncSetAttribute(csg_prune_flat_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
+                }
             }
         }
         const size_t prim_bytes = c->tree.prims.size() * sizeof(PrimRec);
@@ -671,6 +682,8 @@ size_t csg_generate_scene(int n_primitives, uint64_t seed, char* buf, size_t buf
     }
     return s.size();
 }
+
+float csg_cube_normal_threshold(float half_size, float level) { return cube_normal_threshold_of(half_size, level); }
 
 int csg_scene_set_optimize(csg_scene* scene, int level)
 {
@@ -1141,6 +1154,18 @@ int csg_fp32_peak_tflops(int device, float* tflops)
     *tflops = best;
     return CSG_OK;
 }
+
+#ifdef CSG_PRUNE_PROBE
+int csg_debug_prune_probe(void* out, size_t bytes)
+{
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out, g_prune_probe, std::min(bytes, sizeof(unsigned long long) * 4096 * 16)));
+    void* sym = nullptr;
+    CU(cudaGetSymbolAddress(&sym, g_prune_probe));
+    CU(cudaMemset(sym, 0, sizeof(unsigned long long) * 4096 * 16));
+    return CSG_OK;
+}
+#endif
 
 const char* csg_context_info(csg_context* ctx) { return ctx ? ctx->info.c_str() : ""; }
 

@@ -328,6 +328,29 @@ Box leaf_cull_box(const RefPrim& p, int type)
     return b;
 }
 
+// Smallest positive float a with fl(fl(a / half) * 1.00001f) >= level (RaycastingKernels.cu:422-424 in the reference's own
+// operations: IEEE float division and multiplication, both monotonic in a for half > 0), found by bisection over the bit
+// patterns.  0 when half is not a positive normal number (the kernel then always evaluates the reference's expression).
+float cube_normal_threshold(float half, float level)
+{
+    if (!(half >= 1.17549435e-38f) || !std::isfinite(half)) return 0.0f;
+    auto reaches = [&](uint32_t bits) {
+        float a;
+        std::memcpy(&a, &bits, 4);
+        volatile float q = a / half;          // volatile: one IEEE rounding per operation, no contraction, no excess precision
+        volatile float m = q * 1.00001f;
+        return m >= level;
+    };
+    uint32_t lo = 0u, hi = 0x7f800000u;       // +0 .. +inf; reaches(+inf) is true, reaches(+0) is false
+    while (hi - lo > 1u) {
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        if (reaches(mid)) hi = mid; else lo = mid;
+    }
+    float a;
+    std::memcpy(&a, &hi, 4);
+    return std::isfinite(a) ? a : 0.0f;
+}
+
 struct Builder {
     const Scene& s;
     std::vector<Work> w;
@@ -421,6 +444,8 @@ struct Builder {
 
 }  // namespace
 
+float cube_normal_threshold_of(float half, float level) { return cube_normal_threshold(half, level); }
+
 void flatten(const Scene& s, int optimize, FlatTree& out)
 {
     out.nodes.clear();
@@ -453,6 +478,11 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
         r.color[3] = (float)n.type;
         if (n.type == kCube) {
             r.centre[3] = p.p[0] / 2;  // halfSize, RaycastingKernels.cu:423
+            // cube normal (:422-424): n = (float)(int)((pc / halfSize) * 1.00001f) is a monotonic, odd step function of pc.
+            // base[0], base[1] = the smallest |pc| that gives +-1 and +-2: below base[0] the component is 0, below base[1] it is
+            // +-1, and the kernel falls back to the reference's arithmetic beyond (or always, when both are 0).
+            r.base[0] = cube_normal_threshold(r.centre[3], 1.0f);
+            r.base[1] = cube_normal_threshold(r.centre[3], 2.0f);
         } else if (n.type == kCylinder) {
             const float hh = p.p[1] * 0.5f;  // height / 2
             for (int k = 0; k < 3; ++k) {

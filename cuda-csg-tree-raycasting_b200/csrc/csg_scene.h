@@ -47,7 +47,7 @@ constexpr uint32_t kMetaPure = 1u << 6;
 struct PrimRec {
     float color[4];   // r g b, kind
     float centre[4];  // x y z, p0 (radius | half size)
-    float base[4];    // cylinder: C = centre - (h/2)V, height
+    float base[4];    // cylinder: C = centre - (h/2)V, height;  cube: |p - centre| thresholds of the normal components +-1, +-2 (0: none)
     float axis[4];    // cylinder: V, radius
     float haxis[4];   // cylinder: (h/2)V
 };
@@ -79,6 +79,10 @@ struct Scene {
 std::string parse_scene(const char* text, size_t len, Scene& out);
 std::string write_scene(const Scene& s);
 std::string generate_scene(int n_primitives, uint64_t seed);
+
+// Smallest |p - centre| for which a component of the cube normal ((float)(int)((pc / half) * 1.00001f), RaycastingKernels.cu:422-424)
+// reaches `level` (1 or 2); 0 when `half` is not a positive normal number.
+float cube_normal_threshold_of(float half, float level);
 
 // Builds the GPU layout.  optimize >= 1 re-balances Union-only subtrees spatially.
 void flatten(const Scene& s, int optimize, FlatTree& out);

@@ -91,6 +91,11 @@ int csg_upload_shard(const csg_scene* scene, int width, int height, int device, 
                      int shard_count, csg_context** out);
 void csg_free_context(csg_context* ctx); /* replaces Raycaster::CleanUp (Raycaster.cu:36-45) */
 
+/* Diagnostic (host only): the cube normal of the reference, (float)(int)(((p - centre) / half_size) * 1.00001f) per component
+ * (RaycastingKernels.cu:422-424), is a step function of |p - centre|; this returns the smallest value for which it reaches
+ * `level` (1 or 2), as csg_upload stores it per cube.  0: half_size is not a positive normal number (no shortcut taken). */
+float csg_cube_normal_threshold(float half_size, float level);
+
 /* Load-time tree optimisation.  0 = keep the parsed tree shape; 1 (default) =
  * spatially re-balance maximal Union-only subtrees and tighten culling boxes.  Results are
  * identical except on exact-tie pixels; must be called before csg_upload. */
@@ -128,9 +133,9 @@ int csg_render_stats(csg_context* ctx, const csg_camera* cam, int32_t* iteration
 
 /* Per-tile tree pruning (on by default): before each frame every 64x32-pixel tile gets its own copy of the tree holding only
  * the primitives its rays can reach (operators left with one operand collapse to it).  Results are identical with and
- * without it.  mode 0: every tile reads the whole tree; 1 (default): per-tile trees, built by csg_prune_flat_kernel (prefix
- * sums over the preorder layout; trees of up to 32768 nodes, larger ones use the walk); 2: per-tile trees built by the
- * tree-walking csg_prune_kernel.
+ * without it.  mode 0: every tile reads the whole tree; 1 (default): per-tile trees built with prefix sums over
+ * the preorder layout (the flat pruning kernel; trees of up to 32768 nodes, larger ones use the walk); 2: per-tile trees built
+ * by the tree-walking pruning kernel.
  * csg_prune_stats reports the last frame of shard 0: traced tiles, tiles no primitive reaches, tiles whose tree did not fit
  * its slot (they read the whole tree), and the total number of nodes over all pruned trees. */
 int csg_set_pruning(csg_context* ctx, int mode);

@@ -193,3 +193,37 @@ def test_two_rank_sharding_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_OK" in r.stdout
+
+
+def test_cube_normal_thresholds_reproduce_the_reference_expression(csg):
+    """The kernel replaces (float)(int)((pc / half) * 1.00001f) (RaycastingKernels.cu:422-424) by two comparisons against
+    host-computed thresholds; checked here against the expression itself in float32, around the steps and at random."""
+    import numpy as np
+    f32 = np.float32
+    rng = np.random.default_rng(5)
+
+    def ref(pc, half):
+        with np.errstate(all="ignore"):
+            v = (pc / half) * f32(1.00001)            # float32 operations, one rounding each
+            return np.trunc(v).astype(np.float32) + f32(0.0)   # (float)(int): -0 becomes +0
+
+    halves = [f32(x) for x in (10.0, 1.0, 0.5, 0.35, 3.0, 1e-3, 123.456, 2.0 ** -20, 7e8)] + [f32(h) for h in rng.uniform(0.01, 50, 40)]
+    for half in halves:
+        a1, a2 = f32(csg.cube_normal_threshold(half, 1)), f32(csg.cube_normal_threshold(half, 2))
+        assert 0 < a1 < a2
+        pts = [rng.uniform(-2.5, 2.5, 4000).astype(np.float32) * half]
+        for a in (a1, a2):
+            bits = np.array([a], np.float32).view(np.uint32)[0]
+            near = (np.arange(-300, 301, dtype=np.int64) + int(bits)).astype(np.uint32).view(np.float32)
+            pts += [near, -near]
+        pts.append(np.array([0.0, -0.0, half, -half], np.float32))
+        pc = np.concatenate(pts)
+        want = ref(pc, half)
+        m = np.abs(pc)
+        got = np.where(m < a1, f32(0.0), np.where(m < a2, np.copysign(f32(1.0), pc), want))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"half={half}"
+        # the thresholds are tight: one ulp below a1 still gives 0
+        below = np.nextafter(a1, f32(0.0))
+        assert ref(np.array([below], np.float32), half)[0] == 0 and ref(np.array([a1], np.float32), half)[0] == 1
+    for bad in (0.0, -1.0, float("inf"), float("nan"), 1e-45):
+        assert csg.cube_normal_threshold(bad, 1) == 0.0
