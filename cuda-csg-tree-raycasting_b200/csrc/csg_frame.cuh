@@ -297,6 +297,14 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     return L;                                   // :511
 }
 
+#ifdef CSG_FRAME_PROBE   // one-off instrumented build (tools/gpu_frame_probe.py): per-warp timeline of the frame kernel
+__device__ unsigned long long g_frame_probe[8192][8];
+__device__ __forceinline__ unsigned long long probe_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define FPROBE(k, v) do { if (lane == 0 && pw < 8192) g_frame_probe[pw][k] = (v); } while (0)
+#else
+#define FPROBE(k, v) do { } while (0)
+#endif
+
 template <int MODE, int kThreads, bool kSuper>   // kSuper: more than one ray per pixel (keeps the sample loop and its accumulators out of the common case)
 __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_kernel(const __grid_constant__ FrameParams p)
 {
@@ -309,6 +317,11 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
 
     const int tid = threadIdx.x, lane = tid & 31;
     const float ox = p.cam_pos[0], oy = p.cam_pos[1], oz = p.cam_pos[2];
+#ifdef CSG_FRAME_PROBE
+    const int pw = blockIdx.x * (kThreads / 32) + (tid >> 5);
+    unsigned long long pr_longest = 0, pr_tiles = 0, pr_t0 = 0, pr_longest_ticket = 0;
+    FPROBE(0, probe_now());
+#endif
 
     if (tid < 27) s_table[tid] = kOutcomeTable[tid];
     if (tid == 27) {   // L = normalize(lightDir), LightningKernel :78: the same for every pixel of the frame
@@ -374,10 +387,14 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     }
 
     // everything below reads what csg_prune_kernel wrote (tile descriptors, pruned trees, hand-out order)
+    FPROBE(1, probe_now());
     cudaGridDependencySynchronize();
+    FPROBE(2, probe_now());
 
-    // ---- phase 2: dynamic tile scheduling over the macro tiles that touch the bound: one ticket per warp tile; the next
-    // ticket is requested before the current tile is rendered so the atomic's round trip hides behind the traversal.
+    // ---- phase 2: dynamic tile scheduling over the macro tiles that touch the bound: one ticket per warp tile.  The next
+    // ticket is requested when the traversal of the current tile is over, so that the atomic's round trip hides behind the
+    // shading — not earlier: a ticket taken at the start of a heavy tile would sit with this warp while others run dry
+    // (with few tiles per warp, e.g. a frame sharded over 8 GPUs, that decided the length of the frame).
     // Ticket t -> macro tile number (t >> 6) * shard_count + shard_rank of the rm_w x rm_h macro rectangle, warp tile t & 63.
     unsigned int ticket = 0;
     if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u) - p.counter_base;
@@ -388,10 +405,15 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     // one warp, and the per-ticket set-up (descriptor, tree copy) is still shared by a few passes.
     const int sp = kSuper ? p.sp_shift : 0, gp = kSuper ? p.sp_group : 0;
     while (ticket < (unsigned int)p.n_local_warp_tiles) {
+#ifdef CSG_FRAME_PROBE
+        if (pr_tiles == 0) FPROBE(3, probe_now());
+        pr_t0 = probe_now();
+        const unsigned int pr_ticket = ticket;
+#endif
         const unsigned int cur = ticket >> (sp - gp);
         const int pass0 = (int)(ticket & ((1u << (sp - gp)) - 1u)) << gp;
         unsigned int next = 0;
-        if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+        int req_lane = -1;   // lane that has asked for the next ticket (-1: nobody yet)
         const int k = (int)(cur & 63u);
         // traced tiles are handed out heaviest first (order[] from csg_prune_kernel: tiles whose pruned tree is larger come
         // first, so that the expensive tiles are not the ones still running when the ticket counter runs dry)
@@ -404,7 +426,11 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         const int ky = ((k >> 1) & 1) | ((k >> 2) & 2) | ((k >> 3) & 4);
         const int tx0 = mx * kMacroW + kx * kWarpTileW, ty0 = my * kMacroH + ky * kWarpTileH;   // the warp tile's corner
         ticket = 0xffffffffu;   // placeholder; the real value is broadcast at the end of the iteration
-        if (tx0 >= p.width || ty0 >= p.height) { ticket = __shfl_sync(0xffffffffu, next, 0); continue; }
+        if (tx0 >= p.width || ty0 >= p.height) {
+            if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+            ticket = __shfl_sync(0xffffffffu, next, 0);
+            continue;
+        }
 
         // this macro tile's pruned tree (csg_prune_kernel): only the primitives its rays can reach, operators whose other
         // operand cannot be reached collapsed away.  n_nodes == 0: every ray of the tile is a Miss.
@@ -432,13 +458,16 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             }
             const bool active = x < p.width && y < p.height;
             const uint32_t pix = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;   // :33 (csg_upload keeps width*height below 2^31)
-            if (__ballot_sync(0xffffffffu, active) == 0u) continue;
+            const unsigned int amask = __ballot_sync(0xffffffffu, active);
+            if (amask == 0u) continue;
+            const bool last_pass = pass == pass0 + (1 << gp) - 1;
 
             Hit res = make_miss();
             int iters = 0;
             Ray r;
             r.ox = ox; r.oy = oy; r.oz = oz;
             float accx = 0.f, accy = 0.f, accz = 0.f;
+            if (last_pass && !tile_empty) req_lane = __ffs(amask) - 1;
             if (tile_empty) {
                 const float w = (float)(ss * ss);
                 accx = 0.08f * w; accy = 0.08f * w; accz = 0.11f * w;
@@ -465,6 +494,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                     r.ix = rcp_approx(cx); r.iy = rcp_approx(cy); r.iz = rcp_approx(cz);   // culling boxes only: they carry 1e-5 of slack
                     res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u,
                                                     (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
+                    if (last_pass && s == n_samples - 1 && lane == __ffs(amask) - 1)   // the tile is traced: ask for the next ticket now
+                        next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
                     if (MODE != OUT_AOV) {
                         const float4 c = shade_pixel(res, r, p.prims, p, s_light);
                         accx += c.x; accy += c.y; accz += c.z;
@@ -518,8 +549,18 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                 }
             }
         }
-        ticket = __shfl_sync(0xffffffffu, next, 0);
+#ifdef CSG_FRAME_PROBE
+        { const unsigned long long d = probe_now() - pr_t0; ++pr_tiles; if (d > pr_longest) { pr_longest = d; pr_longest_ticket = pr_ticket; } }
+#endif
+        if (req_lane < 0) {   // nothing was traced (empty tile, tile outside the frame)
+            if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+            req_lane = 0;
+        }
+        ticket = __shfl_sync(0xffffffffu, next, req_lane);
     }
+#ifdef CSG_FRAME_PROBE
+    FPROBE(4, probe_now()); FPROBE(5, pr_longest); FPROBE(6, pr_tiles); FPROBE(7, pr_longest_ticket);
+#endif
 }
 
 // tan(cam.fov / 2.0f) of RaycastKernel :15-16, evaluated with the device tanf once per field of view (kept out of

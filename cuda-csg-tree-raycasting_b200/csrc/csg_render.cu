@@ -1155,6 +1155,18 @@ int csg_fp32_peak_tflops(int device, float* tflops)
     return CSG_OK;
 }
 
+#ifdef CSG_FRAME_PROBE
+int csg_debug_frame_probe(void* out, size_t bytes)
+{
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out, g_frame_probe, std::min(bytes, sizeof(unsigned long long) * 8192 * 8)));
+    void* sym = nullptr;
+    CU(cudaGetSymbolAddress(&sym, g_frame_probe));
+    CU(cudaMemset(sym, 0, sizeof(unsigned long long) * 8192 * 8));
+    return CSG_OK;
+}
+#endif
+
 #ifdef CSG_PRUNE_PROBE
 int csg_debug_prune_probe(void* out, size_t bytes)
 {
