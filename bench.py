@@ -210,7 +210,7 @@ def bench_ours(args):
     e2e_s = float(e2e.cpu().numpy().mean())
 
     # ---- extra (not the headline): the same frames with the opt-in view cache — an unchanged camera keeps its per-tile
-    # trees, so csg_prune_kernel is skipped (the reference application's static camera with a moving light)
+    # trees, so the pruning kernel is skipped (the reference application's static camera with a moving light)
     static_ms = None
     if world == 1:
         ctx.set_view_cache(True)
@@ -303,7 +303,7 @@ def bench_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": data_note,
         "config": {"workload": WORKLOAD, "parallelism": f"screen tiles 64x32 interleaved over {world} GPU(s), NVLink peer stores into rank 0",
                    "l2": "256 MiB device memset between timed frames (L2 flush); inputs are 33 KB of tree + 68 B of camera/light",
-                   "launches_per_frame": "2 per GPU: csg_prune_kernel (per-tile pruned trees, rebuilt every frame) + csg_frame_kernel, "
+                   "launches_per_frame": "2 per GPU: csg_prune_flat_kernel (per-tile pruned trees, rebuilt every frame) + csg_frame_kernel, "
                                          "chained by programmatic dependent launch; both inside the timed region",
                    "optimize": args.optimize, "launch": ctx.info()},
         "e2e": {"value": nrays / e2e_s, "unit": "rays/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 256,

@@ -10,6 +10,6 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 0 2>&1 | tail -1
 timeout 600 python bench.py 2>&1 | tail -1 | tee gpurun_out/bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-baselines > gpurun_out/ncu_launches_run.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"csg_frame_kernel|csg_prune_kernel" -s 8 -c 4 -f -o gpurun_out/prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"csg_frame_kernel|csg_prune" -s 8 -c 4 -f -o gpurun_out/prof \
     python bench.py --steps 3 --warmup 3 --no-baselines > gpurun_out/ncu_full_run.log 2>&1
 ls -la gpurun_out

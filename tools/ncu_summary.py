@@ -55,7 +55,7 @@ def num(d, k):
     return v * mult
 
 
-out = {"tag": tag, "command": "ncu --set full --clock-control none --import-source on -k regex:'csg_frame_kernel|csg_prune_kernel' -s 8 -c 4 python bench.py --steps 3 --warmup 3 --no-baselines",
+out = {"tag": tag, "command": "ncu --set full --clock-control none --import-source on -k regex:'csg_frame_kernel|csg_prune' -s 8 -c 4 python bench.py --steps 3 --warmup 3 --no-baselines",
        "launches": summ}
 frame = [d for d in summ if "frame" in d["Kernel Name"]["value"]]
 prune = [d for d in summ if "prune" in d["Kernel Name"]["value"]]
@@ -131,5 +131,10 @@ with open(os.path.join(dst, f"{tag}_instruction_mix.txt"), "w") as f:
         f.write("\nwarp stall samples by reason:\n")
         for c, n in stall.most_common(12):
             f.write(f"  {c:28s} {n:9d} {100 * n / ts:5.1f}%\n")
+# hottest source lines of both kernels (instructions executed, stall samples)
+for kern, name in (("csg_frame_kernel", "frame"), ("csg_prune", "prune")):
+    txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, kern, "45"], capture_output=True, text=True).stdout
+    with open(os.path.join(dst, f"{tag}_{name}_kernel_lines.txt"), "w") as f:
+        f.write(txt)
 print(json.dumps({k: v["value"] for k, v in (summ[-1] if summ else {}).items()}, indent=1))
 print(open(os.path.join(dst, f"{tag}_instruction_mix.txt")).read()[-700:])
