@@ -391,10 +391,11 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     cudaGridDependencySynchronize();
     FPROBE(2, probe_now());
 
-    // ---- phase 2: dynamic tile scheduling over the macro tiles that touch the bound: one ticket per warp tile.  The next
-    // ticket is requested when the traversal of the current tile is over, so that the atomic's round trip hides behind the
-    // shading — not earlier: a ticket taken at the start of a heavy tile would sit with this warp while others run dry
-    // (with few tiles per warp, e.g. a frame sharded over 8 GPUs, that decided the length of the frame).
+    // ---- phase 2: dynamic tile scheduling over the macro tiles that touch the bound: one ticket per warp tile.  With one
+    // ray per pixel the next ticket is requested when the traversal of the current tile is over, so that the atomic's round
+    // trip hides behind the shading — not earlier: a ticket taken at the start of a heavy tile would sit with this warp while
+    // others run dry (with few tiles per warp, e.g. a frame sharded over 8 GPUs, that decided the length of the frame).
+    // With supersampling a ticket is a few passes of a warp tile and there are plenty: it is requested up front.
     // Ticket t -> macro tile number (t >> 6) * shard_count + shard_rank of the rm_w x rm_h macro rectangle, warp tile t & 63.
     unsigned int ticket = 0;
     if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u) - p.counter_base;
@@ -413,7 +414,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         const unsigned int cur = ticket >> (sp - gp);
         const int pass0 = (int)(ticket & ((1u << (sp - gp)) - 1u)) << gp;
         unsigned int next = 0;
-        int req_lane = -1;   // lane that has asked for the next ticket (-1: nobody yet)
+        int req_lane = kSuper ? 0 : -1;   // lane that has asked for the next ticket (-1: nobody yet)
+        if (kSuper && lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
         const int k = (int)(cur & 63u);
         // traced tiles are handed out heaviest first (order[] from csg_prune_kernel: tiles whose pruned tree is larger come
         // first, so that the expensive tiles are not the ones still running when the ticket counter runs dry)
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         const int tx0 = mx * kMacroW + kx * kWarpTileW, ty0 = my * kMacroH + ky * kWarpTileH;   // the warp tile's corner
         ticket = 0xffffffffu;   // placeholder; the real value is broadcast at the end of the iteration
         if (tx0 >= p.width || ty0 >= p.height) {
-            if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+            if (!kSuper && lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
             ticket = __shfl_sync(0xffffffffu, next, 0);
             continue;
         }
@@ -460,14 +462,13 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             const uint32_t pix = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;   // :33 (csg_upload keeps width*height below 2^31)
             const unsigned int amask = __ballot_sync(0xffffffffu, active);
             if (amask == 0u) continue;
-            const bool last_pass = pass == pass0 + (1 << gp) - 1;
 
             Hit res = make_miss();
             int iters = 0;
             Ray r;
             r.ox = ox; r.oy = oy; r.oz = oz;
             float accx = 0.f, accy = 0.f, accz = 0.f;
-            if (last_pass && !tile_empty) req_lane = __ffs(amask) - 1;
+            if (!kSuper && !tile_empty) req_lane = __ffs(amask) - 1;
             if (tile_empty) {
                 const float w = (float)(ss * ss);
                 accx = 0.08f * w; accy = 0.08f * w; accz = 0.11f * w;
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                     r.ix = rcp_approx(cx); r.iy = rcp_approx(cy); r.iz = rcp_approx(cz);   // culling boxes only: they carry 1e-5 of slack
                     res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u,
                                                     (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
-                    if (last_pass && s == n_samples - 1 && lane == __ffs(amask) - 1)   // the tile is traced: ask for the next ticket now
+                    if (!kSuper && lane == __ffs(amask) - 1)   // the tile is traced: ask for the next ticket now
                         next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
                     if (MODE != OUT_AOV) {
                         const float4 c = shade_pixel(res, r, p.prims, p, s_light);
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
 #ifdef CSG_FRAME_PROBE
         { const unsigned long long d = probe_now() - pr_t0; ++pr_tiles; if (d > pr_longest) { pr_longest = d; pr_longest_ticket = pr_ticket; } }
 #endif
-        if (req_lane < 0) {   // nothing was traced (empty tile, tile outside the frame)
+        if (!kSuper && req_lane < 0) {   // nothing was traced (empty tile)
             if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
             req_lane = 0;
         }

@@ -409,6 +409,7 @@ __device__ unsigned long long g_prune_probe[4096][16];
 #endif
 constexpr int kFlatThreadsMax = 512;   // CTA sizes: 128 (many tiles: throughput), 256, 512 (few tiles: the per-tile latency is the frame's fixed cost)
 constexpr int kFlatMaxNodes = 32768;   // 2 x 16-bit prefix sums per node in shared memory (128 KB at the limit)
+constexpr int kFlatPreferNodes = 2048;  // above this the tree-walking kernel is the faster one (it looks only at what the frustum touches)
 
 struct FlatTileSmem {                  // followed by uint16_t A[n_pad], S[n_pad]
     float box[kSlotMax][6];            // culling box of every record of the tile's tree, origin-relative

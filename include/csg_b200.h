@@ -134,7 +134,7 @@ int csg_render_stats(csg_context* ctx, const csg_camera* cam, int32_t* iteration
 /* Per-tile tree pruning (on by default): before each frame every 64x32-pixel tile gets its own copy of the tree holding only
  * the primitives its rays can reach (operators left with one operand collapse to it).  Results are identical with and
  * without it.  mode 0: every tile reads the whole tree; 1 (default): per-tile trees built with prefix sums over
- * the preorder layout (the flat pruning kernel; trees of up to 32768 nodes, larger ones use the walk); 2: per-tile trees built
+ * the preorder layout (the flat pruning kernel; trees of up to 2048 nodes, larger ones use the walk); 2: per-tile trees built
  * by the tree-walking pruning kernel.
  * csg_prune_stats reports the last frame of shard 0: traced tiles, tiles no primitive reaches, tiles whose tree did not fit
  * its slot (they read the whole tree), and the total number of nodes over all pruned trees. */
