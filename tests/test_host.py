@@ -227,3 +227,14 @@ def test_cube_normal_thresholds_reproduce_the_reference_expression(csg):
         assert ref(np.array([below], np.float32), half)[0] == 0 and ref(np.array([a1], np.float32), half)[0] == 1
     for bad in (0.0, -1.0, float("inf"), float("nan"), 1e-45):
         assert csg.cube_normal_threshold(bad, 1) == 0.0
+
+
+def test_optional_viewer_compiles_against_sdl2_headers():
+    """host/csg_viewer.cpp (SDL2 + OpenGL + CUDA-GL interop, off by default) is syntax-checked against the SDL2 headers the
+    reference vendors; it cannot be linked or run in this image (no SDL2, no OpenGL)."""
+    sdl = "/root/reference/CSGRayCasting/Libraries/include"
+    if not os.path.exists(os.path.join(sdl, "SDL.h")):
+        pytest.skip("SDL2 headers not available (reference checkout absent)")
+    src = os.path.join(ROOT, "cuda-csg-tree-raycasting_b200", "host", "csg_viewer.cpp")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + sdl, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
