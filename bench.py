@@ -308,7 +308,7 @@ def bench_ours(args):
                    "optimize": args.optimize, "launch": ctx.info()},
         "e2e": {"value": nrays / e2e_s, "unit": "rays/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 256,
                 "d2h_bytes_per_step": nrays * 4, "steps": e2e_steps,
-                "what": "csg_render() with a pinned host RGBA8 buffer: camera/light as kernel parameters, the frame rendered in 4 bands of tile rows, each band copied D2H (33 MB in all, PCIe-bound) while the next one renders"},
+                "what": "csg_render() with a pinned host RGBA8 buffer: camera/light as kernel parameters, the frame rendered in bands of tile rows (6 at 4K), each band copied D2H (33 MB in all, PCIe-bound) while the next one renders"},
         "gpu_launches": int(lc.item()),
         "clocks": clocks,
         "roofline": roofline,

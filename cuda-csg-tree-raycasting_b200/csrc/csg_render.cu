@@ -904,10 +904,12 @@ int csg_render(csg_context* ctx, const csg_camera* cam, const csg_light* light, 
     const bool direct = dev && ctx->shards.size() == 1;
     Shard& root = ctx->shards[0];
     const size_t bytes = (size_t)ctx->width * ctx->height * 4;
-    int n_bands = (!dev && ctx->shards.size() == 1 && ctx->shard_count == 1 && !ctx->external_target && ctx->macro_y >= 16) ? 4 : 1;
+    // bands: the first one must be rendered before any byte moves, the others hide behind the copies (PCIe is the bottleneck);
+    // every band costs its own pair of launches.  Measured at 4K (68 tile rows): 1 band 807 us, 4: 672, 6: 659, 8: 686.
+    int n_bands = (!dev && ctx->shards.size() == 1 && ctx->shard_count == 1 && !ctx->external_target && ctx->macro_y >= 16) ? (ctx->macro_y >= 48 ? 6 : 4) : 1;
     if (const char* nb = std::getenv("CSG_B200_BANDS")) n_bands = n_bands > 1 ? std::min(std::max(std::atoi(nb), 1), 8) : 1;   // tuning aid
     if (n_bands > 1) {
-        // Host output on one GPU: the frame is rendered in 4 bands of macro-tile rows; band k travels over PCIe (the 33 MB copy
+        // Host output on one GPU: the frame is rendered in bands of macro-tile rows; band k travels over PCIe (the 33 MB copy
         // is 3x the render time at 4K) while band k+1 renders.
         CU(cudaSetDevice(root.device));
         if (!ctx->copy_stream) {

@@ -104,7 +104,7 @@ int csg_scene_set_optimize(csg_scene* scene, int level);
 /* ---- render: replaces Raycaster::Raycast(float4* devPBO, Camera, DirectionalLight) (Raycaster.cu:23-34).
  * All three are synchronous (return when the output is complete), like the reference. */
 /* rgba8_out: width*height*4 bytes; host OR device pointer (detected with cudaPointerGetAttributes).  With a host pointer on
- * a single-GPU context the frame is rendered in 4 bands of tile rows and each band is copied out while the next renders
+ * a single-GPU context the frame is rendered in bands of tile rows (6 at 4K) and each band is copied out while the next renders
  * (use pinned memory for the copies to overlap). */
 int csg_render(csg_context* ctx, const csg_camera* cam, const csg_light* light, uint8_t* rgba8_out);
 /* rgba_f32_out: width*height float4, linear colour exactly as the reference's LightningKernel writes its
