@@ -12,4 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --cs
     python bench.py --steps 3 --warmup 3 --no-baselines > gpurun_out/ncu_launches_run.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"csg_frame_kernel|csg_prune" -s 8 -c 4 -f -o gpurun_out/prof \
     python bench.py --steps 3 --warmup 3 --no-baselines > gpurun_out/ncu_full_run.log 2>&1
+timeout 300 compute-sanitizer --tool memcheck python tools/gpu_sanitize.py > gpurun_out/memcheck.log 2>&1; tail -2 gpurun_out/memcheck.log
+timeout 300 compute-sanitizer --tool racecheck python tools/gpu_sanitize.py > gpurun_out/racecheck.log 2>&1; tail -2 gpurun_out/racecheck.log
+timeout 300 python tools/gpu_shard_emul.py 30 flat 2>&1 | grep rank0
 ls -la gpurun_out

@@ -8,9 +8,10 @@ import csg_b200 as g
 import scenes
 from oracle_py import View, orbit_view
 
-def go(txt, w, h, ss=1, marks=False, opt=1):
+def go(txt, w, h, ss=1, marks=False, opt=1, walk=False):
     os.environ["CSG_B200_MARKS_FIRST"] = "1" if marks else "0"
     sc = g.Scene.parse(txt, optimize=opt); ctx = sc.upload(w, h); ctx.set_supersampling(ss)
+    ctx.set_pruning(2 if (walk or marks) else 1)   # 1: csg_prune_flat_kernel (default), 2: csg_prune_kernel (walk / leaf marks)
     v = orbit_view(w, h, 7, radius=6.0)
     cam, light = g.Camera(pos=v.pos, pitch=v.pitch, yaw=v.yaw), g.Light()
     a = ctx.render(cam, light).copy()
@@ -25,6 +26,8 @@ print(go(scenes.INLINE["nested"], 200, 120))
 print(go(scenes.INLINE["nested"], 200, 120, ss=4))
 print(go(scenes.INLINE["deep_left_chain"], 130, 70, ss=2, marks=True))
 print(go(g.Scene.generate_text(300, 5), 256, 144))
+print(go(g.Scene.generate_text(300, 5), 256, 144, walk=True))
+print(go(scenes.INLINE["nested"], 200, 120, walk=True))
 print(go(g.Scene.generate_text(300, 5), 256, 144, marks=True, opt=0))
 if "testCheese256" in scenes.corpus_names():
     print(go(scenes.text_of("corpus:testCheese256"), 320, 180))
