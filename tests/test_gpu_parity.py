@@ -286,6 +286,29 @@ def test_flat_and_walking_pruning_kernels_agree_on_the_tile_trees(csg):
     ctx.close()
 
 
+def test_flat_pruning_kernel_on_a_tree_above_its_default_limit(csg, monkeypatch):
+    """Above 2048 nodes the walk is the default (it is faster there); the prefix-sum kernel still has to be right (it fits
+    up to 32768 nodes): 3000 primitives = 5999 nodes, 16-bit prefix sums over 6000 entries, 47 nodes per thread."""
+    monkeypatch.setenv("CSG_B200_PRUNE_FLAT", "1")
+    txt = csg.Scene.generate_text(3000, seed=21)
+    w, h = 640, 360
+    sc = csg.Scene.parse(txt)
+    ctx = sc.upload(w, h)
+    for v in (View(w, h, pos=(0.0, 0.0, 5.0)), View(w, h, pos=(30.0, 10.0, -10.0), pitch=-0.2, yaw=1.2)):
+        cam, light = cam_of(csg, v), light_of(csg, v)
+        ctx.set_pruning(1)
+        a = _frames(csg, ctx, cam, light)
+        st = ctx.prune_stats()
+        ctx.set_pruning(2)
+        b = _frames(csg, ctx, cam, light)
+        ctx.set_pruning(0)
+        c = _frames(csg, ctx, cam, light)
+        for x, y, z in zip(a, b, c):
+            assert np.array_equal(x, z) and np.array_equal(y, z)
+        assert st["traced_tiles"] > 0
+    ctx.close()
+
+
 def test_root_primitive_is_not_pruned_by_its_gating_box(csg, oracle):
     """Q7: a scene that is one primitive is intersected without the (non-conservative, Q6) cylinder box; tiles that see only the
     part of a rotated cylinder that sticks out of that box must still draw it."""
