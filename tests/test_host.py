@@ -238,3 +238,34 @@ def test_optional_viewer_compiles_against_sdl2_headers():
     src = os.path.join(ROOT, "cuda-csg-tree-raycasting_b200", "host", "csg_viewer.cpp")
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + sdl, src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU implementation, or the oracle port when oracle/_ref is absent) runs
+    without a GPU and prints ONE JSON line with the keys the driver reads."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "primary rays/s" and d["unit"] == "rays/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "testCheese512" in d["config"]["workload"] and "3840x2160" in d["config"]["workload"]
+
+
+def test_bench_ours_refuses_to_run_without_a_gpu():
+    """No CPU fallback: our arm of bench.py fails loudly when there is no CUDA device."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pytest.skip("torch missing")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--no-baselines"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stdout + r.stderr)
