@@ -15,6 +15,7 @@ constexpr int kShapeThreads[kShapes] = {768, 384, 256};
 constexpr int min_blocks_for(int threads) { return threads >= 768 ? 1 : threads >= 384 ? 2 : 3; }
 constexpr int kWarpTileW = 8, kWarpTileH = 4;   // one warp = one 8x4 pixel tile (Raycaster.cuh:7-8 uses the same shape)
 constexpr int kMacroW = 64, kMacroH = 32;       // sharding unit: 8x8 warp tiles
+constexpr int kWarpTreeMax = 64;                // records of the largest per-warp shared-memory tree copy
 
 // Hit details + Phong (sphere/cylinder/cubeHitDetails :183-200/:338-372/:436-457 and LightningKernel :49-111).
 __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const float4* __restrict__ prims, const FrameParams& p, const float* __restrict__ s_light)
@@ -405,6 +406,23 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     // 4 / 16 such passes, handed out in tickets of 1 << gp passes each — so a heavy pixel does not serialise 16 traversals in
     // one warp, and the per-ticket set-up (descriptor, tree copy) is still shared by a few passes.
     const int sp = kSuper ? p.sp_shift : 0, gp = kSuper ? p.sp_group : 0;
+    // RaycastKernel :11-27 + Ray ctor (Ray.cuh:12-18): direction of the ray through virtual pixel (vx, vy)
+    auto make_ray = [&p](int vx, int vy, Ray& ray) {
+        const float u = __fdiv_rn(__fadd_rn((float)vx, 0.5f), p.wm1);
+        const float v = __fdiv_rn(__fadd_rn((float)vy, 0.5f), p.hm1);
+        const float nx = __fmul_rn(__fmul_rn(p.aspect, __fmaf_rn(u, 2.0f, -1.0f)), p.tan_half_fov);
+        const float ny = __fmul_rn(__fsub_rn(1.0f, __fadd_rn(v, v)), p.tan_half_fov);
+        float cx = __fadd_rn(p.forward[0], __fmaf_rn(p.right[0], nx, __fmul_rn(p.up[0], ny)));
+        float cy = __fadd_rn(p.forward[1], __fmaf_rn(p.right[1], nx, __fmul_rn(p.up[1], ny)));
+        float cz = __fadd_rn(p.forward[2], __fmaf_rn(p.right[2], nx, __fmul_rn(p.up[2], ny)));
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {   // normalize() then the Ray ctor normalises again (Q3)
+            const float inv = __frcp_rn(__fsqrt_rn(dot_ref(cx, cy, cz, cx, cy, cz)));
+            cx = __fmul_rn(inv, cx); cy = __fmul_rn(inv, cy); cz = __fmul_rn(inv, cz);
+        }
+        ray.dx = cx; ray.dy = cy; ray.dz = cz;
+        ray.ix = rcp_approx(cx); ray.iy = rcp_approx(cy); ray.iz = rcp_approx(cz);   // culling boxes only: they carry 1e-5 of slack
+    };
     while (ticket < (unsigned int)p.n_local_warp_tiles) {
 #ifdef CSG_FRAME_PROBE
         if (pr_tiles == 0) FPROBE(3, probe_now());
@@ -417,9 +435,15 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         int req_lane = kSuper ? 0 : -1;   // lane that has asked for the next ticket (-1: nobody yet)
         if (kSuper && lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
         const int k = (int)(cur & 63u);
-        // traced tiles are handed out heaviest first (order[] from csg_prune_kernel: tiles whose pruned tree is larger come
-        // first, so that the expensive tiles are not the ones still running when the ticket counter runs dry)
-        const int tile_no = p.order ? (int)__ldg(p.order + (cur >> 6)) : (int)(cur >> 6);
+        // traced tiles are handed out heaviest first (order[] from the pruning kernel: tiles whose pruned tree is larger come
+        // first, so that the expensive tiles are not the ones still running when the ticket counter runs dry); an entry carries
+        // the tile's descriptor, so the tile and its tree are known after one load
+        uint4 td = make_uint4(0u, (uint32_t)p.n_nodes, p.full_flags, 0u);
+        int tile_no = (int)(cur >> 6);
+        if (p.order) {
+            td = __ldg(p.order + (cur >> 6));
+            tile_no = (int)td.w;
+        }
         const int j = tile_no * p.shard_count + p.shard_rank;
         // j / rm_w by multiply-high with a host-computed reciprocal (exact for the ranges the host enables it for)
         const int jy = p.rm_magic ? (int)__umulhi((unsigned int)j, p.rm_magic) : j / p.rm_w;
@@ -436,18 +460,46 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
 
         // this macro tile's pruned tree (csg_prune_kernel): only the primitives its rays can reach, operators whose other
         // operand cannot be reached collapsed away.  n_nodes == 0: every ray of the tile is a Miss.
-        const int slot = p.shard_shift >= 0 ? (my * p.macro_x + mx) >> p.shard_shift : (my * p.macro_x + mx) / p.shard_count;
-        const uint4 td = p.desc ? __ldg(reinterpret_cast<const uint4*>(p.desc) + slot) : make_uint4(0u, (uint32_t)p.n_nodes, p.full_flags, 0u);
+        if (!p.order && p.desc) {   // natural order: the descriptor is looked up by position
+            const int slot = p.shard_shift >= 0 ? (my * p.macro_x + mx) >> p.shard_shift : (my * p.macro_x + mx) / p.shard_count;
+            td = __ldg(reinterpret_cast<const uint4*>(p.desc) + slot);
+        }
+        // whole warp tile outside the screen-space bound of the root box: every ray is a Miss (:109 background colour)
+        const bool tile_empty = td.y == 0u || tx0 > p.rect_x1 || tx0 + (kWarpTileW - 1) < p.rect_x0 || ty0 > p.rect_y1 || ty0 + (kWarpTileH - 1) < p.rect_y0;
         const unsigned char* tree = reinterpret_cast<const unsigned char*>(p.pool + 2 * (size_t)td.x);
-        if (td.y != 0u && td.y <= (uint32_t)p.warp_tree_nodes) {
+        const bool tree_fits = !tile_empty && td.y <= (uint32_t)p.warp_tree_nodes;
+        Ray r0;   // one ray per pixel: this lane's ray, generated while the tree is on its way
+        r0.ox = ox; r0.oy = oy; r0.oz = oz;
+        r0.dx = r0.dy = r0.dz = r0.ix = r0.iy = r0.iz = 0.0f;
+        if (!kSuper && !tile_empty) {
+            // the records are requested first (up to four 16-byte loads per lane), the ray is generated while they are in flight
+            // (~100 instructions, no memory), then they go to shared memory
+            static_assert(kWarpTreeMax == 64, "four loads per lane cover 64 records");
+            uint4 tr[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const uint32_t i = (uint32_t)lane + 32u * q4;
+                tr[q4] = (tree_fits && i < 2u * td.y) ? __ldg(p.pool + 2 * (size_t)td.x + i) : make_uint4(0u, 0u, 0u, 0u);
+            }
+            make_ray(tx0 + (lane & 7), ty0 + (lane >> 3), r0);
+            if (tree_fits) {
+                uint4* my_tree = reinterpret_cast<uint4*>(smem_raw + my_tree_off);
+                __syncwarp();   // everybody is done with the previous tile's copy
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint32_t i = (uint32_t)lane + 32u * q4;
+                    if (i < 2u * td.y) my_tree[i] = tr[q4];
+                }
+                __syncwarp();
+                tree = reinterpret_cast<const unsigned char*>(my_tree);
+            }
+        } else if (tree_fits) {
             uint4* my_tree = reinterpret_cast<uint4*>(smem_raw + my_tree_off);
             __syncwarp();   // everybody is done with the previous tile's copy
             for (uint32_t i = lane; i < 2u * td.y; i += 32u) my_tree[i] = __ldg(p.pool + 2 * (size_t)td.x + i);
             __syncwarp();
             tree = reinterpret_cast<const unsigned char*>(my_tree);
         }
-        // whole warp tile outside the screen-space bound of the root box: every ray is a Miss (:109 background colour)
-        const bool tile_empty = td.y == 0u || tx0 > p.rect_x1 || tx0 + (kWarpTileW - 1) < p.rect_x0 || ty0 > p.rect_y1 || ty0 + (kWarpTileH - 1) < p.rect_y0;
 
 #pragma unroll 1
         for (int pass = pass0; pass < pass0 + (1 << gp); ++pass) {
@@ -478,21 +530,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                 for (int s = 0, sx = sp ? ((lane & ((1 << sp) - 1)) & (ss - 1)) : 0, sy = sp ? ((lane & ((1 << sp) - 1)) >> (sp >> 1)) : 0; s < n_samples; ++s) {
                     const int vx = x * ss + sx, vy = y * ss + sy;
                     if (++sx == ss) { sx = 0; ++sy; }
-                    // RaycastKernel :11-27 + Ray ctor (Ray.cuh:12-18)
-                    const float u = __fdiv_rn(__fadd_rn((float)vx, 0.5f), p.wm1);
-                    const float v = __fdiv_rn(__fadd_rn((float)vy, 0.5f), p.hm1);
-                    const float nx = __fmul_rn(__fmul_rn(p.aspect, __fmaf_rn(u, 2.0f, -1.0f)), p.tan_half_fov);
-                    const float ny = __fmul_rn(__fsub_rn(1.0f, __fadd_rn(v, v)), p.tan_half_fov);
-                    float cx = __fadd_rn(p.forward[0], __fmaf_rn(p.right[0], nx, __fmul_rn(p.up[0], ny)));
-                    float cy = __fadd_rn(p.forward[1], __fmaf_rn(p.right[1], nx, __fmul_rn(p.up[1], ny)));
-                    float cz = __fadd_rn(p.forward[2], __fmaf_rn(p.right[2], nx, __fmul_rn(p.up[2], ny)));
-#pragma unroll
-                    for (int rep = 0; rep < 2; ++rep) {   // normalize() then the Ray ctor normalises again (Q3)
-                        const float inv = __frcp_rn(__fsqrt_rn(dot_ref(cx, cy, cz, cx, cy, cz)));
-                        cx = __fmul_rn(inv, cx); cy = __fmul_rn(inv, cy); cz = __fmul_rn(inv, cz);
-                    }
-                    r.dx = cx; r.dy = cy; r.dz = cz;
-                    r.ix = rcp_approx(cx); r.iy = rcp_approx(cy); r.iz = rcp_approx(cz);   // culling boxes only: they carry 1e-5 of slack
+                    if (kSuper) make_ray(vx, vy, r);
+                    else { r.dx = r0.dx; r.dy = r0.dy; r.dz = r0.dz; r.ix = r0.ix; r.iy = r0.iy; r.iz = r0.iz; }
                     res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u,
                                                     (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
                     if (!kSuper && lane == __ffs(amask) - 1)   // the tile is traced: ask for the next ticket now

@@ -338,11 +338,12 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
     const uint32_t cost = overflow ? (uint32_t)min(N, 2 * kCostBuckets - 1) : kept;
     const int bucket = (int)min(cost / 2u, (uint32_t)(kCostBuckets - 1));
     if (lane == 0) {
-        q.desc[slot] = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
-                                : TileDesc{kept ? q.slots_off32 + (uint32_t)slot * (uint32_t)S : 0u, kept, flags, 0u};
-        if (q.order) {
+        const TileDesc td = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
+                                     : TileDesc{kept ? q.slots_off32 + (uint32_t)slot * (uint32_t)S : 0u, kept, flags, 0u};
+        q.desc[slot] = td;
+        if (q.order) {   // the list entry carries the descriptor: the frame kernel gets the tile and its tree in one load
             const unsigned int rank = atomicAdd(&q.hist[bucket], 1u);
-            q.lists[(size_t)bucket * q.n_slots + rank] = (unsigned short)tile;
+            q.lists[(size_t)bucket * q.n_slots + rank] = make_uint4(td.offset32, td.n_nodes, td.flags, (uint32_t)tile);
             __threadfence();
         }
     }
@@ -420,6 +421,7 @@ struct FlatTileSmem {                  // followed by uint16_t A[n_pad], S[n_pad
     float plane[5][4];                 // the tile's frustum
     unsigned int start[kCostBuckets];  // ordering tail
     unsigned int last;
+    unsigned int list_pos;             // this tile's entry in the bucket lists
 };
 
 // Inclusive prefix sum of v[0, n) in place by the whole CTA; every thread owns `chunk` consecutive elements (odd: the
@@ -574,8 +576,7 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
     if (tid == 0 && q.order) {
         const uint32_t cost = overflow ? (uint32_t)min(N, 2 * kCostBuckets - 1) : kept;
         const int bucket = (int)min(cost / 2u, (uint32_t)(kCostBuckets - 1));
-        const unsigned int rank = atomicAdd(&q.hist[bucket], 1u);
-        q.lists[(size_t)bucket * q.n_slots + rank] = (unsigned short)tile;
+        w.list_pos = (unsigned int)bucket * (unsigned int)q.n_slots + atomicAdd(&q.hist[bucket], 1u);   // filled in below
     }
     uint4* dst = q.pool + 2 * ((size_t)q.slots_off32 + (size_t)slot * S);
     uint32_t flags = 0u;
@@ -667,10 +668,13 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
     PROBE(7);
     // ---- descriptor, and the count of finished tiles (release: this tile's list entry; acquire: everybody else's)
     if (tid == 0) {
-        q.desc[slot] = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
-                                : TileDesc{kept ? q.slots_off32 + (uint32_t)slot * (uint32_t)S : 0u, kept, flags, 0u};
+        const TileDesc td = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
+                                     : TileDesc{kept ? q.slots_off32 + (uint32_t)slot * (uint32_t)S : 0u, kept, flags, 0u};
+        q.desc[slot] = td;
         unsigned int last = 0u;
         if (q.order) {
+            // the list entry carries the descriptor: the frame kernel gets the tile and its tree in one load
+            q.lists[w.list_pos] = make_uint4(td.offset32, td.n_nodes, td.flags, (uint32_t)tile);
             unsigned int before;
             asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(before) : "l"(q.done) : "memory");
             last = before == (unsigned int)q.n_tiles - 1u ? 1u : 0u;
@@ -701,7 +705,7 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
     if (tid == 0) *q.done = 0u;
     // every output position looks up its bucket (largest k with start[k] <= i); batches of four loads in flight per thread
     for (int i0 = tid; i0 < q.n_tiles; i0 += 4 * T) {
-        const unsigned short* src[4];
+        const uint4* src[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const unsigned int i = (unsigned int)min(i0 + j * T, q.n_tiles - 1);
@@ -711,7 +715,7 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
                 if (k + step < kCostBuckets && w.start[k + step] <= i) k += step;
             src[j] = q.lists + (size_t)(63 - k) * q.n_slots + (i - w.start[k]);
         }
-        unsigned short v[4];
+        uint4 v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = __ldcg(src[j]);
 #pragma unroll

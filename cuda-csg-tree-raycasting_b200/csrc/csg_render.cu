@@ -75,8 +75,8 @@ struct Shard {  // one GPU's share of the frame
     uint2* d_topo = nullptr;             // per node: meta word, end of its subtree (csg_prune_flat_kernel)
     float4* d_leaf_boxes = nullptr;      // per primitive: culling box (world space) + node number, 2 x float4
     unsigned int* d_hist = nullptr;      // kCostBuckets counters + 1 "done" counter
-    unsigned short* d_lists = nullptr;   // kCostBuckets x n_slots
-    unsigned short* d_order = nullptr;   // n_slots
+    uint4* d_lists = nullptr;            // kCostBuckets x n_slots tile descriptors
+    uint4* d_order = nullptr;            // n_slots ordered tile descriptors
     int n_slots = 0;
     float4* d_prims = nullptr;
     unsigned int* d_counter = nullptr;
@@ -550,11 +550,11 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
             CU(cudaMalloc(&s.d_leaf_boxes, std::max<size_t>(c->tree.leaf_boxes.size(), 8) * sizeof(float)));
             CU(cudaMemcpy(s.d_leaf_boxes, c->tree.leaf_boxes.data(), c->tree.leaf_boxes.size() * sizeof(float), cudaMemcpyHostToDevice));
             const char* no_order = std::getenv("CSG_B200_NO_ORDER");   // tuning aid: tiles handed out in their natural order
-            if (c->prune && s.n_slots <= 65535 && !(no_order && no_order[0] == '1')) {   // tile numbers are stored as 16-bit
+            if (c->prune && s.n_slots <= 65535 && !(no_order && no_order[0] == '1')) {   // bounds the bucket lists (64 x n_slots x 16 bytes)
                 CU(cudaMalloc(&s.d_hist, (kCostBuckets + 1) * sizeof(unsigned int)));
                 CU(cudaMemset(s.d_hist, 0, (kCostBuckets + 1) * sizeof(unsigned int)));
-                CU(cudaMalloc(&s.d_lists, (size_t)kCostBuckets * std::max(s.n_slots, 1) * sizeof(unsigned short)));
-                CU(cudaMalloc(&s.d_order, (size_t)std::max(s.n_slots, 1) * sizeof(unsigned short)));
+                CU(cudaMalloc(&s.d_lists, (size_t)kCostBuckets * std::max(s.n_slots, 1) * sizeof(uint4)));
+                CU(cudaMalloc(&s.d_order, (size_t)std::max(s.n_slots, 1) * sizeof(uint4)));
             }
             if (c->prune_smem > 48 * 1024)
                 CU(cudaFuncSetAttribute(csg_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->prune_smem));
