@@ -269,3 +269,36 @@ def test_bench_ours_refuses_to_run_without_a_gpu():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stdout + r.stderr)
+
+
+def test_sass_has_no_local_memory_in_the_one_ray_per_pixel_kernels(csg):
+    """The traversal stack lives in shared memory and nothing spills: no LDL/STL in the SASS of the one-ray-per-pixel frame
+    kernels (all three CTA shapes, all output modes) nor in the pruning kernels; everything is built for sm_100a."""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-sass", csg.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"arch = sm_(?!100a)", out), "only sm_100a code is shipped"
+    fn, per_fn = None, {}
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            per_fn[fn] = [0, 0]
+            continue
+        if fn and re.search(r"\b(LDL|STL)\b", line):
+            per_fn[fn][0] += 1
+        if fn and re.match(r"\s*/\*[0-9a-f]{4}\*/", line):
+            per_fn[fn][1] += 1
+    frame = {f: v for f, v in per_fn.items() if "csg_frame_kernel" in f}
+    assert len(frame) == 18                                            # 3 output modes x 3 CTA shapes x {1 ray, supersampling}
+    one_ray = {f: v for f, v in frame.items() if "ELb0E" in f}
+    assert len(one_ray) == 9
+    for f, (local_ops, n) in one_ray.items():
+        assert local_ops == 0, f"{f}: {local_ops} local-memory instructions"
+        assert n > 1000
+    prune = {f: v for f, v in per_fn.items() if "csg_prune" in f}
+    assert len(prune) == 4                                             # the walk + the prefix-sum kernel at 128/256/512 threads
+    for f, (local_ops, n) in prune.items():
+        assert local_ops == 0, f"{f}: {local_ops} local-memory instructions"
