@@ -593,9 +593,10 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     char buf[512];
     std::snprintf(buf, sizeof buf,
                   "{\"threads_per_cta\": %d, \"ctas\": %d, \"sms\": %d, \"smem_bytes_per_cta\": %zu, \"tree_bytes\": %zu, "
-                  "\"prune\": %s, \"slot_nodes\": %d, \"stack_levels\": %d, \"n_nodes\": %zu, \"n_prims\": %zu, \"shards\": %d, "
+                  "\"prune\": %s, \"prune_kernel\": \"%s\", \"slot_nodes\": %d, \"stack_levels\": %d, \"n_nodes\": %zu, \"n_prims\": %zu, \"shards\": %d, "
                   "\"macro_tiles\": %d, \"optimize\": %d}",
-                  c->threads, c->shards[0].grid, sms, c->smem_bytes, tree_bytes, c->prune ? "true" : "false", c->slot_nodes,
+                  c->threads, c->shards[0].grid, sms, c->smem_bytes, tree_bytes, c->prune ? "true" : "false",
+                  !c->prune ? "none" : (c->prune_flat && c->flat_ok) ? "prefix sums (csg_prune_flat_kernel)" : "tree walk (csg_prune_kernel)", c->slot_nodes,
                   c->stack_levels, c->tree.nodes.size(), c->tree.prims.size(), shard_count, total_macros, scene->scene.optimize);
     c->info = buf;
     *out = c;
