@@ -45,6 +45,18 @@ def scene_bytes():
     return ("Difference\nCube 0 0 -20 FFFF00 20\n" + union(leaves)).encode(), "synthetic cheese (512 seeded spheres), reference corpus absent"
 
 
+def cpu_model():
+    """Model name of the host CPU the baseline ran on (printed next to the CPU baseline)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -279,7 +291,7 @@ def bench_ours(args):
             step = 4
             sec = rc.render(text, v, row_step=step, outputs=False)
             rows = (HEIGHT + step - 1) // step
-            cpu_baseline = {"value": rows * WIDTH / sec, "unit": "rays/s", "cores": rc.max_threads(), "kind": "reference",
+            cpu_baseline = {"value": rows * WIDTH / sec, "unit": "rays/s", "cores": rc.max_threads(), "cpu_model": cpu_model(), "kind": "reference",
                             "sample": f"every {step}th scanline of the same frame ({rows} rows, {rows * WIDTH} rays, {sec:.2f} s); "
                                       "reference RaycastKernel+LightningKernel source compiled for the host, OpenMP dynamic over rows"}
         else:
@@ -287,7 +299,7 @@ def bench_ours(args):
             t0 = time.perf_counter()
             fr = orc.render(text, v, rows=(HEIGHT // 2 - 64, HEIGHT // 2 + 64))
             sec = time.perf_counter() - t0
-            cpu_baseline = {"value": 128 * WIDTH / sec, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+            cpu_baseline = {"value": 128 * WIDTH / sec, "unit": "rays/s", "cores": os.cpu_count(), "cpu_model": cpu_model(), "kind": "port",
                             "sample": "128 centre scanlines, C oracle with OpenMP"}
         if oracle_py.have_ref_gpu():
             rg = oracle_py.RefGPU()
@@ -363,7 +375,7 @@ def bench_reference(args):
            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3 * (HEIGHT / rows) if kind == "reference" else None,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_note,
            "config": {"workload": WORKLOAD},
-           "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
+           "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "cpu_model": cpu_model(), "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0,
            "note": "ms_per_step is the sample time scaled to a full frame"}
