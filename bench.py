@@ -270,10 +270,21 @@ def bench_ours(args):
     except Exception:
         pass
     achieved = value * fpr / 1e12 if fpr else None
+    # the HBM view of the same frame, to show why it is not the bound: algorithmic bytes = the RGBA8 framebuffer (4 B/ray)
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    hbm_achieved = nrays * 4 / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_measured, "unit": "TFLOP/s",
                 "frac": (achieved / peak_measured) if achieved else None, "traffic": traffic,
                 "peak_source": "FFMA-only probe kernel measured in this run (csg_fp32_peak_tflops)",
                 "peak_nominal": peak_nominal, "flop_per_ray": fpr, "executed": executed,
+                "hbm": {"algorithmic_bytes_per_frame": nrays * 4, "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": hbm_achieved / hbm_peak, "peak_source": hbm_src,
+                        "note": "4 B/ray of RGBA8 out is all the path has to move: a few per cent of HBM bandwidth, hence the FP32/issue roofline"},
                 "note": "achieved = rays/s x the REFERENCE algorithm's algorithmic flop/ray (fixed yard-stick, SURVEY.md 8d).  Our kernels skip "
                         "almost all of that work (per-tile pruned trees, nearest-hit search, tighter boxes), so frac exceeds 1: it measures the "
                         "frame against doing the reference's arithmetic at FP32 peak.  'executed' is what the frame kernel really issued: it is "
