@@ -341,3 +341,118 @@ def test_explicit_frame_traversal_equals_the_reference_machine(scene_id, optimiz
     assert checked > 500
     # (duplicate_spheres: two coincident spheres tie everywhere and the reference returns Miss for every pixel, Q5)
     assert hits > 0 or scene_id in ("inline:duplicate_spheres",)
+
+
+# ---- the same, on per-tile trees: prefix-sum pruning (test_flat_tree.prune_by_prefix_sums) + the refit of boxes and flags that
+#      csg_prune_flat_kernel does, then the traversal model on the tile's own tree — against the oracle on the whole scene
+def pruned_tile_tree(rec, view, cam, tan_half, x0, y0, x1, y1):
+    """Records of the tree of pixel tile [x0, x1) x [y0, y1) (world space; boxes, leaf / pure / bounded flags refitted), or None
+    when no primitive is reachable from it."""
+    import test_flat_tree as ft
+    meta = rec[:, 7].astype(np.int64)
+    kind = meta & 7
+    end = ft.subtree_ends(kind, meta)
+    pos = np.array([cam.x, cam.y, cam.z], np.float64)
+    planes = ft.tile_planes(view, cam, tan_half, x0, y0, x1, y1)
+    alive = np.zeros(len(kind), bool)
+    for n in np.nonzero(kind >= 3)[0]:
+        lo, hi = ft.cull_box(rec[n])
+        lo, hi = lo - pos, hi - pos
+        alive[n] = not any((np.maximum(p * lo, p * hi)).sum() < 0 for p in planes)
+    recs, _ = ft.prune_by_prefix_sums(kind, meta, end, alive)
+    if not recs:
+        return None
+    out = np.zeros((len(recs), 8), np.uint32)
+    f = out.view(np.float32)
+    for i, (n, ri) in enumerate(recs):
+        out[i] = rec[n]
+        if ri >= 0:
+            out[i, 7] = int(kind[n]) | (ri << 8)
+    k2 = out[:, 7].astype(np.int64) & 7
+    flg = np.zeros(len(recs), np.int64)                       # bit0 pure, bit1 bounded
+
+    def box_of(j):
+        if k2[j] >= 3:
+            lo, hi = ft.cull_box(out[j])
+            return np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+        return f[j, 0:3].copy(), f[j, 3:6].copy()
+    for i in range(len(recs) - 1, -1, -1):                    # reverse preorder: operands before their operator
+        if k2[i] >= 3:
+            flg[i] = (1 if k2[i] in (K_SPHERE, K_CUBE) else 0) | (2 if k2[i] != K_CYL else 0)
+            continue
+        a, b = i + 1, int(out[i, 7]) >> 8
+        (alo, ahi), (blo, bhi) = box_of(a), box_of(b)
+        if k2[i] == K_UNION:
+            lo, hi = np.minimum(alo, blo), np.maximum(ahi, bhi)
+        elif k2[i] == K_DIFF:
+            lo, hi = alo, ahi
+        else:
+            va, vb = np.prod(np.maximum(ahi - alo, 0)), np.prod(np.maximum(bhi - blo, 0))
+            lo, hi = (alo, ahi) if va <= vb else (blo, bhi)
+        f[i, 0:3], f[i, 3:6] = lo, hi
+        flg[i] = ((flg[a] & flg[b] & 1) if k2[i] == K_UNION else 0) | (flg[a] & flg[b] & 2)
+        out[i, 7] = (int(k2[i]) | (b << 8) | (LEFT_LEAF if k2[a] >= 3 else 0) | (RIGHT_LEAF if k2[b] >= 3 else 0) |
+                     (BOUNDED if flg[i] & 2 else 0) | (PURE if flg[i] & 1 else 0))
+    return out
+
+
+class TileModel(Model):
+    """A tile's tree.  A tree that collapsed to one primitive is still reached through its operators in the reference, so a
+    cylinder keeps its gating box (root_gated in the kernel) — unless the scene itself is that one primitive (Q7)."""
+
+    def __init__(self, *a, scene_is_one_primitive=False):
+        super().__init__(*a)
+        self.root_gated = not scene_is_one_primitive
+
+    def traverse(self, direction):
+        if (int(self.meta[0]) & 7) >= 3:
+            return self.leaf(0, (C.c_float * 3)(*direction), 0.0, self.root_gated)
+        return super().traverse(direction)
+
+
+@pytest.mark.parametrize("optimize", [0, 1])
+@pytest.mark.parametrize("scene_id", ["inline:nested", "inline:rotated_cylinder_union", "inline:deep_left_chain", "corpus:testWikipediaMult",
+                                      "corpus:testCylinderSpheres2", "corpus:testCheese256", "synthetic:200"])
+def test_traversal_of_the_per_tile_trees_equals_the_reference_machine(scene_id, optimize, csg, oracle):
+    if scene_id.startswith("corpus:") and scene_id[7:] not in scenes.corpus_names():
+        pytest.skip("scene corpus not staged")
+    txt = csg.Scene.generate_text(200, seed=13) if scene_id.startswith("synthetic:") else scenes.text_of(scene_id)
+    sc = csg.Scene.parse(txt, optimize=optimize)
+    rec, _, _ = sc.flatten()
+    _, prims48 = sc.dump()
+    sc.close()
+    rec = rec.reshape(-1, 8)
+    prims48 = np.asarray(prims48).reshape(-1, 48)
+    w, h, tw, th = 192, 96, 32, 16
+    if "Cheese" in scene_id:
+        views = [View(w, h)]
+    elif scene_id.startswith("synthetic:"):
+        views = [View(w, h, pos=(0.0, 0.0, 5.0)), View(w, h, pos=(30.0, 10.0, -10.0), pitch=-0.2, yaw=1.2)]
+    else:
+        views = [View(w, h), orbit_view(w, h, 5, radius=4.0)]
+    checked = pruned_tiles = 0
+    for v in views:
+        ref = oracle.render(txt, v, want_rgba=False)
+        rh, rp, rt = ref.hit.reshape(h, w), ref.prim.reshape(h, w), ref.t.reshape(h, w)
+        cam = oracle.camera(v)
+        tan_half = float(np.tan(np.float32(cam.fov) * np.float32(0.5)))
+        out3 = (C.c_float * 3)()
+        for ty in range(0, h, th):
+            for tx in range(0, w, tw):
+                tree = pruned_tile_tree(rec, v, cam, tan_half, tx, ty, tx + tw, ty + th)
+                if tree is None:
+                    assert not rh[ty:ty + th, tx:tx + tw].any()
+                    pruned_tiles += 1
+                    continue
+                pruned_tiles += len(tree) < len(rec)
+                model = TileModel(oracle, tree, prims48, v.pos, scene_is_one_primitive=len(rec) == 1)
+                for y in range(ty, ty + th, 3):
+                    for x in range(tx + (y % 2), tx + tw, 3):
+                        oracle.lib.orc_raygen(C.byref(cam), w, h, x, y, C.c_float(tan_half), out3)
+                        got = model.traverse((float(out3[0]), float(out3[1]), float(out3[2])))
+                        assert (not got.miss) == bool(rh[y, x]), f"{scene_id} opt={optimize} pixel ({x},{y})"
+                        if rh[y, x]:
+                            assert got.prim == int(rp[y, x]) and np.float32(got.t).view(np.uint32) == rt[y, x].view(np.uint32)
+                        checked += 1
+    assert checked > 300
+    assert pruned_tiles > 0 or "CylinderSpheres2" in scene_id   # that scene fills the frame: nothing to prune

@@ -34,56 +34,11 @@ boxes = {int(n): ft.cull_box(rec[n]) for n in leaf_nodes}
 
 
 def pruned_tree(mx, my):
-    """Records of the tile's tree (world space, boxes refitted), or None when nothing is reachable."""
-    planes = ft.tile_planes(view, cam, tan_half, mx * 64, my * 32, min(mx * 64 + 64, W), min(my * 32 + 32, H))
-    alive = np.zeros(len(kind), bool)
-    for n in leaf_nodes:
-        lo, hi = boxes[int(n)][0] - pos, boxes[int(n)][1] - pos
-        alive[n] = not any((np.maximum(p * lo, p * hi)).sum() < 0 for p in planes)
-    recs, _ = ft.prune_by_prefix_sums(kind, meta, end, alive)
-    if not recs:
-        return None
-    out = np.zeros((len(recs), 8), np.uint32)
-    f = out.view(np.float32)
-    for i, (n, ri) in enumerate(recs):
-        out[i] = rec[n]
-        if ri >= 0:
-            out[i, 7] = int(kind[n]) | (ri << 8)
-    # refit bottom-up (reverse preorder): boxes and flags as csg_prune_flat_kernel does
-    k2 = out[:, 7].astype(np.int64) & 7
-    flg = np.zeros(len(recs), np.int64)
-    for i in range(len(recs) - 1, -1, -1):
-        if k2[i] >= 3:
-            lo, hi = ft.cull_box(out[i])
-            if k2[i] != tm.K_SPHERE:
-                pass
-            flg[i] = (1 if k2[i] in (tm.K_SPHERE, tm.K_CUBE) else 0) | (2 if k2[i] != tm.K_CYL else 0)
-            continue
-        a, b = i + 1, int(out[i, 7]) >> 8
-
-        def cb(j):
-            if k2[j] >= 3:
-                lo, hi = ft.cull_box(out[j])
-                return np.asarray(lo, np.float32), np.asarray(hi, np.float32)
-            return f[j, 0:3].copy(), f[j, 3:6].copy()
-        (alo, ahi), (blo, bhi) = cb(a), cb(b)
-        if k2[i] == tm.K_UNION:
-            lo, hi = np.minimum(alo, blo), np.maximum(ahi, bhi)
-        elif k2[i] == tm.K_DIFF:
-            lo, hi = alo, ahi
-        else:
-            va, vb = np.prod(np.maximum(ahi - alo, 0)), np.prod(np.maximum(bhi - blo, 0))
-            lo, hi = (alo, ahi) if va <= vb else (blo, bhi)
-        f[i, 0:3], f[i, 3:6] = lo, hi
-        flg[i] = ((flg[a] & flg[b] & 1) if k2[i] == tm.K_UNION else 0) | (flg[a] & flg[b] & 2)
-        m = int(k2[i]) | ((int(out[i, 7]) >> 8) << 8)
-        m |= (tm.LEFT_LEAF if k2[a] >= 3 else 0) | (tm.RIGHT_LEAF if k2[b] >= 3 else 0)
-        m |= (tm.BOUNDED if flg[i] & 2 else 0) | (tm.PURE if flg[i] & 1 else 0)
-        out[i, 7] = m
-    return out
+    """Records of the tile's tree (world space, boxes and flags refitted), or None when nothing is reachable."""
+    return tm.pruned_tile_tree(rec, view, cam, tan_half, mx * 64, my * 32, min(mx * 64 + 64, W), min(my * 32 + 32, H))
 
 
-class Counting(tm.Model):
+class Counting(tm.TileModel):
     def __init__(self, *a):
         super().__init__(*a)
         self.n = collections.Counter()
