@@ -130,6 +130,12 @@ class Raycaster {
         csg_light l{light.polar, light.azimuth};
         if (csg_render_batch(ctx_, cs.data(), n, &l, rgba8) != CSG_OK) throw std::runtime_error(csg_last_error());
     }
+    // Not in the reference (its kernel has one ray per pixel, no culling options): samples per axis (1, 2 or 4 rays per pixel
+    // side: csg_set_supersampling), the per-tile tree pruning mode (0 off, 1 default, 2 tree walk: csg_set_pruning) and the view
+    // cache for a static camera with a moving light (csg_set_view_cache).  Call after ChangeSize.
+    void SetSupersampling(int samplesPerAxis) { if (csg_set_supersampling(ctx_, samplesPerAxis) != CSG_OK) throw std::runtime_error(csg_last_error()); }
+    void SetPruning(int mode) { if (csg_set_pruning(ctx_, mode) != CSG_OK) throw std::runtime_error(csg_last_error()); }
+    void SetViewCache(bool on) { if (csg_set_view_cache(ctx_, on ? 1 : 0) != CSG_OK) throw std::runtime_error(csg_last_error()); }
     csg_context* context() { return ctx_; }
 
   private:

@@ -2,7 +2,7 @@
 // for the raycast path: load a scene file, render one frame (or a camera orbit), write a binary PPM, print timings.
 //
 //   csg_render scene.txt [--w 3840] [--h 2160] [--cam x y z pitch yaw] [--fov deg] [--light polar azimuth]
-//              [--frames N] [--gpus N] [--no-optimize] [--out frame.ppm]
+//              [--frames N] [--gpus N] [--no-optimize] [--ss K] [--pruning 0|1|2] [--out frame.ppm]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -19,10 +19,10 @@ int main(int argc, char** argv)
 {
     if (argc < 2) {
         std::fprintf(stderr, "usage: %s scene.txt [--w W] [--h H] [--cam x y z pitch yaw] [--fov deg] [--light polar azimuth] "
-                             "[--frames N] [--gpus N] [--no-optimize] [--out frame.ppm]\n", argv[0]);
+                             "[--frames N] [--gpus N] [--no-optimize] [--ss K] [--pruning 0|1|2] [--out frame.ppm]\n", argv[0]);
         return 2;
     }
-    int w = 800, h = 600, frames = 1, gpus = 1, optimize = 1;   // 800x600 is the reference's window size (Application.h:16-17)
+    int w = 800, h = 600, frames = 1, gpus = 1, optimize = 1, samples = 1, pruning = 1;   // 800x600 is the reference's window size (Application.h:16-17)
     const char* out = nullptr;
     Camera cam;
     DirectionalLight light;
@@ -32,6 +32,8 @@ int main(int argc, char** argv)
         else if (!std::strcmp(argv[i], "--h")) { need(1); h = std::atoi(argv[++i]); }
         else if (!std::strcmp(argv[i], "--frames")) { need(1); frames = std::atoi(argv[++i]); }
         else if (!std::strcmp(argv[i], "--gpus")) { need(1); gpus = std::atoi(argv[++i]); }
+        else if (!std::strcmp(argv[i], "--ss")) { need(1); samples = std::atoi(argv[++i]); }
+        else if (!std::strcmp(argv[i], "--pruning")) { need(1); pruning = std::atoi(argv[++i]); }
         else if (!std::strcmp(argv[i], "--fov")) { need(1); cam.setFOV((float)std::atof(argv[++i])); }
         else if (!std::strcmp(argv[i], "--out")) { need(1); out = argv[++i]; }
         else if (!std::strcmp(argv[i], "--no-optimize")) optimize = 0;
@@ -52,6 +54,8 @@ int main(int argc, char** argv)
         csg_scene_set_optimize(tree.handle(), optimize);
         Raycaster rc;
         rc.ChangeSize(w, h, tree, gpus);
+        if (samples != 1) rc.SetSupersampling(samples);
+        if (pruning != 1) rc.SetPruning(pruning);
         std::vector<uint8_t> img((size_t)w * h * 4);
         for (int k = 0; k < frames; ++k) {
             auto t0 = std::chrono::steady_clock::now();
