@@ -26,7 +26,7 @@ EXPORTS = [
     "csg_render", "csg_render_batch", "csg_render_f32", "csg_render_aov", "csg_render_stats", "csg_set_supersampling", "csg_set_pruning", "csg_set_view_cache", "csg_prune_stats", "csg_render_enqueue", "csg_sync", "csg_last_frame_ms",
     "csg_launch_count", "csg_framebuffer", "csg_framebuffer_ipc_handle", "csg_set_gather_target_ipc",
     "csg_set_gather_target", "csg_read_framebuffer", "csg_device_tan_half_fov", "csg_fp32_peak_tflops", "csg_context_info",
-    "csg_last_error", "csg_version", "csg_cube_normal_threshold",
+    "csg_last_error", "csg_version", "csg_cube_normal_threshold", "csg_shard_tile",
 ]
 
 
@@ -95,6 +95,7 @@ def _load():
         "csg_last_error": (C.c_char_p, []),
         "csg_version": (C.c_char_p, []),
         "csg_cube_normal_threshold": (f, [f, f]),
+        "csg_shard_tile": (i, [i] * 10 + [C.POINTER(i)] * 5),
     }
     for name in EXPORTS:
         fn = getattr(lib, name)  # AttributeError here = the library does not export what the header declares
@@ -125,6 +126,17 @@ def version():
 
 def cube_normal_threshold(half_size, level):
     return float(lib.csg_cube_normal_threshold(float(half_size), float(level)))
+
+
+def shard_tile(macro_x, macro_y, rect, mode, rank, count, tile):
+    """(mx, my, slot, n_tiles, n_slots) of tile number `tile` of shard `rank`; tile < 0: only the two counts."""
+    mx, my, slot, nt, ns = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rc = lib.csg_shard_tile(macro_x, macro_y, rect[0], rect[1], rect[2], rect[3], mode, rank, count, tile,
+                            C.byref(mx), C.byref(my), C.byref(slot), C.byref(nt), C.byref(ns))
+    if tile < 0:
+        return None, None, None, nt.value, ns.value
+    _check(rc)
+    return mx.value, my.value, slot.value, nt.value, ns.value
 
 
 def fp32_peak_tflops(device=0):

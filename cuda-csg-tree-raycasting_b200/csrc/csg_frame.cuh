@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         s_light[0] = p.light[0] * il; s_light[1] = p.light[1] * il; s_light[2] = p.light[2] * il;
     }
     __syncthreads();
+    gate_enter(p.gate);   // sharded frames: nothing of this frame happens before the root GPU has started it
     const uint32_t my_stack = (uint32_t)__cvta_generic_to_shared(s_stack + tid);   // frames are addressed in the shared window: 32-bit
     // per-warp copy of the current tile's tree (when it fits): traversal then reads shared memory instead of L1/L2
     const uint32_t my_tree_off = 128u + 16u * (uint32_t)((p.stack_levels + 2) * kThreads + (tid >> 5) * (2 * p.warp_tree_nodes));   // bytes from smem_raw
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             const int my = p.div_magic ? (int)__umulhi((unsigned int)m, p.div_magic) : m / p.macro_x;
             const int mx = m - my * p.macro_x;
             if (my < p.band_m0 || my >= p.band_m1) continue;                                                   // another band of this frame
+            if (p.shard_mode && my % p.shard_count != p.shard_rank) continue;                                  // another shard's row
             if (mx >= p.rm_x0 && mx < p.rm_x0 + p.rm_w && my >= p.rm_y0 && my < p.rm_y0 + p.rm_h) continue;   // traced in phase 2
             const int x0 = mx * kMacroW, y0 = my * kMacroH;
             if (MODE == OUT_RGBA8 && (p.width & 3) == 0) {
@@ -444,10 +446,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             td = __ldg(p.order + (cur >> 6));
             tile_no = (int)td.w;
         }
-        const int j = tile_no * p.shard_count + p.shard_rank;
-        // j / rm_w by multiply-high with a host-computed reciprocal (exact for the ranges the host enables it for)
-        const int jy = p.rm_magic ? (int)__umulhi((unsigned int)j, p.rm_magic) : j / p.rm_w;
-        const int mx = p.rm_x0 + (j - jy * p.rm_w), my = p.rm_y0 + jy;
+        int mx, my;
+        shard_tile_coords(tile_no, p.shard_mode, p.shard_rank, p.shard_count, p.rm_x0, p.rm_y0, p.rm_w, p.rm_magic, p.row_first, mx, my);
         const int kx = (k & 1) | ((k >> 1) & 2) | ((k >> 2) & 4);        // Morton order inside the macro tile
         const int ky = ((k >> 1) & 1) | ((k >> 2) & 2) | ((k >> 3) & 4);
         const int tx0 = mx * kMacroW + kx * kWarpTileW, ty0 = my * kMacroH + ky * kWarpTileH;   // the warp tile's corner
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         // this macro tile's pruned tree (csg_prune_kernel): only the primitives its rays can reach, operators whose other
         // operand cannot be reached collapsed away.  n_nodes == 0: every ray of the tile is a Miss.
         if (!p.order && p.desc) {   // natural order: the descriptor is looked up by position
-            const int slot = p.shard_shift >= 0 ? (my * p.macro_x + mx) >> p.shard_shift : (my * p.macro_x + mx) / p.shard_count;
+            const int slot = slot_of_macro(p.shard_mode, mx, my, p.macro_x, p.shard_count);
             td = __ldg(reinterpret_cast<const uint4*>(p.desc) + slot);
         }
         // whole warp tile outside the screen-space bound of the root box: every ray is a Miss (:109 background colour)
@@ -601,6 +601,22 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
 #ifdef CSG_FRAME_PROBE
     FPROBE(4, probe_now()); FPROBE(5, pr_longest); FPROBE(6, pr_tiles); FPROBE(7, pr_longest_ticket);
 #endif
+    // ---- join of a sharded frame (GateParams): a peer's last CTA tells the root that all of this shard's pixels have landed in
+    // the root's framebuffer; the root's last CTA waits for every peer before the kernel (and with it the frame) ends
+    if (p.gate.role != GATE_NONE) {
+        __threadfence_system();   // this thread's pixel stores (over NVLink on a peer) are performed
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int before = atomicAdd(p.gate.exit_counter, 1u);
+            if (before == gridDim.x - 1u) {
+                *p.gate.exit_counter = 0u;   // ready for the next frame
+                __threadfence_system();
+                if (p.gate.role == GATE_PEER) st_release_sys(&p.gate.words->done[p.gate.rank], p.gate.seq);
+                else
+                    for (int r = 1; r < p.gate.n_shards; ++r) wait_seq(&p.gate.words->done[r], p.gate.seq, p.gate.err);
+            }
+        }
+    }
 }
 
 // tan(cam.fov / 2.0f) of RaycastKernel :15-16, evaluated with the device tanf once per field of view (kept out of

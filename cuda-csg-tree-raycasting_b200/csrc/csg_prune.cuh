@@ -51,10 +51,7 @@ __device__ __forceinline__ void rel_cull_box(const uint4 ua, const uint4 ub, flo
 // Traced macro tile number `tile` of this shard -> macro tile coordinates.
 __device__ __forceinline__ void tile_of(const PruneParams& q, int tile, int& mx, int& my)
 {
-    const int j = tile * q.shard_count + q.shard_rank;
-    const int jy = q.rm_magic ? (int)__umulhi((unsigned int)j, q.rm_magic) : j / q.rm_w;
-    mx = q.rm_x0 + (j - jy * q.rm_w);
-    my = q.rm_y0 + jy;
+    shard_tile_coords(tile, q.shard_mode, q.shard_rank, q.shard_count, q.rm_x0, q.rm_y0, q.rm_w, q.rm_magic, q.row_first, mx, my);
 }
 
 // Frustum of a macro tile: its pixels plus a margin of one pixel.  Inward plane normals: 4 sides through the camera position
@@ -128,6 +125,7 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
     const int N = q.n_nodes, S = q.slot_nodes;
     const int tile_ctas = (q.n_tiles + kPruneWarps - 1) / kPruneWarps;
     cudaTriggerProgrammaticLaunchCompletion();   // the frame kernel may be scheduled now; it waits for this grid before it reads our output
+    gate_enter(q.gate);
 
     if ((int)blockIdx.x >= tile_ctas) {
         // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
@@ -154,7 +152,7 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
     // ---- the tile and its frustum
     int mx, my;
     tile_of(q, tile, mx, my);
-    const int slot = (my * q.macro_x + mx) / q.shard_count;
+    const int slot = slot_of_macro(q.shard_mode, mx, my, q.macro_x, q.shard_count);
     float pn[5][3];   // inward plane normals: 4 sides through the origin + the camera plane
     tile_frustum(q, mx, my, pn);
 
@@ -456,6 +454,7 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
     const float ox = q.cam_pos[0], oy = q.cam_pos[1], oz = q.cam_pos[2];
     const int N = q.n_nodes, S = q.slot_nodes;
     cudaTriggerProgrammaticLaunchCompletion();   // the frame kernel may be scheduled now; it waits for this grid before it reads our output
+    gate_enter(q.gate);
 
     if ((int)blockIdx.x >= q.n_tiles) {
         // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
@@ -477,7 +476,7 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
 
     int mx, my;
     tile_of(q, tile, mx, my);
-    const int slot = (my * q.macro_x + mx) / q.shard_count;
+    const int slot = slot_of_macro(q.shard_mode, mx, my, q.macro_x, q.shard_count);
     const int chunk = ((N + T - 1) / T) | 1;
     // the frustum is worked out by the first warp only (divisions, cross products: ~150 dependent instructions), while the
     // other warps clear the flags; everybody then keeps the five planes in registers, with the absolute values of the

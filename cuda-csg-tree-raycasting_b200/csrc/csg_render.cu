@@ -61,6 +61,32 @@ int fail(int code, const std::string& msg)
         if (e_ != cudaSuccess) return fail(CSG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+// inside create_context: a failing CUDA call frees what the half-built context already owns
+#define CUC(call)                                                                    \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            const std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); \
+            csg_free_context(c);                                                     \
+            return fail(CSG_ERR_CUDA, m_);                                           \
+        }                                                                            \
+    } while (0)
+
+// Hit words keep the primitive id in 22 bits and node records their right operand in 24 (csg_kernel.cuh, csg_scene.h); the host
+// builders recurse once per tree level.  Anything beyond is refused, not aliased / overflowed.
+constexpr size_t kMaxPrims = (size_t)1 << 22, kMaxNodes = (size_t)1 << 24;
+constexpr int kMaxParsedDepth = 16384;
+int scene_within_limits(const Scene& sc)
+{
+    if (sc.prims.size() >= kMaxPrims || sc.nodes.size() >= kMaxNodes)
+        return fail(CSG_ERR_LIMIT, "scene too large: " + std::to_string(sc.prims.size()) + " primitives / " + std::to_string(sc.nodes.size()) +
+                                       " nodes (limits: 2^22 primitives, 2^24 nodes)");
+    const int d = sc.depth();   // iterative
+    if (d > kMaxParsedDepth)
+        return fail(CSG_ERR_LIMIT, "tree depth " + std::to_string(d) + " exceeds " + std::to_string(kMaxParsedDepth) + " operator levels");
+    return CSG_OK;
+}
+
 struct Shard {  // one GPU's share of the frame
     int device = 0;
     int rank = 0;
@@ -86,6 +112,14 @@ struct Shard {  // one GPU's share of the frame
     int n_local_warp_tiles = 0;
     uint8_t* target = nullptr;   // where this shard writes RGBA8 (root framebuffer, possibly a peer pointer)
     void* ipc_mapped = nullptr;
+    uint8_t* local_fb = nullptr;         // this shard's own full-size framebuffer (row-sharded frames for host output); shard 0: the context's
+    bool owns_local_fb = false;
+    cudaStream_t copy_stream = nullptr;  // device -> host copies of this shard's bands
+    cudaEvent_t ev_band[8] = {};
+    SyncWords* sync_words = nullptr;     // the ROOT's sync words as seen from this shard's device (nullptr: no gate / join)
+    unsigned int* d_exit = nullptr;      // finished CTAs of the frame kernel (join)
+    int* h_err = nullptr;                // mapped host word raised by a device-side wait that timed out
+    int* d_err = nullptr;
 };
 
 }  // namespace
@@ -109,8 +143,10 @@ struct csg_context {
     cudaEvent_t ev_batch0 = nullptr, ev_batch1 = nullptr;
     int warp_tree_nodes = 0;     // per-warp shared-memory copy of the current tile's tree: capacity in records
     int band_m0 = 0, band_m1 = 0;   // macro-tile rows the next enqueue covers (0, 0 = the whole frame)
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_band[8] = {};
+    unsigned int frame_seq = 0;  // sequence number of the last sharded frame (gate / join words)
+    size_t sync_off = 0;         // byte offset of the SyncWords behind the framebuffer (same allocation: one IPC handle covers both)
+    int last_mode = 0;           // shard mode of the last frame (csg_prune_stats)
+    bool shard_sync = true;      // sharded frames are started and joined on the device (SyncWords); csg_set_gather_target(pointer) turns it off
     bool view_cache = false;     // csg_set_view_cache
     bool external_target = false;   // csg_set_gather_target: pixels go to a buffer that is not rank 0's own framebuffer
     bool prune_alloc = false;    // tile slots were allocated at upload
@@ -227,7 +263,7 @@ void screen_bound(const csg_context* c, const csg_camera* cam, FrameParams& fp)
     fp.rect_x1 = (int)std::ceil(xmax / c->ss);  fp.rect_y1 = (int)std::ceil(ymax / c->ss);
 }
 
-void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, const float light[3], FrameParams& fp)
+void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, const float light[3], int shard_mode, FrameParams& fp)
 {
     std::memset(&fp, 0, sizeof fp);
     for (int i = 0; i < 3; ++i) {
@@ -248,12 +284,17 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
                        ? (unsigned int)((1ull << 32) / (unsigned long long)c->macro_x + 1ull) : 0u;
     fp.shard_rank = s.rank;
     fp.shard_count = c->shard_count;
-    // background tiles: the shard that owns the framebuffer fills all of them; with an external target everybody fills its own
-    const bool owns_fb = s.rank == 0 && !c->external_target;
-    fp.fill_stride = owns_fb ? 1 : c->shard_count;
-    fp.fill_first = owns_fb ? 0 : (c->external_target ? s.rank : (1 << 30));
-    fp.shard_shift = -1;
-    for (int b = 0; b < 16; ++b) if ((1 << b) == c->shard_count) fp.shard_shift = b;
+    fp.shard_mode = shard_mode;
+    if (shard_mode) {
+        // rows: every shard fills the background tiles of its own macro-tile rows (the kernel skips the other rows)
+        fp.fill_stride = 1;
+        fp.fill_first = 0;
+    } else {
+        // background tiles: the shard that owns the framebuffer fills all of them; with an external target everybody fills its own
+        const bool owns_fb = s.rank == 0 && !c->external_target;
+        fp.fill_stride = owns_fb ? 1 : c->shard_count;
+        fp.fill_first = owns_fb ? 0 : (c->external_target ? s.rank : (1 << 30));
+    }
     fp.counter_base = s.counter_base;
     fp.tile_counter = s.d_counter;
     fp.pool = s.d_pool;
@@ -286,7 +327,9 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
         fp.rm_w = ax1 / kMacroW - fp.rm_x0 + 1; fp.rm_h = ay1 / kMacroH - fp.rm_y0 + 1;
     }
     const long long traced = (long long)fp.rm_w * fp.rm_h;
-    const long long mine = traced > s.rank ? (traced - s.rank + c->shard_count - 1) / c->shard_count : 0;
+    fp.row_first = shard_row_first(fp.rm_y0, s.rank, c->shard_count);
+    const long long mine = shard_mode ? (long long)shard_row_count(fp.rm_y0, fp.rm_h, s.rank, c->shard_count) * fp.rm_w
+                                      : (traced > s.rank ? (traced - s.rank + c->shard_count - 1) / c->shard_count : 0);
     fp.sp_shift = (c->ss == 2) ? 2 : (c->ss == 4) ? 4 : 0;   // sample-parallel supersampling: 4 or 16 rays per pixel
     {
         const char* serial = std::getenv("CSG_B200_SERIAL_SS");   // testing aid: loop over the samples in one lane
@@ -305,7 +348,11 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
 
 // Enqueue one frame on every shard.  mode: OUT_RGBA8 -> out = rgba8 target (NULL: each shard's own target),
 // OUT_F32 / OUT_AOV only on single-shard contexts.
-int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], int mode, void* out)
+// shard_mode 0: macro tiles interleaved over the shards, every shard stores into one framebuffer (the root's, over NVLink), the
+//               frame is started and joined on the device through the root's SyncWords (GateParams);
+// shard_mode 1: macro-tile rows interleaved over the shards, every shard renders into its own local framebuffer (host output:
+//               each shard then copies its own rows over its own PCIe link); no dependency between the shards.
+int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], int mode, void* out, int shard_mode = 0)
 {
     if (!c || !cam) return fail(CSG_ERR_ARG, "null argument");
     if (mode != OUT_RGBA8 && c->shards.size() != 1) return fail(CSG_ERR_ARG, "f32/aov output needs a single-shard context");
@@ -319,17 +366,31 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
         c->cached_fov = cam->fov;
         c->launches++;
     }
-    if (c->band_m0 == 0) CU(cudaEventRecord(root.ev_start, root.stream));   // later bands of a banded frame keep the first band's start mark
-    for (size_t i = 1; i < c->shards.size(); ++i) {   // peers start after the root's start mark
-        CU(cudaSetDevice(c->shards[i].device));
-        CU(cudaStreamWaitEvent(c->shards[i].stream, root.ev_start, 0));
-    }
+    // device-side start gate + join: frames whose shards all store into the root's framebuffer
+    const bool joined = c->shard_count > 1 && shard_mode == 0 && mode == OUT_RGBA8 && c->shard_sync;
+    if (joined) ++c->frame_seq;
+    c->last_mode = shard_mode;
     const int total_warps_per_cta = c->threads / 32;
-    for (Shard& s : c->shards) {
+    // The other shards first, the root last: a peer's kernels wait on the device for the root's start word, so by the time
+    // the root's first kernel runs (right behind its start event) the peers of an in-process context are already queued.
+    for (size_t k = c->shards.size(); k-- > 0;) {
+        Shard& s = c->shards[k];
         CU(cudaSetDevice(s.device));
+        if (&s == &root && c->band_m0 == 0) CU(cudaEventRecord(root.ev_start, root.stream));   // later bands of a banded frame keep the first band's start mark
         FrameParams fp;
-        fill_params(c, s, cam, light, fp);
-        c->last_rm[0] = fp.rm_x0; c->last_rm[1] = fp.rm_y0; c->last_rm[2] = fp.n_local_warp_tiles ? fp.rm_w : 0; c->last_rm[3] = fp.n_local_warp_tiles ? fp.rm_h : 0;
+        fill_params(c, s, cam, light, shard_mode, fp);
+        if (&s == &root) { c->last_rm[0] = fp.rm_x0; c->last_rm[1] = fp.rm_y0; c->last_rm[2] = fp.rm_h ? fp.rm_w : 0; c->last_rm[3] = fp.rm_h; }
+        GateParams gate;
+        std::memset(&gate, 0, sizeof gate);
+        if (joined && s.sync_words) {
+            gate.role = s.rank == 0 ? GATE_ROOT : GATE_PEER;
+            gate.seq = c->frame_seq;
+            gate.n_shards = c->shard_count;
+            gate.rank = s.rank;
+            gate.words = s.sync_words;
+            gate.exit_counter = s.d_exit;
+            gate.err = s.d_err;
+        }
         {   // per-tile pruned trees + the staged copy of the whole tree for this camera
             PruneParams q;
             std::memset(&q, 0, sizeof q);
@@ -339,7 +400,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.tan_half_fov = fp.tan_half_fov; q.wm1 = fp.wm1; q.hm1 = fp.hm1; q.aspect = fp.aspect; q.ss = fp.ss;
             q.width = fp.width; q.height = fp.height; q.macro_x = fp.macro_x;
             q.rm_x0 = fp.rm_x0; q.rm_y0 = fp.rm_y0; q.rm_w = fp.rm_w; q.rm_magic = fp.rm_magic;
-            q.shard_rank = fp.shard_rank; q.shard_count = fp.shard_count;
+            q.shard_rank = fp.shard_rank; q.shard_count = fp.shard_count; q.shard_mode = fp.shard_mode; q.row_first = fp.row_first;
             q.n_tiles = c->prune ? (fp.n_local_warp_tiles >> (fp.sp_shift - fp.sp_group)) / 64 : 0;
             q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes; q.parent = s.d_parent;
             q.leaf_boxes = s.d_leaf_boxes; q.n_leaves = (int)(c->tree.leaf_boxes.size() / 8);
@@ -352,9 +413,11 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes;
             q.slots_off32 = (uint32_t)fp.n_nodes; q.full_flags = c->full_flags;
             // view cache (opt-in): same camera, size, sampling and tile set as the trees this shard already holds -> keep them
+            // (compared before the gate goes in: its sequence number changes with every frame)
             const bool cached = c->view_cache && s.last_q_valid && std::memcmp(&q, &s.last_q, sizeof q) == 0;
             s.last_q = q;
             s.last_q_valid = true;
+            q.gate = gate;
             const int stage_ctas = std::max(1, std::min(64, (fp.n_nodes + kPruneThreads - 1) / kPruneThreads));
             if (!cached) {
                 if (c->prune_flat && c->flat_ok) {
@@ -374,9 +437,10 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("prune kernel launch: ") + cudaGetErrorString(e));
             if (!cached) c->launches++;
         }
+        fp.gate = gate;
         int rc = CSG_OK;
         if (mode == OUT_RGBA8) {
-            fp.out = out ? out : (void*)s.target;
+            fp.out = out ? out : (void*)(shard_mode ? s.local_fb : s.target);
             if (!fp.out) return fail(CSG_ERR_ARG, "no output target");
             rc = launch_mode<OUT_RGBA8>(c, s, fp);
         } else if (mode == OUT_F32) {
@@ -396,7 +460,8 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
         if (&s != &root) CU(cudaEventRecord(s.ev_done, s.stream));
     }
     CU(cudaSetDevice(root.device));
-    for (size_t i = 1; i < c->shards.size(); ++i) CU(cudaStreamWaitEvent(root.stream, c->shards[i].ev_done, 0));
+    if (!joined || !root.sync_words)   // no device-side join (row-sharded frames, or no sync words): the root's done event follows the peers' events
+        for (size_t i = 1; i < c->shards.size(); ++i) CU(cudaStreamWaitEvent(root.stream, c->shards[i].ev_done, 0));
     CU(cudaEventRecord(root.ev_done, root.stream));
     c->frame_pending = true;
     return CSG_OK;
@@ -412,6 +477,11 @@ int sync_frame(csg_context* c)
         c->frame_pending = false;
     }
     CU(cudaGetLastError());
+    for (Shard& s : c->shards)
+        if (s.h_err && *reinterpret_cast<volatile int*>(s.h_err)) {
+            *s.h_err = 0;
+            return fail(CSG_ERR_CUDA, "sharded frame: a device-side wait for another shard timed out (did every rank enqueue the frame?)");
+        }
     return CSG_OK;
 }
 
@@ -432,6 +502,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     if (width < 2 || height < 2) return fail(CSG_ERR_ARG, "width and height must be >= 2");  // (w-1),(h-1) divisors, Q1
     if ((long long)width * height >= (1ll << 31)) return fail(CSG_ERR_ARG, "width*height must be below 2^31");
     if (scene->scene.nodes.empty()) return fail(CSG_ERR_ARG, "empty scene");
+    if (int rc = scene_within_limits(scene->scene)) return rc;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -453,13 +524,13 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     c->root_box_valid = c->tree.root_box_valid;
     for (int i = 0; i < 6; ++i) c->root_box[i] = c->tree.root_box[i];
 
-    auto cleanup_fail = [&](int code) { csg_free_context(c); return code; };
+    auto cleanup_fail = [&](int code) { const std::string keep = g_err; csg_free_context(c); g_err = keep; return code; };
 
     // shared memory plan: [table 128 B][stack 16 B x (levels+2) x threads][tree 32 B/node]
-    CU(cudaSetDevice(devices[0]));
+    CUC(cudaSetDevice(devices[0]));
     int max_optin = 0, sms = 0;
-    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, devices[0]));
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devices[0]));
+    CUC(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, devices[0]));
+    CUC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devices[0]));
     const size_t tree_bytes = c->tree.nodes.size() * sizeof(NodeRec);
     const size_t table_bytes = 32 * sizeof(uint32_t);
     {
@@ -522,73 +593,86 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         Shard& s = c->shards[i];
         s.device = devices[i];
         s.rank = shard_rank0 + (int)i;
-        CU(cudaSetDevice(s.device));
+        CUC(cudaSetDevice(s.device));
         int bps = 0, rc;
         rc = configure_shape(c->threads, c->smem_bytes, &bps);
-        if (rc) return cleanup_fail(rc);
+        if (rc) { const std::string keep = g_err; csg_free_context(c); g_err = keep; return rc; }
         if (bps < 1) { g_err = "kernel does not fit on an SM"; return cleanup_fail(CSG_ERR_LIMIT); }
         int dev_sms = 0;
-        CU(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s.device));
-        const int my_macros = (total_macros - s.rank + shard_count - 1) / shard_count;
+        CUC(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s.device));
+        const int my_macros = slots_per_shard(c->macro_x, c->macro_y, shard_count);   // upper bound of this shard's macro tiles, either shard mode
         s.n_local_warp_tiles = my_macros * 64;
         const int want = (s.n_local_warp_tiles + (c->threads / 32) - 1) / (c->threads / 32);
         if (const char* cap = std::getenv("CSG_B200_CTAS_PER_SM")) bps = std::max(1, std::min(bps, std::atoi(cap)));   // tuning aid
         s.grid = std::max(1, std::min(dev_sms * bps, want));   // persistent CTAs: a multiple of the SM count
-        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CU(cudaEventCreate(&s.ev_start));
-        CU(cudaEventCreate(&s.ev_done));
-        CU(cudaMalloc(&s.d_nodes, std::max<size_t>(tree_bytes, 32)));
-        CU(cudaMemcpy(s.d_nodes, c->tree.nodes.data(), tree_bytes, cudaMemcpyHostToDevice));
+        CUC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CUC(cudaEventCreate(&s.ev_start));
+        CUC(cudaEventCreate(&s.ev_done));
+        CUC(cudaMalloc(&s.d_nodes, std::max<size_t>(tree_bytes, 32)));
+        CUC(cudaMemcpy(s.d_nodes, c->tree.nodes.data(), tree_bytes, cudaMemcpyHostToDevice));
         {
-            s.n_slots = my_macros;
+            // slot of macro tile m = m / shard_count (csg_prune.cuh); a shard is handed tiles by their position inside the traced
+            // rectangle, so any macro tile of the frame can come its way: ceil(total / count) slots, whatever the rank
+            s.n_slots = slots_per_shard(c->macro_x, c->macro_y, shard_count);
             const size_t pool_records = c->tree.nodes.size() + (c->prune ? (size_t)s.n_slots * c->slot_nodes : 0);
-            CU(cudaMalloc(&s.d_pool, std::max<size_t>(pool_records, 1) * sizeof(NodeRec)));
-            CU(cudaMalloc(&s.d_desc, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
-            CU(cudaMemset(s.d_desc, 0, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
-            CU(cudaMalloc(&s.d_parent, std::max<size_t>(c->tree.parent.size(), 1) * sizeof(int)));
-            CU(cudaMemcpy(s.d_parent, c->tree.parent.data(), c->tree.parent.size() * sizeof(int), cudaMemcpyHostToDevice));
-            CU(cudaMalloc(&s.d_leaf_boxes, std::max<size_t>(c->tree.leaf_boxes.size(), 8) * sizeof(float)));
-            CU(cudaMemcpy(s.d_leaf_boxes, c->tree.leaf_boxes.data(), c->tree.leaf_boxes.size() * sizeof(float), cudaMemcpyHostToDevice));
+            CUC(cudaMalloc(&s.d_pool, std::max<size_t>(pool_records, 1) * sizeof(NodeRec)));
+            CUC(cudaMalloc(&s.d_desc, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
+            CUC(cudaMemset(s.d_desc, 0, std::max<size_t>(s.n_slots, 1) * sizeof(TileDesc)));
+            CUC(cudaMalloc(&s.d_parent, std::max<size_t>(c->tree.parent.size(), 1) * sizeof(int)));
+            CUC(cudaMemcpy(s.d_parent, c->tree.parent.data(), c->tree.parent.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CUC(cudaMalloc(&s.d_leaf_boxes, std::max<size_t>(c->tree.leaf_boxes.size(), 8) * sizeof(float)));
+            CUC(cudaMemcpy(s.d_leaf_boxes, c->tree.leaf_boxes.data(), c->tree.leaf_boxes.size() * sizeof(float), cudaMemcpyHostToDevice));
             const char* no_order = std::getenv("CSG_B200_NO_ORDER");   // tuning aid: tiles handed out in their natural order
             if (c->prune && s.n_slots <= 65535 && !(no_order && no_order[0] == '1')) {   // bounds the bucket lists (64 x n_slots x 16 bytes)
-                CU(cudaMalloc(&s.d_hist, (kCostBuckets + 1) * sizeof(unsigned int)));
-                CU(cudaMemset(s.d_hist, 0, (kCostBuckets + 1) * sizeof(unsigned int)));
-                CU(cudaMalloc(&s.d_lists, (size_t)kCostBuckets * std::max(s.n_slots, 1) * sizeof(uint4)));
-                CU(cudaMalloc(&s.d_order, (size_t)std::max(s.n_slots, 1) * sizeof(uint4)));
+                CUC(cudaMalloc(&s.d_hist, (kCostBuckets + 1) * sizeof(unsigned int)));
+                CUC(cudaMemset(s.d_hist, 0, (kCostBuckets + 1) * sizeof(unsigned int)));
+                CUC(cudaMalloc(&s.d_lists, (size_t)kCostBuckets * std::max(s.n_slots, 1) * sizeof(uint4)));
+                CUC(cudaMalloc(&s.d_order, (size_t)std::max(s.n_slots, 1) * sizeof(uint4)));
             }
             if (c->prune_smem > 48 * 1024)
-                CU(cudaFuncSetAttribute(csg_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->prune_smem));
+                CUC(cudaFuncSetAttribute(csg_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->prune_smem));
             if (c->flat_ok) {
                 std::vector<uint2> topo(c->tree.nodes.size());
                 for (size_t k = 0; k < topo.size(); ++k) topo[k] = make_uint2(c->tree.nodes[k].meta, c->tree.subtree_end[k]);
-                CU(cudaMalloc(&s.d_topo, std::max<size_t>(topo.size(), 1) * sizeof(uint2)));
-                CU(cudaMemcpy(s.d_topo, topo.data(), topo.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+                CUC(cudaMalloc(&s.d_topo, std::max<size_t>(topo.size(), 1) * sizeof(uint2)));
+                CUC(cudaMemcpy(s.d_topo, topo.data(), topo.size() * sizeof(uint2), cudaMemcpyHostToDevice));
                 if (c->flat_smem > 48 * 1024) {
-                    CU(cudaFuncSetAttribute(csg_prune_flat_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
-                    CU(cudaFuncSetAttribute(csg_prune_flat_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
-                    CU(cudaFuncSetAttribute(csg_prune_flat_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
+                    CUC(cudaFuncSetAttribute(csg_prune_flat_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
+                    CUC(cudaFuncSetAttribute(csg_prune_flat_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
+                    CUC(cudaFuncSetAttribute(csg_prune_flat_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->flat_smem));
                 }
             }
         }
         const size_t prim_bytes = c->tree.prims.size() * sizeof(PrimRec);
-        CU(cudaMalloc(&s.d_prims, std::max<size_t>(prim_bytes, 80)));
-        CU(cudaMemcpy(s.d_prims, c->tree.prims.data(), prim_bytes, cudaMemcpyHostToDevice));
-        CU(cudaMalloc(&s.d_tan, sizeof(float)));
-        CU(cudaMalloc(&s.d_counter, sizeof(unsigned int)));
-        CU(cudaMemset(s.d_counter, 0, sizeof(unsigned int)));
+        CUC(cudaMalloc(&s.d_prims, std::max<size_t>(prim_bytes, 80)));
+        CUC(cudaMemcpy(s.d_prims, c->tree.prims.data(), prim_bytes, cudaMemcpyHostToDevice));
+        CUC(cudaMalloc(&s.d_tan, sizeof(float)));
+        CUC(cudaMalloc(&s.d_counter, sizeof(unsigned int)));
+        CUC(cudaMemset(s.d_counter, 0, sizeof(unsigned int)));
+        CUC(cudaMalloc(&s.d_exit, sizeof(unsigned int)));
+        CUC(cudaMemset(s.d_exit, 0, sizeof(unsigned int)));
+        CUC(cudaHostAlloc(&s.h_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        *s.h_err = 0;
+        CUC(cudaHostGetDevicePointer(&s.d_err, s.h_err, 0));
         if (i == 0) {
-            CU(cudaMalloc(&c->d_fb, (size_t)width * height * 4));
-            CU(cudaMemset(c->d_fb, 0, (size_t)width * height * 4));
+            // the framebuffer, and behind it (same allocation, so that one IPC handle covers both) the SyncWords of sharded frames
+            c->sync_off = (((size_t)width * height * 4) + 255) & ~(size_t)255;
+            CUC(cudaMalloc(&c->d_fb, c->sync_off + sizeof(SyncWords)));
+            CUC(cudaMemset(c->d_fb, 0, c->sync_off + sizeof(SyncWords)));
+            s.local_fb = c->d_fb;
         } else {
             // NVLink peer stores into the root framebuffer
             int can = 0;
-            CU(cudaDeviceCanAccessPeer(&can, s.device, devices[0]));
+            CUC(cudaDeviceCanAccessPeer(&can, s.device, devices[0]));
             if (!can) { g_err = "device " + std::to_string(s.device) + " cannot access device " + std::to_string(devices[0]) + " (P2P)"; return cleanup_fail(CSG_ERR_CUDA); }
             cudaError_t pe = cudaDeviceEnablePeerAccess(devices[0], 0);
             if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { g_err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe); return cleanup_fail(CSG_ERR_CUDA); }
             cudaGetLastError();
         }
         s.target = c->d_fb;
+        // in-process: every shard sees the root's words through peer access; one process per GPU: the root has them, the
+        // others get them with the root's IPC handle (csg_set_gather_target_ipc)
+        s.sync_words = (shard_count > 1 && (!multi_process || s.rank == 0)) ? reinterpret_cast<SyncWords*>(c->d_fb + c->sync_off) : nullptr;
     }
     char buf[512];
     std::snprintf(buf, sizeof buf,
@@ -658,6 +742,7 @@ int csg_scene_dump(const csg_scene* scene, void* nodes44, void* prims48)
 int csg_scene_flatten(const csg_scene* scene, void* nodes32, int32_t* parents, int* n_nodes, int* depth)
 {
     if (!scene) return fail(CSG_ERR_ARG, "null scene");
+    if (int rc = scene_within_limits(scene->scene)) return rc;
     FlatTree t;
     flatten(scene->scene, scene->scene.optimize, t);
     if (nodes32) std::memcpy(nodes32, t.nodes.data(), t.nodes.size() * sizeof(NodeRec));
@@ -669,7 +754,7 @@ int csg_scene_flatten(const csg_scene* scene, void* nodes32, int32_t* parents, i
 
 size_t csg_scene_write(const csg_scene* scene, char* buf, size_t buflen)
 {
-    if (!scene) return 0;
+    if (!scene || scene_within_limits(scene->scene)) return 0;
     const std::string s = write_scene(scene->scene);
     if (buf && buflen) {
         const size_t n = std::min(buflen - 1, s.size());
@@ -783,17 +868,20 @@ void csg_free_context(csg_context* c)
 {
     if (!c) return;
     if (c->twin) csg_free_context(c->twin);
-    if (c->copy_stream) {
-        cudaStreamSynchronize(c->copy_stream);
-        cudaStreamDestroy(c->copy_stream);
-        for (cudaEvent_t e : c->ev_band) if (e) cudaEventDestroy(e);
-    }
     if (c->ev_batch0) cudaEventDestroy(c->ev_batch0);
     if (c->ev_batch1) cudaEventDestroy(c->ev_batch1);
     for (Shard& s : c->shards) {
         cudaSetDevice(s.device);
         if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.copy_stream) {
+            cudaStreamSynchronize(s.copy_stream);
+            cudaStreamDestroy(s.copy_stream);
+            for (cudaEvent_t e : s.ev_band) if (e) cudaEventDestroy(e);
+        }
         if (s.ipc_mapped) cudaIpcCloseMemHandle(s.ipc_mapped);
+        if (s.owns_local_fb) cudaFree(s.local_fb);
+        cudaFree(s.d_exit);
+        if (s.h_err) cudaFreeHost(s.h_err);
         cudaFree(s.d_nodes);
         cudaFree(s.d_pool);
         cudaFree(s.d_desc);
@@ -878,6 +966,9 @@ int csg_set_gather_target_ipc(csg_context* ctx, const void* handle64)
     if (s.ipc_mapped) cudaIpcCloseMemHandle(s.ipc_mapped);
     s.ipc_mapped = p;
     s.target = static_cast<uint8_t*>(p);
+    // the root's SyncWords sit behind its framebuffer in the same allocation (same width x height on every rank)
+    s.sync_words = reinterpret_cast<SyncWords*>(s.target + ctx->sync_off);
+    ctx->shard_sync = true;
     return CSG_OK;
 }
 
@@ -886,6 +977,9 @@ int csg_set_gather_target(csg_context* ctx, uint8_t* rgba8_dev)
     if (!ctx) return fail(CSG_ERR_ARG, "null context");
     for (Shard& s : ctx->shards) s.target = rgba8_dev ? rgba8_dev : ctx->d_fb;
     ctx->external_target = rgba8_dev != nullptr;
+    // one process per GPU: a raw pointer says nothing about where the root keeps its SyncWords — such frames are neither gated
+    // nor joined on the device (every rank has to be set up the same way; the caller synchronises the ranks itself)
+    if (ctx->multi_process) ctx->shard_sync = rgba8_dev == nullptr;
     return CSG_OK;
 }
 
@@ -898,51 +992,88 @@ int csg_read_framebuffer(csg_context* ctx, uint8_t* rgba8_host)
     return CSG_OK;
 }
 
+// Bands of macro-tile rows a host-bound frame is rendered in: the first one must be rendered before any byte moves, the others
+// hide behind the copies (PCIe is the bottleneck); every band costs its own pair of launches.  Measured at 4K (68 tile rows) on
+// one GPU: 1 band 807 us, 4: 672, 6: 659, 8: 686.  With N shards every shard moves 1/N of the bytes over its own link.
+static int host_bands(const csg_context* ctx)
+{
+    int n = ctx->macro_y >= 16 * ctx->shard_count ? (ctx->macro_y >= 48 ? std::max(1, 6 / ctx->shard_count) : std::max(1, 4 / ctx->shard_count)) : 1;
+    if (const char* nb = std::getenv("CSG_B200_BANDS")) n = std::min(std::max(std::atoi(nb), 1), 8);   // tuning aid
+    return n;
+}
+
 int csg_render(csg_context* ctx, const csg_camera* cam, const csg_light* light, uint8_t* rgba8_out)
 {
     if (!ctx || !cam || !light || !rgba8_out) return fail(CSG_ERR_ARG, "null argument");
     const bool dev = is_device_pointer(rgba8_out);
     float ld[3];
     csg_light_direction(light, ld);
-    // multi-shard contexts always gather into the root framebuffer first
-    const bool direct = dev && ctx->shards.size() == 1;
     Shard& root = ctx->shards[0];
     const size_t bytes = (size_t)ctx->width * ctx->height * 4;
-    // bands: the first one must be rendered before any byte moves, the others hide behind the copies (PCIe is the bottleneck);
-    // every band costs its own pair of launches.  Measured at 4K (68 tile rows): 1 band 807 us, 4: 672, 6: 659, 8: 686.
-    int n_bands = (!dev && ctx->shards.size() == 1 && ctx->shard_count == 1 && !ctx->external_target && ctx->macro_y >= 16) ? (ctx->macro_y >= 48 ? 6 : 4) : 1;
-    if (const char* nb = std::getenv("CSG_B200_BANDS")) n_bands = n_bands > 1 ? std::min(std::max(std::atoi(nb), 1), 8) : 1;   // tuning aid
-    if (n_bands > 1) {
-        // Host output on one GPU: the frame is rendered in bands of macro-tile rows; band k travels over PCIe (the 33 MB copy
-        // is 3x the render time at 4K) while band k+1 renders.
-        CU(cudaSetDevice(root.device));
-        if (!ctx->copy_stream) {
-            CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-            for (cudaEvent_t& e : ctx->ev_band) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!dev && !ctx->external_target) {
+        // Host output.  The frame is dealt out in macro-tile ROWS (shard mode 1): every shard renders its rows into its own local
+        // framebuffer and copies them to the host buffer itself — N GPUs move the frame over N PCIe links (one process per GPU:
+        // this rank's rows only; the caller passes every rank the same buffer, e.g. shared memory).  Rows come in bands: band k
+        // travels while band k+1 renders.
+        const int n_bands = host_bands(ctx);
+        const int count = ctx->shard_count;
+        const size_t row_bytes = (size_t)kMacroH * ctx->width * 4;
+        for (Shard& s : ctx->shards) {
+            CU(cudaSetDevice(s.device));
+            if (!s.local_fb) {
+                CU(cudaMalloc(&s.local_fb, bytes));
+                s.owns_local_fb = true;
+            }
+            if (!s.copy_stream) {
+                CU(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+                for (cudaEvent_t& e : s.ev_band) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
         }
         int rc = CSG_OK;
         int rm[4] = {0, 0, 0, 0};   // union of the bands' traced rectangles, for csg_prune_stats
         for (int b = 0; b < n_bands && !rc; ++b) {
             ctx->band_m0 = ctx->macro_y * b / n_bands;
             ctx->band_m1 = ctx->macro_y * (b + 1) / n_bands;
-            rc = enqueue_frame(ctx, cam, ld, OUT_RGBA8, nullptr);
+            rc = enqueue_frame(ctx, cam, ld, OUT_RGBA8, nullptr, 1);
             if (rc) break;
             if (ctx->last_rm[2] > 0 && ctx->last_rm[3] > 0) {
                 if (rm[3] == 0) { rm[0] = ctx->last_rm[0]; rm[1] = ctx->last_rm[1]; rm[2] = ctx->last_rm[2]; }
                 rm[3] = ctx->last_rm[1] + ctx->last_rm[3] - rm[1];
             }
-            const size_t r0 = (size_t)ctx->band_m0 * kMacroH, r1 = std::min<size_t>((size_t)ctx->band_m1 * kMacroH, (size_t)ctx->height);
-            const size_t off = r0 * ctx->width * 4, len = (r1 - r0) * ctx->width * 4;
-            CU(cudaEventRecord(ctx->ev_band[b], root.stream));
-            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
-            CU(cudaMemcpyAsync(rgba8_out + off, ctx->d_fb + off, len, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            for (Shard& s : ctx->shards) {
+                // this shard's rows of the band: first, first + count, ...; all but a ragged last row of the frame in one 2-D copy
+                const int first = shard_row_first(ctx->band_m0, s.rank, count);
+                int n_rows = shard_row_count(ctx->band_m0, ctx->band_m1 - ctx->band_m0, s.rank, count);
+                if (n_rows == 0) continue;
+                CU(cudaSetDevice(s.device));
+                CU(cudaEventRecord(s.ev_band[b], s.stream));
+                CU(cudaStreamWaitEvent(s.copy_stream, s.ev_band[b], 0));
+                const int last = first + (n_rows - 1) * count;
+                const size_t last_lines = std::min<size_t>((size_t)(last + 1) * kMacroH, (size_t)ctx->height) - (size_t)last * kMacroH;
+                if (last_lines < (size_t)kMacroH) {
+                    const size_t off = (size_t)last * row_bytes;
+                    CU(cudaMemcpyAsync(rgba8_out + off, s.local_fb + off, last_lines * ctx->width * 4, cudaMemcpyDeviceToHost, s.copy_stream));
+                    --n_rows;
+                }
+                if (n_rows > 0) {
+                    const size_t off = (size_t)first * row_bytes;
+                    if (count == 1) CU(cudaMemcpyAsync(rgba8_out + off, s.local_fb + off, n_rows * row_bytes, cudaMemcpyDeviceToHost, s.copy_stream));
+                    else CU(cudaMemcpy2DAsync(rgba8_out + off, count * row_bytes, s.local_fb + off, count * row_bytes, row_bytes, (size_t)n_rows,
+                                              cudaMemcpyDeviceToHost, s.copy_stream));
+                }
+            }
         }
         ctx->band_m0 = ctx->band_m1 = 0;
         for (int i = 0; i < 4; ++i) ctx->last_rm[i] = rm[i];
         if (rc) return rc;
-        CU(cudaStreamSynchronize(ctx->copy_stream));
+        for (Shard& s : ctx->shards) {
+            CU(cudaSetDevice(s.device));
+            CU(cudaStreamSynchronize(s.copy_stream));
+        }
         return sync_frame(ctx);
     }
+    // device destination (or an external gather target): multi-shard contexts gather into the root framebuffer first
+    const bool direct = dev && ctx->shards.size() == 1 && ctx->shard_count == 1;
     int rc = enqueue_frame(ctx, cam, ld, OUT_RGBA8, direct ? (void*)rgba8_out : nullptr);
     if (rc) return rc;
     if (!direct) {
@@ -1092,9 +1223,9 @@ int csg_prune_stats(csg_context* ctx, int* traced_tiles, int* empty_tiles, int* 
     for (int jy = 0; jy < ctx->last_rm[3]; ++jy)
         for (int jx = 0; jx < ctx->last_rm[2]; ++jx) {
             const int j = jy * ctx->last_rm[2] + jx;
-            if (j % ctx->shard_count != s.rank) continue;
-            const int m = (ctx->last_rm[1] + jy) * ctx->macro_x + ctx->last_rm[0] + jx;
-            const TileDesc& t = d[(size_t)(m / ctx->shard_count)];
+            const int mx = ctx->last_rm[0] + jx, my = ctx->last_rm[1] + jy;
+            if ((ctx->last_mode ? my : j) % ctx->shard_count != s.rank) continue;
+            const TileDesc& t = d[(size_t)slot_of_macro(ctx->last_mode, mx, my, ctx->macro_x, ctx->shard_count)];
             ++traced;
             if (t.n_nodes == 0) ++empty;
             else if (t.offset32 == 0 && ctx->prune) ++fb;
@@ -1189,5 +1320,27 @@ int csg_debug_prune_probe(void* out, size_t bytes)
 #endif
 
 const char* csg_context_info(csg_context* ctx) { return ctx ? ctx->info.c_str() : ""; }
+
+int csg_shard_tile(int macro_x, int macro_y, int rm_x0, int rm_y0, int rm_w, int rm_h, int shard_mode, int shard_rank, int shard_count,
+                   int tile, int* mx, int* my, int* slot, int* n_tiles, int* n_slots)
+{
+    if (macro_x < 1 || macro_y < 1 || rm_w < 0 || rm_h < 0 || rm_x0 < 0 || rm_y0 < 0 || rm_x0 + rm_w > macro_x || rm_y0 + rm_h > macro_y ||
+        shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count)
+        return fail(CSG_ERR_ARG, "bad tile rectangle or shard");
+    const long long traced = (long long)rm_w * rm_h;
+    const long long mine = shard_mode ? (long long)shard_row_count(rm_y0, rm_h, shard_rank, shard_count) * rm_w
+                                      : (traced > shard_rank ? (traced - shard_rank + shard_count - 1) / shard_count : 0);
+    if (n_tiles) *n_tiles = (int)mine;
+    if (n_slots) *n_slots = slots_per_shard(macro_x, macro_y, shard_count);
+    if (tile < 0 || tile >= mine) return fail(CSG_ERR_ARG, "tile out of range");
+    // the same host-computed reciprocal the kernels divide with (fill_params)
+    const unsigned int magic = (rm_w > 1 && rm_w < 4096 && traced < (1ll << 20)) ? (unsigned int)((1ull << 32) / (unsigned long long)rm_w + 1ull) : 0u;
+    int x, y;
+    shard_tile_coords(tile, shard_mode, shard_rank, shard_count, rm_x0, rm_y0, rm_w, magic, shard_row_first(rm_y0, shard_rank, shard_count), x, y);
+    if (mx) *mx = x;
+    if (my) *my = y;
+    if (slot) *slot = slot_of_macro(shard_mode, x, y, macro_x, shard_count);
+    return CSG_OK;
+}
 
 }  // extern "C"

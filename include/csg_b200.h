@@ -103,9 +103,13 @@ int csg_scene_set_optimize(csg_scene* scene, int level);
 
 /* ---- render: replaces Raycaster::Raycast(float4* devPBO, Camera, DirectionalLight) (Raycaster.cu:23-34).
  * All three are synchronous (return when the output is complete), like the reference. */
-/* rgba8_out: width*height*4 bytes; host OR device pointer (detected with cudaPointerGetAttributes).  With a host pointer on
- * a single-GPU context the frame is rendered in bands of tile rows (6 at 4K) and each band is copied out while the next renders
- * (use pinned memory for the copies to overlap). */
+/* rgba8_out: width*height*4 bytes; host OR device pointer (detected with cudaPointerGetAttributes).
+ * Host pointer: the frame is dealt out to the context's GPUs in rows of 64x32-pixel tiles; every GPU renders its rows into its
+ * own memory and copies them to rgba8_out over its own PCIe link, band by band while the next band renders (6 bands at 4K on
+ * one GPU; use pinned memory — cudaHostAllocPortable / cudaHostRegisterPortable for several GPUs — for the copies to overlap).
+ * On a csg_upload_shard context (one process per GPU) the call renders and copies THIS rank's rows only: give every rank the
+ * same buffer (shared memory) and the frame is complete when every rank has returned.
+ * Device pointer: multi-GPU contexts gather the frame in GPU 0's framebuffer over NVLink, then copy it. */
 int csg_render(csg_context* ctx, const csg_camera* cam, const csg_light* light, uint8_t* rgba8_out);
 /* rgba_f32_out: width*height float4, linear colour exactly as the reference's LightningKernel writes its
  * PBO (RaycastingKernels.cu:49-111); host or device pointer.  This is the literal PBO drop-in. */
@@ -159,7 +163,10 @@ uint64_t csg_launch_count(const csg_context* ctx);
 int csg_framebuffer(csg_context* ctx, uint8_t** rgba8_dev);
 /* Multi-process gather: 64-byte cudaIpcMemHandle_t of this context's framebuffer (root rank) ... */
 int csg_framebuffer_ipc_handle(csg_context* ctx, void* handle64);
-/* ... and on the other ranks: open the root's handle and make it the target of csg_render_enqueue(NULL). */
+/* ... and on the other ranks: open the root's handle and make it the target of csg_render_enqueue(NULL).  The handle also
+ * carries the root's sync words: a sharded frame starts, on every GPU, when the root GPU starts it, and the root's frame is
+ * complete (csg_sync / csg_last_frame_ms on rank 0) only when every rank's pixels have landed — all on the device, no host
+ * round trip.  Every rank must enqueue every frame; a rank that waits more than 2 s for another fails with CSG_ERR_CUDA. */
 int csg_set_gather_target_ipc(csg_context* ctx, const void* handle64);
 /* Same, for a pointer that is already addressable from this context's device. */
 int csg_set_gather_target(csg_context* ctx, uint8_t* rgba8_dev);
@@ -176,6 +183,13 @@ int csg_fp32_peak_tflops(int device, float* tflops);
 
 /* Description of the launch configuration chosen at upload, as JSON (threads, CTAs, smem, tree bytes...). */
 const char* csg_context_info(csg_context* ctx);
+
+/* Host-side view of the tile hand-out the kernels use (no device needed; for tests): a frame of macro_x x macro_y macro tiles
+ * whose traced rectangle is (rm_x0, rm_y0, rm_w, rm_h), dealt out to shard_count shards by interleaved tiles (shard_mode 0) or
+ * interleaved macro-tile rows (shard_mode 1).  Reports how many tiles shard_rank gets (*n_tiles), how many tree slots a shard
+ * owns (*n_slots), and for its tile number `tile` the macro tile (*mx, *my) and the slot its tree is written to. */
+int csg_shard_tile(int macro_x, int macro_y, int rm_x0, int rm_y0, int rm_w, int rm_h, int shard_mode, int shard_rank, int shard_count,
+                   int tile, int* mx, int* my, int* slot, int* n_tiles, int* n_slots);
 
 const char* csg_last_error(void);
 const char* csg_version(void);

@@ -413,9 +413,9 @@ static void sphere_hit(const ray_t* ray, const orc_prim* sp, hitmin* h, float tm
     if (discriminant < 0) return;        /* :149 */
     float sq = sqrtf(discriminant);
     float temp = (-b) - sq;              /* :151 */
-    if (!(temp > tmin)) {                /* :152  temp <= tmin (or unordered) */
+    if (temp <= tmin) {                  /* :152  (a NaN root is NOT rejected: the reference's own comparison) */
         temp = sq - b;                   /* :153 */
-        if (!(temp > tmin)) {            /* :154-160 */
+        if (temp <= tmin) {              /* :154-160 */
             h->t = -1;
             h->hit = R_MISS;
             h->primitiveIdx = -1;
