@@ -5,12 +5,26 @@
   python bench.py --impl reference [--gpus N] [--steps K] ...      the reference's own implementation on the host cores
 
 A step = one frame = one pass of the hot path over all width*height primary rays.
-N > 1: launched by torchrun, one process per GPU; the frame is sharded in interleaved 64x32-pixel tiles, every rank's
-kernel stores its pixels straight into rank 0's framebuffer over NVLink (CUDA-IPC peer pointer); no collective on the
-data path.  Prints ONE JSON line on rank 0.
+
+N > 1: launched by torchrun, one process per GPU.
+  value (device time): the frame is sharded in interleaved 64x32-pixel tiles, every rank's kernel stores its pixels straight
+      into rank 0's framebuffer over NVLink (CUDA-IPC peer pointer); no collective on the data path.  The frame is started and
+      joined ON THE DEVICE through sync words behind rank 0's framebuffer: a peer's kernels do nothing before rank 0's GPU has
+      started the frame, and rank 0's last kernel does not end before every peer has reported its pixels landed.  ms_per_step
+      is therefore rank 0's CUDA-event span "frame started on the root GPU -> framebuffer complete on the root GPU" (SURVEY.md
+      8d) — peers' work and any lateness of their launches are inside it.
+  e2e: csg_render() into ONE host framebuffer (shared memory, page-locked in every rank): the frame is dealt out in rows of
+      tiles, every GPU renders its rows and copies them over its own PCIe link.  Time = first rank's call -> last rank's
+      return (CLOCK_MONOTONIC is system-wide).
+  parity_n: outside the timed region the gathered N-GPU framebuffer (both paths) is compared byte for byte with the frame
+      rank 0 renders alone.
+Prints ONE JSON line on rank 0; `configs` (every BASELINE.json config at this N) and `parity_n` are its last keys.
 """
 import argparse
+import hashlib
 import json
+import math
+import mmap
 import os
 import subprocess
 import sys
@@ -26,12 +40,27 @@ FLOP_KEY = f"{SCENE}@{WIDTH}x{HEIGHT}/default"
 SM_COUNT, FP32_LANES = 148, 128
 
 
-def scene_bytes():
-    """The reference's scene file (staged by `make -C oracle ref`); falls back to a seeded cheese of our own making."""
-    path = os.path.join(ROOT, "oracle", "_ref", "scenes", SCENE + ".txt")
+def config_of(n_gpus):
+    """`config` of the JSON line — the same for both arms (the reference arm renders the same frame on the host cores)."""
+    return {"workload": WORKLOAD,
+            "parallelism": f"screen tiles 64x32 interleaved over {n_gpus} GPU(s), NVLink peer stores into rank 0" if n_gpus > 1
+                           else "1 GPU",
+            "l2": "256 MiB device memset between timed frames (L2 flush); inputs are 33 KB of tree + 68 B of camera/light"}
+
+
+def corpus_scene(name):
+    path = os.path.join(ROOT, "oracle", "_ref", "scenes", name + ".txt")
     if os.path.exists(path):
         with open(path, "rb") as f:
-            return f.read(), f"reference scene file Test/{SCENE}.txt (no randomness; no dataset or checkpoint involved)"
+            return f.read()
+    return None
+
+
+def scene_bytes():
+    """The reference's scene file (staged by `make -C oracle ref`); falls back to a seeded cheese of our own making."""
+    text = corpus_scene(SCENE)
+    if text is not None:
+        return text, f"reference scene file Test/{SCENE}.txt (no randomness; no dataset or checkpoint involved)"
     import random
     rnd = random.Random(512)
     leaves = [f"Sphere {rnd.uniform(-10, 10):.5f} {rnd.uniform(-10, 10):.5f} {rnd.uniform(-30, -10):.5f} F5F500 {rnd.uniform(0.01, 2):.5f}"
@@ -55,6 +84,25 @@ def cpu_model():
     except OSError:
         pass
     return "unknown"
+
+
+def host_threads():
+    """Host threads the CPU arms use: every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def source_hash():
+    """Hash of the kernel sources; profiles/ncu_summary.json records the one it was captured from."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "cuda-csg-tree-raycasting_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h", ".cpp")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -103,7 +151,77 @@ class ClockSampler:
         return {"sm_mhz": sm[(len(sm) * 3) // 4], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def dist_setup(n):
+class SharedHost:
+    """One host buffer all ranks of the node see: a /dev/shm file mapped by every rank and page-locked (cudaHostRegister) in
+    every rank, plus a few words for a spin barrier.  world == 1: plain pinned memory."""
+
+    def __init__(self, g, nbytes, rank, world, dist, tag, pin=True):
+        import numpy as np
+        import torch
+        self.g, self.pin = g, pin
+        self.rank, self.world, self.dist = rank, world, dist
+        self.nbytes = nbytes
+        self.gen = 0
+        self.path = None
+        if world == 1:
+            self.t = torch.empty(nbytes, dtype=torch.uint8)
+            if pin:
+                self.t = self.t.pin_memory()
+            self.arr = self.t.numpy()
+            self.ptr = self.t.data_ptr()
+            self.slots = None
+            return
+        self.path = f"/dev/shm/csg_b200_{os.environ.get('MASTER_PORT', '0')}_{tag}"
+        total = nbytes + 4096
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(total)
+        dist.barrier()
+        self.f = open(self.path, "r+b")
+        self.mm = mmap.mmap(self.f.fileno(), total)
+        whole = np.frombuffer(self.mm, dtype=np.uint8)
+        self.arr = whole[:nbytes]
+        self.slots = whole[nbytes:nbytes + 8 * world].view(np.int64)
+        if rank == 0:
+            whole[:] = 0          # touch every page before it is page-locked
+        dist.barrier()
+        self.ptr = self.arr.ctypes.data
+        if pin:
+            g.pin_host_buffer(self.ptr, nbytes)
+        dist.barrier()
+
+    def spin_barrier(self):
+        """All ranks leave within about a microsecond of each other (NCCL/gloo barriers release ranks tens of us apart)."""
+        if self.slots is None:
+            return
+        self.gen += 1
+        self.slots[self.rank] = self.gen
+        t0 = time.monotonic()
+        while int(self.slots.min()) < self.gen:
+            if time.monotonic() - t0 > 60:
+                raise RuntimeError("spin barrier timed out")
+
+    def close(self):
+        if self.path is None:
+            return
+        if self.pin:
+            self.g.unpin_host_buffer(self.ptr)
+        self.dist.barrier()
+        self.slots = None
+        self.arr = None
+        try:
+            self.mm.close()
+        except BufferError:
+            pass
+        self.f.close()
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def dist_setup():
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -115,12 +233,153 @@ def dist_setup(n):
     return rank, world, local
 
 
+class Job:
+    """One workload on this rank's GPU: sharded context (+ the NVLink gather target), cameras, light."""
+
+    def __init__(self, g, env, text, width, height, ss=1, optimize=1, cams=None):
+        self.g, self.env = g, env
+        self.text, self.width, self.height, self.ss = text, width, height, ss
+        self.nrays = width * height * ss * ss
+        self.scene = g.Scene.parse(text, optimize=optimize)
+        self.ctx = self.scene.upload_shard(width, height, env.local, env.rank, env.world)
+        if ss > 1:
+            self.ctx.set_supersampling(ss)
+        self.cams = cams or [g.Camera()]
+        self.light = g.Light()
+        if env.world > 1:   # gather target: rank 0's framebuffer (and its sync words), opened on the other ranks through CUDA IPC
+            box = [self.ctx.ipc_handle() if env.rank == 0 else None]
+            env.dist.broadcast_object_list(box, src=0)
+            if env.rank != 0:
+                self.ctx.set_gather_target_ipc(box[0])
+            env.dist.barrier()
+
+    def frame_device(self, k=0):
+        """One frame, device-resident; returns this rank's CUDA-event span (rank 0: the whole sharded frame)."""
+        self.ctx.enqueue(self.cams[k % len(self.cams)], self.light)
+        self.ctx.sync()
+        return self.ctx.last_frame_ms()
+
+    def time_device(self, steps, warmup):
+        env = self.env
+        for k in range(warmup):
+            env.flush.zero_()
+            env.barrier()
+            self.frame_device(k)
+        ms = []
+        env.barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            env.flush.zero_()
+            env.barrier()
+            ms.append(self.frame_device(k))
+        env.barrier()
+        wall = (time.perf_counter() - t0) * 1e3 / max(steps, 1)
+        return ms, wall
+
+    def single_gpu_frame(self, k=0):
+        """The same frame rendered by this rank's GPU alone (a separate single-GPU context): what the N-GPU frame must equal."""
+        import numpy as np
+        one = self.scene.upload_shard(self.width, self.height, self.env.local, 0, 1)
+        if self.ss > 1:
+            one.set_supersampling(self.ss)
+        one.enqueue(self.cams[k % len(self.cams)], self.light)
+        img = one.read_framebuffer(np.empty((self.height, self.width, 4), np.uint8))
+        one.close()
+        return img
+
+    def gathered_frame(self, k=0):
+        """The N-GPU frame as it sits in rank 0's framebuffer after one sharded frame."""
+        import numpy as np
+        self.env.barrier()
+        self.frame_device(k)
+        self.env.barrier()
+        if self.env.rank != 0:
+            return None
+        return self.ctx.read_framebuffer(np.empty((self.height, self.width, 4), np.uint8))
+
+    def close(self):
+        self.ctx.close()
+        self.scene.close()
+
+
+class Env:
+    pass
+
+
+def orbit_cameras(g, n=64, radius=5.0, pitch_deg=-20.0):
+    """camera k of n looks at the origin from `radius`; forward as Camera.cpp:10-12 computes it."""
+    import numpy as np
+    cams = []
+    for k in range(n):
+        pitch = float(np.float32(pitch_deg * math.pi / 180.0))
+        yaw = float(np.float32(2.0 * math.pi * k / n))
+        fwd = (-math.sin(yaw) * math.cos(pitch), math.sin(pitch), -math.cos(yaw) * math.cos(pitch))
+        cams.append(g.Camera(pos=tuple(-radius * f for f in fwd), pitch=pitch, yaw=yaw))
+    return cams
+
+
+def run_configs(g, env, args):
+    """Every BASELINE.json config at this N: a few steps each, device time as for the headline (root-side span), and the
+    gathered frame compared with the single-GPU frame."""
+    import numpy as np
+    import torch
+    out = {}
+    steps, warmup = 5, 3
+
+    def sharded(key, text, w, h, ss, what):
+        if text is None:
+            out[key] = {"skipped": "scene corpus not staged"}
+            return
+        job = Job(g, env, text, w, h, ss=ss)
+        ms, _ = job.time_device(steps, warmup)
+        got = job.gathered_frame()
+        rec = None
+        if env.rank == 0:
+            ref = job.single_gpu_frame()
+            t = float(np.mean(ms))
+            rec = {"what": what, "n_gpus": env.world, "ms_per_step": t, "rays_per_s": job.nrays / (t * 1e-3), "steps": steps,
+                   "mismatching_bytes_vs_1gpu": int((got != ref).sum())}
+        job.close()
+        if env.rank == 0:
+            out[key] = rec
+
+    sharded("configs[0]", corpus_scene("testWikipedia"), 1920, 1080, 1, "Test/testWikipedia.txt @ 1920x1080, default camera, 1 frame per step")
+    if env.world == 1:
+        # configs[1]: the 64-frame orbit on one GPU, through csg_render_batch (two pipelined frame slots), frames stay on the device
+        text = corpus_scene("testSphereCutByCubesAndCylinder")
+        if text is None:
+            out["configs[1]"] = {"skipped": "scene corpus not staged"}
+        else:
+            sc = g.Scene.parse(text)
+            ctx = sc.upload(WIDTH, HEIGHT)
+            cams = orbit_cameras(g)
+            dev = torch.empty(len(cams) * WIDTH * HEIGHT * 4, dtype=torch.uint8, device=env.dev)
+            light = g.Light()
+            ts = []
+            for k in range(2 + 3):
+                env.flush.zero_()
+                torch.cuda.synchronize()
+                ctx.render_batch(cams, light, dev.data_ptr())
+                if k >= 2:
+                    ts.append(ctx.last_frame_ms())
+            t = float(np.mean(ts))
+            out["configs[1]"] = {"what": "Test/testSphereCutByCubesAndCylinder.txt @ 3840x2160, 64-frame orbit (R=5, pitch -20 deg) per step, csg_render_batch, frames device-resident",
+                                 "n_gpus": 1, "ms_per_step": t, "ms_per_frame": t / len(cams), "rays_per_s": len(cams) * WIDTH * HEIGHT / (t * 1e-3), "steps": 3}
+            del dev
+            ctx.close()
+            sc.close()
+        sharded("configs[2]", corpus_scene("testCheese256"), WIDTH, HEIGHT, 1, "Test/testCheese256.txt @ 3840x2160, default camera, 1 frame per step")
+    sharded("configs[4]", g.Scene.generate_text(4096, seed=1234), 7680, 4320, 4,
+            "synthetic balanced tree, 4096 primitives (csg_generate_scene seed 1234) @ 7680x4320 x 16 rays/pixel, default camera")
+    return out
+
+
 def bench_ours(args):
     import numpy as np
     import torch
     import csg_b200 as g
 
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_setup()
     if world != args.gpus:
         if rank == 0:
             print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})"}))
@@ -131,95 +390,83 @@ def bench_ours(args):
     if world > 1:
         import torch.distributed as dist
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
 
-    text, data_note = scene_bytes()
-    scene = g.Scene.parse(text, optimize=args.optimize)
-    ctx = scene.upload_shard(WIDTH, HEIGHT, local, rank, world)
-    cam, light = g.Camera(), g.Light()
-    nrays = WIDTH * HEIGHT
-
-    # gather target: rank 0's framebuffer, opened on the other ranks through CUDA IPC (NVLink peer stores)
-    if world > 1:
-        box = [ctx.ipc_handle() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        if rank != 0:
-            ctx.set_gather_target_ipc(box[0])
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    env = Env()
+    env.rank, env.world, env.local, env.dist = rank, world, local, dist
+    env.dev = torch.device("cuda", local)
+    env.flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.dev)   # > 126 MB L2
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+    env.barrier = barrier
 
-    def frame_device():
-        ctx.enqueue(cam, light)
-        ctx.sync()
-        return ctx.last_frame_ms()
+    text, data_note = scene_bytes()
+    job = Job(g, env, text, WIDTH, HEIGHT, optimize=args.optimize)
+    ctx, cam, light = job.ctx, job.cams[0], job.light
+    nrays = WIDTH * HEIGHT
+    warmup = max(3, args.warmup)
 
-    # ---- warm-up (the clock sampler starts here: nvidia-smi needs a few hundred ms before its first sample)
+    # ---- warm-up (the clock sampler starts here: nvidia-smi needs a few hundred ms before its first sample), then the timed
+    # region: exactly K steps; per-step device time from CUDA events on the launching stream, L2 flushed between steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.5)
-    for _ in range(max(3, args.warmup)):
-        flush.zero_()
-        barrier()
-        frame_device()
-    barrier()
-
-    # ---- timed: exactly K steps; per-step device time from CUDA events on the launching stream, L2 flushed between steps
+    job.time_device(0, warmup)
     launches0 = ctx.launch_count()
-    step_ms = []
-    barrier()
-    t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        barrier()
-        step_ms.append(frame_device())
-    barrier()
-    t_wall1 = time.perf_counter()
+    step_ms, wall_ms = job.time_device(args.steps, 0)
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    ms = torch.tensor(step_ms, dtype=torch.float64, device=dev)
-    lc = torch.tensor([launches], dtype=torch.int64, device=dev)
+    ms = torch.tensor(step_ms, dtype=torch.float64, device=env.dev)
+    lc = torch.tensor([launches], dtype=torch.int64, device=env.dev)
+    ms_max = ms.clone()
     if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)    # a frame is done when the slowest shard is done
+        dist.broadcast(ms, src=0)                        # the root GPU's span covers every rank's work (device-side gate + join)
+        dist.all_reduce(ms_max, op=dist.ReduceOp.MAX)    # per-rank spans, for the record (a peer's includes its wait for the root's start)
         dist.all_reduce(lc, op=dist.ReduceOp.SUM)
     ms = ms.cpu().numpy()
     ms_per_step = float(ms.mean())
     value = nrays / (ms_per_step * 1e-3)
 
-    # ---- e2e: the synchronous public call with a HOST buffer: parameters H2D, kernel(s), framebuffer D2H into pinned memory
-    host_fb = torch.empty(nrays * 4, dtype=torch.uint8).pin_memory() if rank == 0 else None
+    # ---- e2e: the synchronous public call with a HOST buffer: parameters H2D, kernels, framebuffer D2H into page-locked memory
+    host = SharedHost(g, nrays * 4, rank, world, dist, "fb")
     e2e_steps = max(5, min(args.steps, 20))
 
     def frame_e2e():
-        if world == 1:
-            ctx.render(cam, light, host_fb.data_ptr())
-        else:
-            ctx.enqueue(cam, light)
-            ctx.sync()
-            dist.barrier()                      # all shards have landed in rank 0's framebuffer
-            if rank == 0:
-                ctx.read_framebuffer(host_fb.data_ptr())
+        host.spin_barrier()
+        t0 = time.monotonic_ns()
+        ctx.render(cam, light, host.ptr)
+        return t0, time.monotonic_ns()
     for _ in range(3):
         barrier()
         frame_e2e()
-    e2e_t = []
+    span = []
     for _ in range(e2e_steps):
-        flush.zero_()
+        env.flush.zero_()
         barrier()
-        t0 = time.perf_counter()
-        frame_e2e()
-        torch.cuda.synchronize()
-        e2e_t.append(time.perf_counter() - t0)
-    e2e = torch.tensor(e2e_t, dtype=torch.float64, device=dev)
+        span.append(frame_e2e())
+    t = torch.tensor(span, dtype=torch.int64, device=env.dev)            # [steps, 2]
+    t0s, t1s, own = t[:, 0].clone(), t[:, 1].clone(), (t[:, 1] - t[:, 0]).clone()
     if dist is not None:
-        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e.cpu().numpy().mean())
+        dist.all_reduce(t0s, op=dist.ReduceOp.MIN)
+        dist.all_reduce(t1s, op=dist.ReduceOp.MAX)
+        dist.all_reduce(own, op=dist.ReduceOp.MAX)
+    e2e_s = float((t1s - t0s).double().mean().item()) * 1e-9              # first rank's call -> last rank's return
+    e2e_own_s = float(own.double().mean().item()) * 1e-9                  # slowest rank's own call
+    barrier()
+    e2e_frame = host.arr.copy().reshape(HEIGHT, WIDTH, 4) if rank == 0 else None
+
+    # ---- parity of the N-GPU frames with the frame one GPU renders alone (outside the timed regions)
+    gathered = job.gathered_frame()
+    parity_n = None
+    if rank == 0:
+        ref = job.single_gpu_frame()
+        parity_n = {"n": world, "mismatching_bytes": int((gathered != ref).sum()), "e2e_mismatching_bytes": int((e2e_frame != ref).sum()),
+                    "bytes": int(ref.size), "hit_pixels": int((ref.reshape(-1, 4)[:, :3] != np.array([20, 20, 28], np.uint8)).any(axis=1).sum())}
+    host.close()
 
     # ---- extra (not the headline): the same frames with the opt-in view cache — an unchanged camera keeps its per-tile
     # trees, so the pruning kernel is skipped (the reference application's static camera with a moving light)
@@ -228,13 +475,17 @@ def bench_ours(args):
         ctx.set_view_cache(True)
         sv = []
         for k in range(13):
-            flush.zero_()
+            env.flush.zero_()
             barrier()
-            t = frame_device()
+            tt = job.frame_device()
             if k >= 3:
-                sv.append(t)
+                sv.append(tt)
         ctx.set_view_cache(False)
         static_ms = float(np.mean(sv))
+    info = ctx.info()
+    job.close()
+
+    configs = run_configs(g, env, args) if not args.no_configs else None
 
     if rank != 0:
         if dist is not None:
@@ -242,8 +493,11 @@ def bench_ours(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline (rank 0): FP32-bound path.  achieved = rays/s x algorithmic flop/ray of the REFERENCE
-    # algorithm (instrumented oracle, profiles/flop_per_ray.json); peak = FFMA-only probe measured now on this GPU.
+    # ---- roofline (rank 0).  The path is FP32 / instruction-issue bound, not HBM: `frac` is the FP32 work the
+    # frame kernel really executed (ncu count of the committed profile of this same command, at this run's frame time)
+    # against the FFMA-only probe measured now on this GPU; `issue_frac` is the kernel's issue-slot utilisation from the same
+    # profile.  The reference algorithm's flop count is a separate yard-stick (vs_reference_algorithm): the kernels skip ~98 %
+    # of that work, so it says how fast the frame is, not how busy the pipes are.
     fpr = None
     try:
         with open(os.path.join(ROOT, "profiles", "flop_per_ray.json")) as f:
@@ -253,24 +507,29 @@ def bench_ours(args):
     peak_measured = g.fp32_peak_tflops(local)
     sm_max = clocks.get("sm_max_mhz") or 1965.0
     peak_nominal = SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12
-    traffic, executed = None, None
+    traffic, executed, achieved, frac, issue_frac = None, None, None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
             prof = json.load(f)
         traffic = prof.get("dram_bytes_per_launch")
         fk = prof.get("frame_kernel")
         if fk:
-            # what the frame kernel actually issued (ncu capture of this same command, committed under profiles/): FP32 flop per
-            # frame, pipe and issue-slot utilisation.  The frame rate is this run's; the per-frame counts are the profile's.
-            exec_tflops = fk["executed_fp32_flop"] / (ms_per_step * 1e-3) / 1e12
+            matches = prof.get("source_hash") == source_hash()
+            # the frame kernel's own launch duration, measured live: with the view cache on a step is that one launch (static_ms)
+            kernel_ms = static_ms if world == 1 else None
+            share = kernel_ms / ms_per_step if kernel_ms else None
+            exec_tflops = fk["executed_fp32_flop"] / (kernel_ms * 1e-3) / 1e12 if kernel_ms else None
+            achieved = exec_tflops
+            frac = exec_tflops / peak_measured if (exec_tflops and peak_measured) else None
+            issue_frac = fk["issue_active_pct"] / 100.0
             executed = {"fp32_flop_per_frame": fk["executed_fp32_flop"], "fp32_flop_per_ray": fk["executed_fp32_flop"] / nrays,
-                        "achieved": exec_tflops, "frac": exec_tflops / peak_measured if peak_measured else None,
-                        "fma_pipe_pct": fk["fma_pipe_pct"], "alu_pipe_pct": fk["alu_pipe_pct"], "issue_active_pct": fk["issue_active_pct"],
-                        "warp_instructions_per_frame": fk["warp_instructions"], "source": "profiles/ncu_summary.json (" + prof.get("tag", "?") + ")"}
+                        "warp_instructions_per_frame": fk["warp_instructions"], "frame_kernel_us_in_profile": fk["us"],
+                        "frame_kernel_ms_live": kernel_ms, "frame_kernel_share_of_step": share, "fma_pipe_pct": fk["fma_pipe_pct"], "alu_pipe_pct": fk["alu_pipe_pct"],
+                        "issue_active_pct": fk["issue_active_pct"], "local_memory_instructions": (fk.get("local_load_instructions") or 0) + (fk.get("local_store_instructions") or 0),
+                        "source": "profiles/ncu_summary.json (" + prof.get("tag", "?") + ")",
+                        "profile_matches_source": matches, "source_hash": source_hash(), "profile_source_hash": prof.get("source_hash")}
     except Exception:
         pass
-    achieved = value * fpr / 1e12 if fpr else None
-    # the HBM view of the same frame, to show why it is not the bound: algorithmic bytes = the RGBA8 framebuffer (4 B/ray)
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -278,17 +537,19 @@ def bench_ours(args):
     except Exception:
         pass
     hbm_achieved = nrays * 4 / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_measured, "unit": "TFLOP/s",
-                "frac": (achieved / peak_measured) if achieved else None, "traffic": traffic,
-                "peak_source": "FFMA-only probe kernel measured in this run (csg_fp32_peak_tflops)",
-                "peak_nominal": peak_nominal, "flop_per_ray": fpr, "executed": executed,
+    ref_alg = value * fpr / 1e12 if fpr else None
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_measured, "unit": "TFLOP/s", "frac": frac, "issue_frac": issue_frac,
+                "traffic": traffic,
+                "peak_source": "FFMA-only probe kernel measured in this run (csg_fp32_peak_tflops)", "peak_nominal": peak_nominal,
+                "executed": executed,
+                "vs_reference_algorithm": {"flop_per_ray": fpr, "tflops_equivalent": ref_alg, "ratio_to_peak": (ref_alg / peak_measured) if ref_alg else None,
+                                           "note": "rays/s x the REFERENCE algorithm's algorithmic flop/ray (instrumented oracle, profiles/flop_per_ray.json): "
+                                                   "a speed-up-over-the-reference's-arithmetic figure, NOT a roofline fraction"},
                 "hbm": {"algorithmic_bytes_per_frame": nrays * 4, "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": hbm_achieved / hbm_peak, "peak_source": hbm_src,
                         "note": "4 B/ray of RGBA8 out is all the path has to move: a few per cent of HBM bandwidth, hence the FP32/issue roofline"},
-                "note": "achieved = rays/s x the REFERENCE algorithm's algorithmic flop/ray (fixed yard-stick, SURVEY.md 8d).  Our kernels skip "
-                        "almost all of that work (per-tile pruned trees, nearest-hit search, tighter boxes), so frac exceeds 1: it measures the "
-                        "frame against doing the reference's arithmetic at FP32 peak.  'executed' is what the frame kernel really issued: it is "
-                        "issue/latency-bound, not FP32-bound."}
+                "note": "frac = FP32 flop the frame kernel executed (fadd + fmul + 2 ffma thread instructions, ncu) / its duration / measured FFMA peak; "
+                        "the kernel is instruction-issue / latency bound (issue_frac), not FP32-pipe bound; N > 1: per-GPU figures are not derived"}
 
     # ---- baselines measured beside it (rank 0, N=1 only): the reference on the host cores and the reference CUDA kernel
     cpu_baseline = None
@@ -297,20 +558,21 @@ def bench_ours(args):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_py
         v = oracle_py.View(WIDTH, HEIGHT)
+        nt = host_threads()
         if oracle_py.have_ref_cpu():
             rc = oracle_py.RefCPU()
             step = 4
-            sec = rc.render(text, v, row_step=step, outputs=False)
+            sec = rc.render(text, v, row_step=step, nthreads=nt, outputs=False)
             rows = (HEIGHT + step - 1) // step
-            cpu_baseline = {"value": rows * WIDTH / sec, "unit": "rays/s", "cores": rc.max_threads(), "cpu_model": cpu_model(), "kind": "reference",
+            cpu_baseline = {"value": rows * WIDTH / sec, "unit": "rays/s", "cores": nt, "cpu_model": cpu_model(), "kind": "reference",
                             "sample": f"every {step}th scanline of the same frame ({rows} rows, {rows * WIDTH} rays, {sec:.2f} s); "
                                       "reference RaycastKernel+LightningKernel source compiled for the host, OpenMP dynamic over rows"}
         else:
             orc = oracle_py.Oracle()
             t0 = time.perf_counter()
-            fr = orc.render(text, v, rows=(HEIGHT // 2 - 64, HEIGHT // 2 + 64))
+            orc.render(text, v, rows=(HEIGHT // 2 - 64, HEIGHT // 2 + 64), nthreads=nt)
             sec = time.perf_counter() - t0
-            cpu_baseline = {"value": 128 * WIDTH / sec, "unit": "rays/s", "cores": os.cpu_count(), "cpu_model": cpu_model(), "kind": "port",
+            cpu_baseline = {"value": 128 * WIDTH / sec, "unit": "rays/s", "cores": nt, "cpu_model": cpu_model(), "kind": "port",
                             "sample": "128 centre scanlines, C oracle with OpenMP"}
         if oracle_py.have_ref_gpu():
             rg = oracle_py.RefGPU()
@@ -322,16 +584,19 @@ def bench_ours(args):
 
     out = {
         "metric": "primary rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": data_note,
-        "config": {"workload": WORKLOAD, "parallelism": f"screen tiles 64x32 interleaved over {world} GPU(s), NVLink peer stores into rank 0",
-                   "l2": "256 MiB device memset between timed frames (L2 flush); inputs are 33 KB of tree + 68 B of camera/light",
-                   "launches_per_frame": "2 per GPU: csg_prune_flat_kernel (per-tile pruned trees, rebuilt every frame) + csg_frame_kernel, "
-                                         "chained by programmatic dependent launch; both inside the timed region",
-                   "optimize": args.optimize, "launch": ctx.info()},
-        "e2e": {"value": nrays / e2e_s, "unit": "rays/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 256,
-                "d2h_bytes_per_step": nrays * 4, "steps": e2e_steps,
-                "what": "csg_render() with a pinned host RGBA8 buffer: camera/light as kernel parameters, the frame rendered in bands of tile rows (6 at 4K), each band copied D2H (33 MB in all, PCIe-bound) while the next one renders"},
+        "config": config_of(world),
+        "timing": {"what": "rank 0's CUDA events: frame started on the root GPU -> framebuffer complete on the root GPU; peers' kernels are gated on "
+                           "the root's start word and the root's last kernel joins every peer's done word (device-side, over NVLink)",
+                   "ms_per_step_min": float(ms.min()), "ms_per_step_max": float(ms.max()),
+                   "ms_per_step_max_over_ranks_own_spans": float(ms_max.cpu().numpy().mean()),
+                   "wall_ms_per_step_incl_flush_and_barriers": wall_ms},
+        "e2e": {"value": nrays / e2e_s, "unit": "rays/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 256 * world,
+                "d2h_bytes_per_step": nrays * 4, "steps": e2e_steps, "ms_per_step_slowest_rank_own_call": e2e_own_s * 1e3,
+                "what": "csg_render() into one page-locked host RGBA8 frame (N > 1: shared memory registered in every rank): camera/light as kernel "
+                        "parameters, the frame dealt out in rows of 64x32 tiles, every GPU renders its rows in bands and copies each band D2H over its "
+                        "own PCIe link while the next band renders; time = first rank's call -> last rank's return (CLOCK_MONOTONIC)"},
         "gpu_launches": int(lc.item()),
         "clocks": clocks,
         "roofline": roofline,
@@ -340,8 +605,11 @@ def bench_ours(args):
         "static_view": None if static_ms is None else {
             "ms_per_step": static_ms, "value": nrays / (static_ms * 1e-3), "unit": "rays/s",
             "what": "NOT the headline: csg_set_view_cache(1), camera unchanged between frames -> per-tile trees reused, 1 launch per frame"},
-        "ms_per_step_min": float(ms.min()), "ms_per_step_max": float(ms.max()),
-        "wall_ms_per_step_incl_flush": (t_wall1 - t_wall0) * 1e3 / args.steps,
+        "details": {"launches_per_frame": "2 per GPU: csg_prune_flat_kernel (per-tile pruned trees, rebuilt every frame) + csg_frame_kernel, "
+                                          "chained by programmatic dependent launch; both inside the timed region",
+                    "optimize": args.optimize, "launch": info},
+        "configs": configs,
+        "parity_n": parity_n,
     }
     print(json.dumps(out))
     if dist is not None:
@@ -352,7 +620,8 @@ def bench_ours(args):
 
 def bench_reference(args):
     """The reference's own CPU implementation of the path (oracle/_ref/libref_cpu.so: its RaycastKernel + LightningKernel
-    source compiled for the host, OpenMP over rows), all host threads, same config and metric.  Rank 0 only."""
+    source compiled for the host, OpenMP over rows) on every host core, same frame, same metric: W warm-up frames, then
+    exactly K full frames.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -360,36 +629,32 @@ def bench_reference(args):
     import oracle_py
     text, data_note = scene_bytes()
     v = oracle_py.View(WIDTH, HEIGHT)
-    step = 8   # bounded sample: every 8th scanline of the frame per step
-    rows = (HEIGHT + step - 1) // step
+    nt = host_threads()
     if oracle_py.have_ref_cpu():
         rc = oracle_py.RefCPU()
-        kind, cores = "reference", rc.max_threads()
-        run = lambda: rc.render(text, v, row_step=step, outputs=False)  # noqa: E731
+        kind = "reference"
+        run = lambda: rc.render(text, v, nthreads=nt, outputs=False)  # noqa: E731
     else:
         orc = oracle_py.Oracle()
-        kind, cores = "port", os.cpu_count()
-        rows = 128
+        kind = "port"
 
         def run():
             t0 = time.perf_counter()
-            orc.render(text, v, rows=(HEIGHT // 2 - 64, HEIGHT // 2 + 64), want_rgba=True)
+            orc.render(text, v, nthreads=nt, want_rgba=True)
             return time.perf_counter() - t0
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         run()
-    steps = max(1, min(args.steps, 5))
-    secs = [run() for _ in range(steps)]
+    secs = [run() for _ in range(args.steps)]
     sec = sum(secs) / len(secs)
-    value = rows * WIDTH / sec
-    sample = f"every {step}th scanline of the frame per step ({rows} rows, {rows * WIDTH} rays)"
+    value = WIDTH * HEIGHT / sec
     out = {"impl": "reference", "metric": "primary rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
-           "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3 * (HEIGHT / rows) if kind == "reference" else None,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_note,
-           "config": {"workload": WORKLOAD},
-           "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "cpu_model": cpu_model(), "kind": kind, "sample": sample},
+           "config": config_of(args.gpus),
+           "cpu_baseline": {"value": value, "unit": "rays/s", "cores": nt, "cpu_model": cpu_model(), "kind": kind,
+                            "sample": f"the whole frame, every step ({HEIGHT} rows, {WIDTH * HEIGHT} rays); OMP_NUM_THREADS ignored: num_threads({nt})"},
            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0,
-           "note": "ms_per_step is the sample time scaled to a full frame"}
+           "gpu_launches": 0}
     print(json.dumps(out))
     return 0
 
@@ -402,8 +667,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--optimize", type=int, default=1, help="load-time tree optimisation level (csg_scene_set_optimize)")
     ap.add_argument("--no-baselines", action="store_true", help="skip the CPU / reference-CUDA baselines")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configs")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.steps == 200 and args.warmup == 5:   # the defaults are sized for the GPU arm: a full CPU frame takes seconds
+            args.steps, args.warmup = 5, 1
         return bench_reference(args)
     return bench_ours(args)
 

@@ -27,6 +27,7 @@ EXPORTS = [
     "csg_launch_count", "csg_framebuffer", "csg_framebuffer_ipc_handle", "csg_set_gather_target_ipc",
     "csg_set_gather_target", "csg_read_framebuffer", "csg_device_tan_half_fov", "csg_fp32_peak_tflops", "csg_context_info",
     "csg_last_error", "csg_version", "csg_cube_normal_threshold", "csg_shard_tile",
+    "csg_pin_host_buffer", "csg_unpin_host_buffer", "csg_set_gather_root",
 ]
 
 
@@ -96,6 +97,9 @@ def _load():
         "csg_version": (C.c_char_p, []),
         "csg_cube_normal_threshold": (f, [f, f]),
         "csg_shard_tile": (i, [i] * 10 + [C.POINTER(i)] * 5),
+        "csg_pin_host_buffer": (i, [vp, C.c_size_t]),
+        "csg_unpin_host_buffer": (i, [vp]),
+        "csg_set_gather_root": (i, [vp, vp]),
     }
     for name in EXPORTS:
         fn = getattr(lib, name)  # AttributeError here = the library does not export what the header declares
@@ -137,6 +141,14 @@ def shard_tile(macro_x, macro_y, rect, mode, rank, count, tile):
         return None, None, None, nt.value, ns.value
     _check(rc)
     return mx.value, my.value, slot.value, nt.value, ns.value
+
+
+def pin_host_buffer(ptr, nbytes):
+    _check(lib.csg_pin_host_buffer(_ptr(ptr), nbytes))
+
+
+def unpin_host_buffer(ptr):
+    _check(lib.csg_unpin_host_buffer(_ptr(ptr)))
 
 
 def fp32_peak_tflops(device=0):
@@ -362,6 +374,9 @@ class Context:
     def set_gather_target_ipc(self, handle_bytes):
         buf = C.create_string_buffer(handle_bytes, 64)
         _check(lib.csg_set_gather_target_ipc(self.h, buf))
+
+    def set_gather_root(self, root_ctx):
+        _check(lib.csg_set_gather_root(self.h, root_ctx.h))
 
     def set_gather_target(self, dev_ptr):
         _check(lib.csg_set_gather_target(self.h, _ptr(dev_ptr)))

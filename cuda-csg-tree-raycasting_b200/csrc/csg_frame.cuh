@@ -309,7 +309,7 @@ __device__ __forceinline__ unsigned long long probe_now() { unsigned long long t
 template <int MODE, int kThreads, bool kSuper>   // kSuper: more than one ray per pixel (keeps the sample loop and its accumulators out of the common case)
 __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_kernel(const __grid_constant__ FrameParams p)
 {
-    // shared memory: [outcome table 128 B][stack: (levels+2) x kThreads x 16 B][per-warp tree copy: warp_tree_nodes x 32 B].
+    // shared memory: [outcome table 128 B][stack: (levels+2) x kThreads x 16 B][scratch frame: kThreads x 16 B][per-warp tree copy: warp_tree_nodes x 32 B].
     // Every 64x32-pixel macro tile has its own pruned, origin-relative tree (csg_prune_kernel), a few hundred bytes to a few
     // KB; a warp copies the tree of its current tile into shared memory when it fits, and reads it through L1 otherwise.
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -334,8 +334,10 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     gate_enter(p.gate);   // sharded frames: nothing of this frame happens before the root GPU has started it
     const uint32_t my_stack = (uint32_t)__cvta_generic_to_shared(s_stack + tid);   // frames are addressed in the shared window: 32-bit
     // per-warp copy of the current tile's tree (when it fits): traversal then reads shared memory instead of L1/L2
-    const uint32_t my_tree_off = 128u + 16u * (uint32_t)((p.stack_levels + 2) * kThreads + (tid >> 5) * (2 * p.warp_tree_nodes));   // bytes from smem_raw
+    const uint32_t my_tree_off = 128u + 16u * (uint32_t)((p.stack_levels + 3) * kThreads + (tid >> 5) * (2 * p.warp_tree_nodes));   // bytes from smem_raw
     const float* s_light = reinterpret_cast<const float*>(s_table + 28);
+    // supersampling: one more 16-byte frame per thread behind the traversal stack (colour accumulators)
+    const uint32_t my_scratch = my_stack + (uint32_t)((p.stack_levels + 2) * kThreads) * 16u;
 
     // per-frame constants of ray generation, RaycastKernel :11-16
     // Per-frame constants of ray generation (RaycastKernel :11-16) arrive precomputed in the parameter block (wm1 = w-1,
@@ -431,11 +433,15 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         pr_t0 = probe_now();
         const unsigned int pr_ticket = ticket;
 #endif
-        const unsigned int cur = ticket >> (sp - gp);
-        const int pass0 = (int)(ticket & ((1u << (sp - gp)) - 1u)) << gp;
+        const int ts = kSuper ? p.sp_tshift : 0;   // = sp - gp, precomputed: a plain parameter load is rematerialised, a difference kept alive across the tile spilled
+        const unsigned int cur = ticket >> ts;
+        const int pass0 = (int)(ticket & ((1u << ts) - 1u)) << gp;
         unsigned int next = 0;
         int req_lane = kSuper ? 0 : -1;   // lane that has asked for the next ticket (-1: nobody yet)
-        if (kSuper && lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+        if (kSuper) {   // requested up front; parked in the scratch frame (w) while the tile is traced, not in a register
+            if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+            sts128(my_scratch, make_uint4(0u, 0u, 0u, next));
+        }
         const int k = (int)(cur & 63u);
         // traced tiles are handed out heaviest first (order[] from the pruning kernel: tiles whose pruned tree is larger come
         // first, so that the expensive tiles are not the ones still running when the ticket counter runs dry); an entry carries
@@ -501,8 +507,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             tree = reinterpret_cast<const unsigned char*>(my_tree);
         }
 
+        int pass = pass0;   // pass0 is a multiple of 1 << gp: the ticket's passes end where the low gp bits wrap
 #pragma unroll 1
-        for (int pass = pass0; pass < pass0 + (1 << gp); ++pass) {
+        do {
             int x = tx0, y = ty0;   // this lane's pixel
             if (sp == 0) { x += lane & 7; y += lane >> 3; }
             else {   // 32 >> sp pixels of one row per pass, 1 << sp lanes per pixel
@@ -525,20 +532,38 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                 const float w = (float)(ss * ss);
                 accx = 0.08f * w; accy = 0.08f * w; accz = 0.11f * w;
             } else if (active) {
-                const int n_samples = sp ? 1 : ss * ss;
+                if (kSuper) {
+                    // More than one ray per pixel: the running colour sum lives in this thread's scratch frame in shared memory,
+                    // not in registers, while a sample is traced (the traversal needs every register of the 80 there are; three
+                    // accumulators and the sample counters across it were what spilled to local memory).
+                    sts128(my_scratch, make_uint4(0u, 0u, 0u, lds128(my_scratch).w));
+                    const int n_samples = sp ? 1 : ss * ss;
+                    const int sl = lane & ((1 << sp) - 1);   // sample-parallel: this lane's sample of the pixel
 #pragma unroll 1
-                for (int s = 0, sx = sp ? ((lane & ((1 << sp) - 1)) & (ss - 1)) : 0, sy = sp ? ((lane & ((1 << sp) - 1)) >> (sp >> 1)) : 0; s < n_samples; ++s) {
-                    const int vx = x * ss + sx, vy = y * ss + sy;
-                    if (++sx == ss) { sx = 0; ++sy; }
-                    if (kSuper) make_ray(vx, vy, r);
-                    else { r.dx = r0.dx; r.dy = r0.dy; r.dz = r0.dz; r.ix = r0.ix; r.iy = r0.iy; r.iz = r0.iz; }
+                    for (int s = 0; s < n_samples; ++s) {
+                        const int sy = sp ? (sl >> (sp >> 1)) : s / ss;
+                        const int sx = sp ? (sl & (ss - 1)) : s - sy * ss;
+                        make_ray(x * ss + sx, y * ss + sy, r);
+                        res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u,
+                                                        (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
+                        if (MODE != OUT_AOV) {
+                            const float4 c = shade_pixel(res, r, p.prims, p, s_light);
+                            const uint4 a = lds128(my_scratch);
+                            sts128(my_scratch, make_uint4(__float_as_uint(__uint_as_float(a.x) + c.x), __float_as_uint(__uint_as_float(a.y) + c.y),
+                                                          __float_as_uint(__uint_as_float(a.z) + c.z), a.w));
+                        }
+                    }
+                    const uint4 a = lds128(my_scratch);
+                    accx = __uint_as_float(a.x); accy = __uint_as_float(a.y); accz = __uint_as_float(a.z);
+                } else {
+                    r.dx = r0.dx; r.dy = r0.dy; r.dz = r0.dz; r.ix = r0.ix; r.iy = r0.iy; r.iz = r0.iz;
                     res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u,
                                                     (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
-                    if (!kSuper && lane == __ffs(amask) - 1)   // the tile is traced: ask for the next ticket now
+                    if (lane == __ffs(amask) - 1)   // the tile is traced: ask for the next ticket now
                         next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
                     if (MODE != OUT_AOV) {
                         const float4 c = shade_pixel(res, r, p.prims, p, s_light);
-                        accx += c.x; accy += c.y; accz += c.z;
+                        accx = c.x; accy = c.y; accz = c.z;
                     }
                 }
             }
@@ -556,10 +581,14 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                     // sum the pixel's samples in sample order (the order of the one-lane loop), in every lane of the pixel
                     const int base = lane & ~((1 << sp) - 1);
                     float sxr = 0.f, syr = 0.f, szr = 0.f;
-                    for (int s = 0; s < (1 << sp); ++s) {
-                        sxr += __shfl_sync(0xffffffffu, accx, base + s);
-                        syr += __shfl_sync(0xffffffffu, accy, base + s);
-                        szr += __shfl_sync(0xffffffffu, accz, base + s);
+#pragma unroll 1
+                    for (int s = 0; s < (1 << sp); s += 4) {   // 4 or 16 samples: whole groups of four, no remainder loop
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            sxr += __shfl_sync(0xffffffffu, accx, base + s + u);
+                            syr += __shfl_sync(0xffffffffu, accy, base + s + u);
+                            szr += __shfl_sync(0xffffffffu, accz, base + s + u);
+                        }
                     }
                     accx = sxr; accy = syr; accz = szr;
                 }
@@ -588,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                     }
                 }
             }
-        }
+        } while ((++pass & ((1 << gp) - 1)) != 0);
 #ifdef CSG_FRAME_PROBE
         { const unsigned long long d = probe_now() - pr_t0; ++pr_tiles; if (d > pr_longest) { pr_longest = d; pr_longest_ticket = pr_ticket; } }
 #endif
@@ -596,6 +625,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
             req_lane = 0;
         }
+        if (kSuper) next = lds128(my_scratch).w;
         ticket = __shfl_sync(0xffffffffu, next, req_lane);
     }
 #ifdef CSG_FRAME_PROBE

@@ -107,7 +107,8 @@ struct Shard {  // one GPU's share of the frame
     float4* d_prims = nullptr;
     unsigned int* d_counter = nullptr;
     unsigned int counter_base = 0;
-    float* d_tan = nullptr;
+    float* d_tan = nullptr;              // device alias of h_tan
+    float* h_tan = nullptr;              // page-locked, mapped: csg_tan_kernel writes tanf(fov/2) straight into host memory
     int grid = 0;
     int n_local_warp_tiles = 0;
     uint8_t* target = nullptr;   // where this shard writes RGBA8 (root framebuffer, possibly a peer pointer)
@@ -341,9 +342,25 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
         const char* g = std::getenv("CSG_B200_SS_GROUP");   // tuning aid
         if (g) fp.sp_group = std::min(std::max(std::atoi(g), 0), fp.sp_shift);
     }
-    fp.n_local_warp_tiles = (int)((mine * 64) << (fp.sp_shift - fp.sp_group));
+    fp.sp_tshift = fp.sp_shift - fp.sp_group;
+    fp.n_local_warp_tiles = (int)((mine * 64) << fp.sp_tshift);
     fp.rm_magic = (fp.rm_w > 1 && fp.rm_w < 4096 && traced < (1ll << 20)) ? (unsigned int)((1ull << 32) / (unsigned long long)fp.rm_w + 1ull) : 0u;
     if (fp.rm_w == 0) fp.rm_w = 1;   // never divide by zero; n_local_warp_tiles is 0 anyway
+}
+
+// tanf(fov / 2) as the device evaluates it.  The kernel writes into mapped page-locked host memory and only the context's own
+// stream is waited for: no copy engine and no device-wide synchronisation are involved, so this also works while another
+// shard's kernels of the same frame sit on the device waiting for this shard to start (the gate of sharded frames).
+int device_tan(csg_context* c, float fov, float* out)
+{
+    Shard& root = c->shards[0];
+    CU(cudaSetDevice(root.device));
+    csg_tan_kernel<<<1, 1, 0, root.stream>>>(fov, root.d_tan);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(root.stream));
+    *out = *reinterpret_cast<volatile float*>(root.h_tan);
+    c->launches++;
+    return CSG_OK;
 }
 
 // Enqueue one frame on every shard.  mode: OUT_RGBA8 -> out = rgba8 target (NULL: each shard's own target),
@@ -359,12 +376,10 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
     if (mode == OUT_AOV && c->ss != 1) return fail(CSG_ERR_ARG, "AOV output is per primary ray: set supersampling to 1");
     Shard& root = c->shards[0];
     CU(cudaSetDevice(root.device));
-    if (!(cam->fov == c->cached_fov)) {   // new field of view: one tiny launch + 4-byte readback, then cached
-        csg_tan_kernel<<<1, 1, 0, root.stream>>>(cam->fov, root.d_tan);
-        CU(cudaMemcpyAsync(&c->cached_tan, root.d_tan, sizeof(float), cudaMemcpyDeviceToHost, root.stream));
-        CU(cudaStreamSynchronize(root.stream));
+    if (!(cam->fov == c->cached_fov)) {   // new field of view: one tiny launch, then cached
+        int rc = device_tan(c, cam->fov, &c->cached_tan);
+        if (rc) return rc;
         c->cached_fov = cam->fov;
-        c->launches++;
     }
     // device-side start gate + join: frames whose shards all store into the root's framebuffer
     const bool joined = c->shard_count > 1 && shard_mode == 0 && mode == OUT_RGBA8 && c->shard_sync;
@@ -526,7 +541,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
 
     auto cleanup_fail = [&](int code) { const std::string keep = g_err; csg_free_context(c); g_err = keep; return code; };
 
-    // shared memory plan: [table 128 B][stack 16 B x (levels+2) x threads][tree 32 B/node]
+    // shared memory plan: [table 128 B][stack 16 B x (levels+3) x threads][tree 32 B/node]
     CUC(cudaSetDevice(devices[0]));
     int max_optin = 0, sms = 0;
     CUC(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, devices[0]));
@@ -565,7 +580,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         for (int i = 0; i < kShapes; ++i) {
             const int T = kShapeThreads[i];
             if (force_shape && std::atoi(force_shape) != T) continue;
-            const size_t base_need = (size_t)(c->stack_levels + 2) * T * sizeof(uint4) + table_bytes;   // +2: sentinel frame, search marker
+            const size_t base_need = (size_t)(c->stack_levels + 3) * T * sizeof(uint4) + table_bytes;   // +3: sentinel frame, search marker, scratch frame (supersampling)
             if (base_need > (size_t)max_optin) continue;
             const int ctas = (int)std::min<size_t>(min_blocks_for(T), sm_total / (base_need + 1024));
             const int warps = ctas * T / 32;
@@ -646,7 +661,8 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         const size_t prim_bytes = c->tree.prims.size() * sizeof(PrimRec);
         CUC(cudaMalloc(&s.d_prims, std::max<size_t>(prim_bytes, 80)));
         CUC(cudaMemcpy(s.d_prims, c->tree.prims.data(), prim_bytes, cudaMemcpyHostToDevice));
-        CUC(cudaMalloc(&s.d_tan, sizeof(float)));
+        CUC(cudaHostAlloc(&s.h_tan, sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
+        CUC(cudaHostGetDevicePointer(&s.d_tan, s.h_tan, 0));
         CUC(cudaMalloc(&s.d_counter, sizeof(unsigned int)));
         CUC(cudaMemset(s.d_counter, 0, sizeof(unsigned int)));
         CUC(cudaMalloc(&s.d_exit, sizeof(unsigned int)));
@@ -893,7 +909,7 @@ void csg_free_context(csg_context* c)
         cudaFree(s.d_order);
         cudaFree(s.d_prims);
         cudaFree(s.d_counter);
-        cudaFree(s.d_tan);
+        if (s.h_tan) cudaFreeHost(s.h_tan);
         if (s.ev_start) cudaEventDestroy(s.ev_start);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -972,6 +988,30 @@ int csg_set_gather_target_ipc(csg_context* ctx, const void* handle64)
     return CSG_OK;
 }
 
+int csg_set_gather_root(csg_context* ctx, csg_context* root)
+{
+    if (!ctx || !root) return fail(CSG_ERR_ARG, "null argument");
+    if (ctx->width != root->width || ctx->height != root->height || ctx->shard_count != root->shard_count)
+        return fail(CSG_ERR_ARG, "the root context must be a shard of the same frame");
+    const int root_dev = root->shards[0].device;
+    for (Shard& s : ctx->shards) {
+        CU(cudaSetDevice(s.device));
+        if (s.device != root_dev) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, s.device, root_dev));
+            if (!can) return fail(CSG_ERR_CUDA, "device " + std::to_string(s.device) + " cannot access device " + std::to_string(root_dev) + " (P2P)");
+            cudaError_t pe = cudaDeviceEnablePeerAccess(root_dev, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(CSG_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
+            cudaGetLastError();
+        }
+        s.target = root->d_fb;
+        s.sync_words = reinterpret_cast<SyncWords*>(root->d_fb + root->sync_off);
+    }
+    ctx->external_target = false;
+    ctx->shard_sync = true;
+    return CSG_OK;
+}
+
 int csg_set_gather_target(csg_context* ctx, uint8_t* rgba8_dev)
 {
     if (!ctx) return fail(CSG_ERR_ARG, "null context");
@@ -980,6 +1020,20 @@ int csg_set_gather_target(csg_context* ctx, uint8_t* rgba8_dev)
     // one process per GPU: a raw pointer says nothing about where the root keeps its SyncWords — such frames are neither gated
     // nor joined on the device (every rank has to be set up the same way; the caller synchronises the ranks itself)
     if (ctx->multi_process) ctx->shard_sync = rgba8_dev == nullptr;
+    return CSG_OK;
+}
+
+int csg_pin_host_buffer(void* host, size_t bytes)
+{
+    if (!host || !bytes) return fail(CSG_ERR_ARG, "null argument");
+    CU(cudaHostRegister(host, bytes, cudaHostRegisterPortable));
+    return CSG_OK;
+}
+
+int csg_unpin_host_buffer(void* host)
+{
+    if (!host) return fail(CSG_ERR_ARG, "null argument");
+    CU(cudaHostUnregister(host));
     return CSG_OK;
 }
 
@@ -1251,12 +1305,8 @@ int csg_set_supersampling(csg_context* ctx, int samples_per_axis)
 int csg_device_tan_half_fov(csg_context* ctx, float fov, float* out)
 {
     if (!ctx || !out) return fail(CSG_ERR_ARG, "null argument");
-    Shard& root = ctx->shards[0];
-    CU(cudaSetDevice(root.device));
-    csg_tan_kernel<<<1, 1, 0, root.stream>>>(fov, root.d_tan);
-    CU(cudaMemcpyAsync(out, root.d_tan, sizeof(float), cudaMemcpyDeviceToHost, root.stream));
-    CU(cudaStreamSynchronize(root.stream));
-    ctx->launches++;
+    int rc = device_tan(ctx, fov, out);
+    if (rc) return rc;
     return CSG_OK;
 }
 

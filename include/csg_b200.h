@@ -168,8 +168,20 @@ int csg_framebuffer_ipc_handle(csg_context* ctx, void* handle64);
  * complete (csg_sync / csg_last_frame_ms on rank 0) only when every rank's pixels have landed — all on the device, no host
  * round trip.  Every rank must enqueue every frame; a rank that waits more than 2 s for another fails with CSG_ERR_CUDA. */
 int csg_set_gather_target_ipc(csg_context* ctx, const void* handle64);
-/* Same, for a pointer that is already addressable from this context's device. */
+/* Same inside one process (e.g. one host thread per GPU, each with its own csg_upload_shard context): `root` is the rank-0
+ * context of the same frame; its framebuffer and sync words become this context's gather target.  (Shards of one frame on
+ * the SAME device — a testing set-up — must enqueue the root first: a peer's kernels wait on the device for the root to start
+ * and a full grid of them leaves the root no room.) */
+int csg_set_gather_root(csg_context* ctx, csg_context* root);
+/* Same, for a pointer that is already addressable from this context's device.  On a csg_upload_shard context such frames are
+ * neither gated nor joined on the device (a bare pointer carries no sync words): the caller synchronises the ranks. */
 int csg_set_gather_target(csg_context* ctx, uint8_t* rgba8_dev);
+
+/* Page-locks a host buffer for every GPU of the process (cudaHostRegisterPortable), so that csg_render's device -> host
+ * copies run at PCIe speed and overlap with rendering; works on memory the caller allocated any way it likes, including a
+ * shared-memory mapping that several one-process-per-GPU ranks render into.  Undo with csg_unpin_host_buffer before freeing. */
+int csg_pin_host_buffer(void* host, size_t bytes);
+int csg_unpin_host_buffer(void* host);
 
 /* Copies `bytes` from the framebuffer to a host buffer (synchronous). */
 int csg_read_framebuffer(csg_context* ctx, uint8_t* rgba8_host);

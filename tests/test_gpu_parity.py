@@ -195,26 +195,6 @@ def test_supersampling_is_reference_at_k_times_resolution_box_filtered(k, csg, o
         ctx.close()
 
 
-def test_multi_gpu_in_process_equals_single_gpu(csg):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    if "testCheese512" not in scenes.corpus_names():
-        pytest.skip("scene corpus not staged")
-    txt = scenes.text_of("corpus:testCheese512")
-    cam, light = csg.Camera(), csg.Light()
-    sc = csg.Scene.parse(txt)
-    one = sc.upload(1920, 1080, 1)
-    a = one.render(cam, light).copy()
-    one.close()
-    n = min(torch.cuda.device_count(), 8)
-    for k in sorted({2, n}):
-        many = sc.upload(1920, 1080, k)
-        b = many.render(cam, light).copy()
-        assert np.array_equal(a, b), f"{k}-GPU frame differs from the 1-GPU frame"
-        many.close()
-
-
 def test_deep_tree_limit_is_an_error_not_a_crash(csg):
     depth = 400
     txt = "Union\n" * depth + "Sphere 0 0 0 FF0000 1\n" + "".join(f"Sphere {i * 0.01} 0 0 00FF00 1\n" for i in range(depth))

@@ -151,21 +151,32 @@ GLOO_WORKER = r'''
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
 from oracle_py import Oracle, View
+import csg_b200 as g
+import bench
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-# Host-side model of the multi-rank frame: each rank renders only the 64x32 macro tiles it owns (with the oracle
-# standing in for the kernel), "stores" them into rank 0's framebuffer (gloo gather), and the result must equal
-# the single-rank frame bit for bit.
+# Host-side model of the multi-rank frame, with the oracle standing in for the kernels and the library's own tile hand-out
+# (csg_shard_tile = what the kernels compile):
+#   tiles: each rank renders the 64x32 macro tiles it is dealt and "stores" them into rank 0's framebuffer (gloo gather);
+#   rows : each rank renders the tile rows it is dealt and writes them into ONE shared host frame (bench.SharedHost, the
+#          /dev/shm buffer + spin barrier bench.py's N > 1 end-to-end leg uses; not page-locked here).
+# Either way the result must equal the single-rank frame byte for byte.
 W, H = 200, 100
 txt = "Difference\n Cube 0 0 0 FF0000 2\n Union\n  Sphere 1 1 1 00FF00 0.8\n  Cylinder 0 0 0 0000FF 0.5 3 0 0 0\n"
 orc = Oracle()
 full = orc.render(txt, View(W, H, pos=(1.5, 1.0, 4.0), pitch=-0.2, yaw=0.3))
 rgba = full.rgba8().reshape(H, W, 4)
 mx, my = (W + 63) // 64, (H + 31) // 32
+rect = (0, 0, mx, my)
+
+def my_tiles(mode):
+    n = g.shard_tile(mx, my, rect, mode, rank, world, -1)[3]
+    return [g.shard_tile(mx, my, rect, mode, rank, world, t)[:2] for t in range(n)]
+
 mine = np.zeros((H, W, 4), np.uint8)
 mask = np.zeros((H, W), np.uint8)
-for m in range(rank, mx * my, world):
-    x0, y0 = (m % mx) * 64, (m // mx) * 32
+for (tx, ty) in my_tiles(0):
+    x0, y0 = tx * 64, ty * 32
     mine[y0:y0 + 32, x0:x0 + 64] = rgba[y0:y0 + 32, x0:x0 + 64]
     mask[y0:y0 + 32, x0:x0 + 64] += 1
 parts = [torch.zeros(H, W, 4, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
@@ -177,6 +188,24 @@ if rank == 0:
     assert (cover == 1).all(), "tiles must partition the frame"
     fb = sum(p.numpy().astype(int) for p in parts).astype(np.uint8)
     assert np.array_equal(fb, rgba)
+
+host = bench.SharedHost(g, W * H * 4, rank, world, dist, "gloo_test", pin=False)
+frame = host.arr.reshape(H, W, 4)
+for step in range(3):
+    host.spin_barrier()
+    for (tx, ty) in my_tiles(1):
+        assert ty % world == rank
+        x0, y0 = tx * 64, ty * 32
+        frame[y0:y0 + 32, x0:x0 + 64] = rgba[y0:y0 + 32, x0:x0 + 64]
+    host.spin_barrier()
+    if rank == 0:
+        assert np.array_equal(frame, rgba), "rows must partition the frame"
+    host.spin_barrier()
+    if rank == 0:
+        frame[:] = 0
+frame = None
+host.close()
+if rank == 0:
     print("GLOO_OK")
 dist.barrier()
 dist.destroy_process_group()
@@ -271,9 +300,10 @@ def test_bench_ours_refuses_to_run_without_a_gpu():
     assert "no CUDA device" in (r.stdout + r.stderr)
 
 
-def test_sass_has_no_local_memory_in_the_one_ray_per_pixel_kernels(csg):
-    """The traversal stack lives in shared memory and nothing spills: no LDL/STL in the SASS of the one-ray-per-pixel frame
-    kernels (all three CTA shapes, all output modes) nor in the pruning kernels; everything is built for sm_100a."""
+def test_sass_has_no_local_memory_in_any_kernel(csg):
+    """The traversal stack lives in shared memory and nothing spills: no LDL/STL in the SASS of any of the 18 frame kernel
+    instantiations (three CTA shapes x three output modes x {one ray per pixel, supersampling}) nor in the pruning kernels;
+    everything is built for sm_100a."""
     import shutil
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not on PATH")
@@ -293,9 +323,8 @@ def test_sass_has_no_local_memory_in_the_one_ray_per_pixel_kernels(csg):
             per_fn[fn][1] += 1
     frame = {f: v for f, v in per_fn.items() if "csg_frame_kernel" in f}
     assert len(frame) == 18                                            # 3 output modes x 3 CTA shapes x {1 ray, supersampling}
-    one_ray = {f: v for f, v in frame.items() if "ELb0E" in f}
-    assert len(one_ray) == 9
-    for f, (local_ops, n) in one_ray.items():
+    assert len([f for f in frame if "ELb0E" in f]) == 9 and len([f for f in frame if "ELb1E" in f]) == 9
+    for f, (local_ops, n) in frame.items():
         assert local_ops == 0, f"{f}: {local_ops} local-memory instructions"
         assert n > 1000
     prune = {f: v for f, v in per_fn.items() if "csg_prune" in f}
