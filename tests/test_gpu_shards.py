@@ -108,7 +108,7 @@ def test_device_side_gate_and_join_between_two_shards(peer_first, csg):
     Peer first only on small frames: a waiting frame kernel of 148 CTAs holds every SM's register file, so on ONE device the
     root's kernels could never start (on its own GPU a peer waits alone)."""
     light = csg.Light()
-    for scene_id, w, h, v in (cases()[:2] if peer_first else cases()[:3]):
+    for scene_id, w, h, v in (cases()[:1] if peer_first else cases()[:3]):   # 257x129: 35 frame CTAs
         sc = csg.Scene.parse(scenes.text_of(scene_id))
         cam = cam_of(csg, v)
         want = single(csg, sc, w, h, cam, light)
