@@ -20,7 +20,8 @@ __device__ __forceinline__ void stage_record(const uint4 ua, const uint4 ub, flo
 {
     float4 a = as_float4(ua), b = as_float4(ub);
     if ((ub.w & 7u) == 3u) {
-        a.x = __fsub_rn(ox, a.x); a.y = __fsub_rn(oy, a.y); a.z = __fsub_rn(oz, a.z);
+        a.x = __fsub_rn(ox, a.x); a.y = __fsub_rn(oy, a.y); a.z = __fsub_rn(oz, a.z);   // sphereHit :139-143
+        a.w = __fmaf_rn(a.w, a.w, -dot_ref(a.x, a.y, a.z, a.x, a.y, a.z));              // :146, r*r - dot(oc,oc): FFMA r,r,-dot in the reference's SASS
     } else {
         a.x = __fsub_rn(a.x, ox); a.y = __fsub_rn(a.y, oy); a.z = __fsub_rn(a.z, oz);
         a.w = __fsub_rn(a.w, ox); b.x = __fsub_rn(b.x, oy); b.y = __fsub_rn(b.y, oz);

@@ -30,7 +30,7 @@ static_assert(sizeof(RefNode) == 44 && sizeof(RefPrim) == 48, "reference layouts
 //   word 7 (all kinds)   kind | leftIsLeaf<<3 | rightIsLeaf<<4 | bounded<<5 | pure<<6 | idx<<8   idx = right child (operator) / primitive id (leaf)
 //                        bounded = no cylinder below: the culling box really bounds every hit of the subtree (allows pruning)
 //   operator   w0..5 = culling box (min xyz, max xyz),  w6 = parent node (-1 at the root)
-//   sphere     w0..2 = centre, w3 = radius, w4..6 = centre again (the kernel turns w0..2 into origin-centre while staging)
+//   sphere     w0..2 = centre, w3 = radius, w4..6 = centre again (staging turns w0..2 into origin-centre and w3 into r*r - |origin-centre|^2)
 //   cube       w0..5 = lb, rt  (centre -/+ size/2, rounded like the reference rounds them)
 //   cylinder   w0..5 = the reference's own leaf box (centre -/+ max(h/2, r)), which gates the primitive (Q6)
 struct NodeRec {

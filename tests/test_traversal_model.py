@@ -116,6 +116,10 @@ class Model:
     def enter_hook(self, n, d, tmin):
         return None
 
+    def leaf_like(self, parent_meta, bit, child):
+        """Compute re-evaluates this operand on the spot when it loops into it (kMetaLeftLeaf / kMetaRightLeaf)."""
+        return bool(parent_meta & bit)
+
     # ---- traverse(), csrc/csg_frame.cuh
     def traverse(self, direction):
         d = (C.c_float * 3)(*direction)
@@ -160,11 +164,19 @@ class Model:
                     if st != ST_LOOPL:
                         b, goB, tnB, mB = self.eval_child(cr, d, dd, tmin, st <= ST_SEARCH)
                     if st == ST_LOOPL:
-                        L = a
-                        st = ST_COMPUTE
+                        if goA:                           # a flat subtree that gave up: descend into it like into any operator
+                            stack.append(("load_r", R.copy(), n))
+                            n, st = cl, ST_ENTER
+                        else:
+                            L = a
+                            st = ST_COMPUTE
                     elif st == ST_LOOPR:
-                        R = b
-                        st = ST_COMPUTE
+                        if goB:
+                            stack.append(("load_l", L.copy(), n))
+                            n, st = cr, ST_ENTER
+                        else:
+                            R = b
+                            st = ST_COMPUTE
                     elif st == ST_SEARCH:
                         abort = False
                         for h in (a, b):
@@ -251,14 +263,14 @@ class Model:
                     st = ST_RETURN
                 elif o == O_LOOPL:
                     tmin = L.t
-                    if m & LEFT_LEAF:
+                    if self.leaf_like(m, LEFT_LEAF, n + 1):
                         st = ST_LOOPL
                     else:
                         stack.append(("load_r", R.copy(), n))
                         n, st = n + 1, ST_ENTER
                 elif o == O_LOOPR:
                     tmin = R.t
-                    if m & RIGHT_LEAF:
+                    if self.leaf_like(m, RIGHT_LEAF, m >> 8):
                         st = ST_LOOPR
                     else:
                         stack.append(("load_l", L.copy(), n))
@@ -595,3 +607,208 @@ def test_prototype_interval_evaluation_of_pure_subtrees_equals_the_reference_mac
                 tests_old += plain.leaf_tests
     print(f"\n{scene_id}: {checked} rays, {shortcuts} interval evaluations, {gave_up} given up; primitive tests {tests_old} -> {tests_new}")
     assert checked > 200
+
+
+# ---- PROTOTYPE (measured on the GPU and rejected): flat evaluation of small sphere-only union subtrees -----------
+# A pure subtree of at most FLAT_MAX_LEAVES spheres treated as ONE operand: its result at tmin is worked out from the
+# spheres' roots alone, in passes over the leaves, no tree walk and no stack (the interval semantics of the prototype above, but
+# nothing is re-tested through the machine):
+#   every sphere the ray meets has a near root t1 and a far root t2 (sphereHit's own values);
+#   t1 > tmin: an Enter ahead.  Without a run it is a candidate for the nearest Enter; with a run that reaches beyond it, it is
+#              part of the run and its far root extends the run;
+#   t1 <= tmin < t2: tmin is inside this sphere: its far root starts / extends the run;
+#   passes repeat until the run stops growing.  No run: the nearest Enter (or Miss).  Run: the Exit that ends it.
+# It gives up — and the subtree is evaluated by the frame machine as before — on every exact tie that involves the run's end or
+# the nearest Enter, and on every abnormal classification (a near root that is not an Enter, a far root that is not an Exit).
+# RESULT: exact (the test below: Cheese256/512, sphere chains, duplicated spheres — bit-identical to the reference machine, the
+# tie cases give up as intended), and on the B200 also bit-identical over all GPU tests — but SLOWER than the tree machine: a warp
+# runs a sphere's full path as soon as one of its 32 rays meets it, so a pass costs ~k x the full test, while the machine's box
+# culling and the search's limit touch 2-3 spheres per ray (Cheese512 @ 4K frame kernel: 0.155 ms -> 0.164 ms with every flat
+# subtree evaluated this way, 0.172 ms when only subtrees entered with tmin inside them are).  Kept as a record of the semantics.
+FLAT_MAX_LEAVES = 24
+GIVE_UP = "give up"
+
+
+class FlatModel(TileModel):
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        n = len(self.meta)
+        self.end = [0] * n
+        self.flat = [False] * n
+        self.flat_evals = self.gave_up = self.passes = 0
+        cnt = [0] * n
+        spheres = [False] * n
+
+        def walk(i):
+            m = int(self.meta[i])
+            if (m & 7) >= 3:
+                self.end[i], cnt[i], spheres[i] = i + 1, 1, (m & 7) == K_SPHERE
+            else:
+                a, b = i + 1, m >> 8
+                walk(a)
+                self.end[i] = walk(b)
+                cnt[i] = cnt[a] + cnt[b]
+                spheres[i] = spheres[a] and spheres[b] and (m & 7) == K_UNION
+                self.flat[i] = spheres[i] and cnt[i] <= FLAT_MAX_LEAVES
+            return self.end[i]
+        walk(0)
+
+    def leaf_like(self, parent_meta, bit, child):
+        return bool(parent_meta & bit) or self.flat[child]
+
+    def traverse(self, direction):
+        if (int(self.meta[0]) & 7) < 3 and self.flat[0]:      # the whole (tile) tree is one flat union (kTileRootFlat)
+            res = self.flat_eval(0, (C.c_float * 3)(*direction), 0.0)
+            if res is not GIVE_UP:
+                return res
+        return super().traverse(direction)
+
+    def eval_child(self, c, d, dd, tmin, gated):
+        m = int(self.meta[c])
+        if (m & 7) < 3 and self.flat[c]:
+            go, _ = self.box(c, dd, tmin)
+            if not go:
+                return Hit(), False, -INF, m
+            res = self.flat_eval(c, d, tmin)
+            if res is GIVE_UP:
+                return Hit(), True, -INF, m           # descend: the frame machine evaluates it
+            return res, False, -INF, m
+        return super().eval_child(c, d, dd, tmin, gated)
+
+    def flat_eval(self, root, d, tmin):
+        self.flat_evals += 1
+        leaves = [c for c in range(root + 1, self.end[root]) if (int(self.meta[c]) & 7) >= 3]
+        have_run, run, run_id = False, 0.0, -1
+        tE, hE, tieE = INF, None, False
+        first_pass = True
+        while True:
+            self.passes += 1
+            grew = False
+            for c in leaves:
+                near = self.leaf(c, d, -INF, True)       # t1 (and its class); a miss here = the ray misses the sphere
+                if near.miss:
+                    continue
+                t1 = near.t
+                if not (t1 <= tmin):                      # sphereHit :152: the near root is the hit
+                    if near.cls != ENTER or t1 != t1:
+                        self.gave_up += 1
+                        return GIVE_UP
+                    if first_pass:
+                        if t1 < tE:
+                            tE, hE, tieE = t1, near, False
+                        elif t1 == tE:
+                            tieE = True
+                    if have_run:
+                        if t1 == run:
+                            self.gave_up += 1
+                            return GIVE_UP
+                        if t1 < run:
+                            far = self.leaf(c, d, t1, True)
+                            if far.cls != EXIT or (far.t == run and far.prim != run_id):
+                                self.gave_up += 1
+                                return GIVE_UP
+                            if far.t > run:
+                                run, run_id, grew = far.t, far.prim, True
+                else:
+                    far = self.leaf(c, d, tmin, True)    # :153: the far root, if it is beyond tmin
+                    if far.miss:
+                        continue
+                    if far.cls != EXIT:
+                        self.gave_up += 1
+                        return GIVE_UP
+                    if not have_run:
+                        have_run, run, run_id, grew = True, far.t, far.prim, True
+                    elif far.t == run:
+                        if far.prim != run_id:
+                            self.gave_up += 1
+                            return GIVE_UP
+                    elif far.t > run:
+                        run, run_id, grew = far.t, far.prim, True
+            first_pass = False
+            if not have_run or not grew:
+                break
+        if not have_run:
+            if tieE:
+                self.gave_up += 1
+                return GIVE_UP
+            return hE.copy() if hE is not None else Hit()
+        return Hit(run, EXIT, run_id)
+
+
+def sphere_chain_scene(seed, n):
+    """Difference(cube, union of n overlapping spheres along and around the view axis): long tunnels, many run extensions."""
+    import random
+    rnd = random.Random(seed)
+    leaves = [f"Sphere {rnd.uniform(-1.2, 1.2):.4f} {rnd.uniform(-1.2, 1.2):.4f} {rnd.uniform(-3.0, 3.0):.4f} 30A0F0 {rnd.uniform(0.3, 0.9):.4f}"
+              for _ in range(n)]
+
+    def union(xs):
+        if len(xs) == 1:
+            return xs[0]
+        h = len(xs) // 2
+        return "Union\n" + union(xs[:h]) + "\n" + union(xs[h:])
+    return "Difference\nCube 0 0 0 FFD000 5\n" + union(leaves) + "\n"
+
+
+FLAT_SCENES = ["corpus:testCheese256", "corpus:testCheese512", "synthetic:200", "inline:deep_left_chain", "inline:duplicate_spheres",
+               "inline:two_spheres_union", "chain:1:20", "chain:2:40", "dupchain"]
+
+
+@pytest.mark.parametrize("scene_id", FLAT_SCENES)
+def test_flat_evaluation_of_small_sphere_unions_equals_the_reference_machine(scene_id, csg, oracle):
+    if scene_id.startswith("corpus:") and scene_id[7:] not in scenes.corpus_names():
+        pytest.skip("scene corpus not staged")
+    if scene_id.startswith("synthetic:"):
+        txt = csg.Scene.generate_text(200, seed=13)
+    elif scene_id.startswith("chain:"):
+        _, seed, n = scene_id.split(":")
+        txt = sphere_chain_scene(int(seed), int(n)).encode()
+    elif scene_id == "dupchain":
+        # duplicated and concentric spheres inside a chain: exact ties between roots of different primitives
+        txt = ("Difference\nCube 0 0 0 FFD000 5\nUnion\nUnion\nSphere 0 0 2 FF0000 0.8\nSphere 0 0 2 00FF00 0.8\nUnion\nUnion\n"
+               "Sphere 0 0 1 0000FF 0.8\nSphere 0 0 1 0000FF 0.5\nUnion\nSphere 0.1 0 0.2 FF00FF 0.8\nSphere 0.1 0 0.2 FFFF00 0.8\n").encode()
+    else:
+        txt = scenes.text_of(scene_id)
+    # dupchain: ties everywhere, and with ties the re-balanced tree (optimize = 1) is not the reference's tree (DESIGN 4.3.6)
+    sc = csg.Scene.parse(txt, optimize=0 if scene_id == "dupchain" else 1)
+    rec, _, _ = sc.flatten()
+    _, prims48 = sc.dump()
+    sc.close()
+    rec = rec.reshape(-1, 8)
+    prims48 = np.asarray(prims48).reshape(-1, 48)
+    w, h, tw, th = 256, 144, 32, 16
+    if "Cheese" in scene_id:
+        views = [View(w, h), View(w, h, pos=(0.5, 1.0, -19.0), pitch=0.3, yaw=2.0)]
+    elif scene_id.startswith("synthetic:"):
+        views = [View(w, h, pos=(0.0, 0.0, 5.0))]
+    elif scene_id.startswith("chain:") or scene_id == "dupchain":
+        views = [View(w, h, pos=(0.0, 0.0, 6.0)), View(w, h, pos=(0.3, 0.2, 1.0), pitch=0.1, yaw=0.2), orbit_view(w, h, 7, radius=6.0)]
+    else:
+        views = [View(w, h), orbit_view(w, h, 5, radius=4.0)]
+    evals = gave_up = passes = checked = 0
+    for v in views:
+        ref = oracle.render(txt, v, want_rgba=False)
+        rh, rp, rt = ref.hit.reshape(h, w), ref.prim.reshape(h, w), ref.t.reshape(h, w)
+        cam = oracle.camera(v)
+        tan_half = float(np.tan(np.float32(cam.fov) * np.float32(0.5)))
+        out3 = (C.c_float * 3)()
+        for ty in range(0, h, th):
+            for tx in range(0, w, tw):
+                tree = pruned_tile_tree(rec, v, cam, tan_half, tx, ty, tx + tw, ty + th)
+                if tree is None:
+                    continue
+                model = FlatModel(oracle, tree, prims48, v.pos)
+                for y in range(ty + 1, ty + th, 4):
+                    for x in range(tx + 1, tx + tw, 4):
+                        oracle.lib.orc_raygen(C.byref(cam), w, h, x, y, C.c_float(tan_half), out3)
+                        got = model.traverse((float(out3[0]), float(out3[1]), float(out3[2])))
+                        assert (not got.miss) == bool(rh[y, x]), f"{scene_id} pixel ({x},{y})"
+                        if rh[y, x]:
+                            assert got.prim == int(rp[y, x]) and np.float32(got.t).view(np.uint32) == rt[y, x].view(np.uint32), f"{scene_id} pixel ({x},{y})"
+                        checked += 1
+                evals += model.flat_evals
+                gave_up += model.gave_up
+                passes += model.passes
+    print(f"\n{scene_id}: {checked} rays, {evals} flat evaluations, {passes} passes, {gave_up} given up")
+    assert checked > 200
+    assert evals > 0
