@@ -105,6 +105,34 @@ def source_hash():
     return h.hexdigest()[:16]
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this rank on the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI device), so that the host pages it
+    first-touches — its rows of the shared host frame — and its launch thread sit on the GPU's own socket."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        with open(path) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus of {path}"
+    except Exception as e:   # no sysfs / no permission: stay where we are
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -155,7 +183,7 @@ class SharedHost:
     """One host buffer all ranks of the node see: a /dev/shm file mapped by every rank and page-locked (cudaHostRegister) in
     every rank, plus a few words for a spin barrier.  world == 1: plain pinned memory."""
 
-    def __init__(self, g, nbytes, rank, world, dist, tag, pin=True):
+    def __init__(self, g, nbytes, rank, world, dist, tag, pin=True, first_touch=None):
         import numpy as np
         import torch
         self.g, self.pin = g, pin
@@ -182,8 +210,14 @@ class SharedHost:
         whole = np.frombuffer(self.mm, dtype=np.uint8)
         self.arr = whole[:nbytes]
         self.slots = whole[nbytes:nbytes + 8 * world].view(np.int64)
-        if rank == 0:
-            whole[:] = 0          # touch every page before it is page-locked
+        # touch every page before it is page-locked: first_touch(rank, array) lets every rank touch the part it will write
+        # (its rows of the frame), so that those pages land on its own NUMA node; default: rank 0 touches everything
+        if first_touch is not None:
+            first_touch(rank, self.arr)
+            if rank == 0:
+                whole[nbytes:] = 0
+        elif rank == 0:
+            whole[:] = 0
         dist.barrier()
         self.ptr = self.arr.ctypes.data
         if pin:
@@ -253,25 +287,33 @@ class Job:
                 self.ctx.set_gather_target_ipc(box[0])
             env.dist.barrier()
 
-    def frame_device(self, k=0):
-        """One frame, device-resident; returns this rank's CUDA-event span (rank 0: the whole sharded frame)."""
+    def frame_device(self, k=0, prequeued=False):
+        """One frame, device-resident; returns this rank's CUDA-event span (rank 0: the whole sharded frame).
+        prequeued (a diagnostic, not the headline): the peers enqueue first — their kernels wait on the device for the root's
+        start word — and the root enqueues once they have: the root's span is then free of host-side launch skew."""
+        env = self.env
+        env.spin()
+        if prequeued and env.rank == 0:
+            env.spin()
         self.ctx.enqueue(self.cams[k % len(self.cams)], self.light)
+        if prequeued and env.rank != 0:
+            env.spin()
         self.ctx.sync()
         return self.ctx.last_frame_ms()
 
-    def time_device(self, steps, warmup):
+    def time_device(self, steps, warmup, prequeued=False):
         env = self.env
         for k in range(warmup):
             env.flush.zero_()
             env.barrier()
-            self.frame_device(k)
+            self.frame_device(k, prequeued)
         ms = []
         env.barrier()
         t0 = time.perf_counter()
         for k in range(steps):
             env.flush.zero_()
             env.barrier()
-            ms.append(self.frame_device(k))
+            ms.append(self.frame_device(k, prequeued))
         env.barrier()
         wall = (time.perf_counter() - t0) * 1e3 / max(steps, 1)
         return ms, wall
@@ -391,6 +433,7 @@ def bench_ours(args):
         import torch.distributed as dist
     torch.cuda.set_device(local)
 
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "not bound (1 GPU)"
     env = Env()
     env.rank, env.world, env.local, env.dist = rank, world, local, dist
     env.dev = torch.device("cuda", local)
@@ -401,6 +444,10 @@ def bench_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
     env.barrier = barrier
+    # N > 1: a few shared words for a spin barrier — every rank enqueues its share of a frame within about a microsecond of the
+    # others (NCCL / gloo barriers release the ranks tens of microseconds apart, and that skew would sit inside the root's span)
+    env.sync = SharedHost(g, 4096, rank, world, dist, "sync", pin=False) if world > 1 else None
+    env.spin = env.sync.spin_barrier if env.sync else (lambda: None)
 
     text, data_note = scene_bytes()
     job = Job(g, env, text, WIDTH, HEIGHT, optimize=args.optimize)
@@ -420,6 +467,10 @@ def bench_ours(args):
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
+    pre_ms = None
+    if world > 1:   # diagnostic: the same frames with the peers' launches queued before the root starts
+        pm, _ = job.time_device(min(args.steps, 20), 2, prequeued=True)
+        pre_ms = float(np.mean(pm))
     ms = torch.tensor(step_ms, dtype=torch.float64, device=env.dev)
     lc = torch.tensor([launches], dtype=torch.int64, device=env.dev)
     ms_max = ms.clone()
@@ -432,7 +483,12 @@ def bench_ours(args):
     value = nrays / (ms_per_step * 1e-3)
 
     # ---- e2e: the synchronous public call with a HOST buffer: parameters H2D, kernels, framebuffer D2H into page-locked memory
-    host = SharedHost(g, nrays * 4, rank, world, dist, "fb")
+    def touch_own_rows(r, arr):
+        # csg_render deals the frame out in rows of 64x32 tiles, row m to rank m % world: 32 scanlines = 491 520 bytes = 120 pages
+        row = 32 * WIDTH * 4
+        for m in range(r, (HEIGHT + 31) // 32, world):
+            arr[m * row:min((m + 1) * row, arr.size)] = 0
+    host = SharedHost(g, nrays * 4, rank, world, dist, "fb", first_touch=touch_own_rows)
     e2e_steps = max(5, min(args.steps, 20))
 
     def frame_e2e():
@@ -486,6 +542,8 @@ def bench_ours(args):
     job.close()
 
     configs = run_configs(g, env, args) if not args.no_configs else None
+    if env.sync:
+        env.sync.close()
 
     if rank != 0:
         if dist is not None:
@@ -591,6 +649,10 @@ def bench_ours(args):
                            "the root's start word and the root's last kernel joins every peer's done word (device-side, over NVLink)",
                    "ms_per_step_min": float(ms.min()), "ms_per_step_max": float(ms.max()),
                    "ms_per_step_max_over_ranks_own_spans": float(ms_max.cpu().numpy().mean()),
+                   "ms_per_step_peers_prequeued": pre_ms,
+                   "prequeued_note": "diagnostic only: peers' launches queued (waiting on the device) before the root starts, i.e. the root's "
+                                     "span without host-side launch skew between the processes; the headline above includes that skew",
+                   "host_binding": numa,
                    "wall_ms_per_step_incl_flush_and_barriers": wall_ms},
         "e2e": {"value": nrays / e2e_s, "unit": "rays/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 256 * world,
                 "d2h_bytes_per_step": nrays * 4, "steps": e2e_steps, "ms_per_step_slowest_rank_own_call": e2e_own_s * 1e3,

@@ -1111,9 +1111,14 @@ int csg_render(csg_context* ctx, const csg_camera* cam, const csg_light* light, 
                 }
                 if (n_rows > 0) {
                     const size_t off = (size_t)first * row_bytes;
+                    static const bool copy2d = !(std::getenv("CSG_B200_COPY2D") && std::getenv("CSG_B200_COPY2D")[0] == '0');   // tuning aid
                     if (count == 1) CU(cudaMemcpyAsync(rgba8_out + off, s.local_fb + off, n_rows * row_bytes, cudaMemcpyDeviceToHost, s.copy_stream));
-                    else CU(cudaMemcpy2DAsync(rgba8_out + off, count * row_bytes, s.local_fb + off, count * row_bytes, row_bytes, (size_t)n_rows,
-                                              cudaMemcpyDeviceToHost, s.copy_stream));
+                    else if (copy2d) CU(cudaMemcpy2DAsync(rgba8_out + off, count * row_bytes, s.local_fb + off, count * row_bytes, row_bytes, (size_t)n_rows,
+                                                          cudaMemcpyDeviceToHost, s.copy_stream));
+                    else
+                        for (int k = 0; k < n_rows; ++k)
+                            CU(cudaMemcpyAsync(rgba8_out + off + (size_t)k * count * row_bytes, s.local_fb + off + (size_t)k * count * row_bytes, row_bytes,
+                                               cudaMemcpyDeviceToHost, s.copy_stream));
                 }
             }
         }
