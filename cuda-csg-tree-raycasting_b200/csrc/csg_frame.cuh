@@ -325,6 +325,15 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
 #endif
 
     if (tid < 27) s_table[tid] = kOutcomeTable[tid];
+    if (kSuper && tid == 28) {
+        // Background of a supersampled pixel none of whose samples hits: the miss colour (:109) summed ss*ss times in the order of
+        // the sample loop (s_table[27] = sum of 0.08f, s_table[31] = sum of 0.11f) — in float that is not ss*ss times the colour
+        // (sixteen 0.11f add up to 1.7600001), and the box filter of the reference's samples is what the frame must equal.
+        float b8 = 0.0f, b11 = 0.0f;
+        for (int i = 0; i < p.ss * p.ss; ++i) { b8 += 0.08f; b11 += 0.11f; }
+        reinterpret_cast<float*>(s_table)[27] = b8;
+        reinterpret_cast<float*>(s_table)[31] = b11;
+    }
     if (tid == 27) {   // L = normalize(lightDir), LightningKernel :78: the same for every pixel of the frame
         const float il = __frcp_rn(__fsqrt_rn(dot_ref(p.light[0], p.light[1], p.light[2], p.light[0], p.light[1], p.light[2])));
         float* s_light = reinterpret_cast<float*>(s_table + 28);
@@ -378,7 +387,13 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                         if (x >= p.width) continue;
                         const size_t pix = (size_t)y * p.width + x;
                         if (MODE == OUT_RGBA8) reinterpret_cast<uint32_t*>(p.out)[pix] = 20u | (20u << 8) | (28u << 16) | 0xFF000000u;
-                        else if (MODE == OUT_F32) reinterpret_cast<float4*>(p.out)[pix] = make_float4(0.08f, 0.08f, 0.11f, 1.0f);
+                        else if (MODE == OUT_F32) {
+                            if (kSuper) {   // the box filter of ss*ss miss samples (s_table[27] / [31])
+                                const float bgw = __frcp_rn((float)(ss * ss));
+                                const float bg8 = reinterpret_cast<const float*>(s_table)[27] * bgw, bg11 = reinterpret_cast<const float*>(s_table)[31] * bgw;
+                                reinterpret_cast<float4*>(p.out)[pix] = make_float4(bg8, bg8, bg11, 1.0f);
+                            } else reinterpret_cast<float4*>(p.out)[pix] = make_float4(0.08f, 0.08f, 0.11f, 1.0f);
+                        }
                         else {
                             if (p.aov_hit) p.aov_hit[pix] = 0;
                             if (p.aov_prim) p.aov_prim[pix] = -1;
@@ -529,8 +544,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             float accx = 0.f, accy = 0.f, accz = 0.f;
             if (!kSuper && !tile_empty) req_lane = __ffs(amask) - 1;
             if (tile_empty) {
-                const float w = (float)(ss * ss);
-                accx = 0.08f * w; accy = 0.08f * w; accz = 0.11f * w;
+                accx = accy = kSuper ? reinterpret_cast<const float*>(s_table)[27] : 0.08f;
+                accz = kSuper ? reinterpret_cast<const float*>(s_table)[31] : 0.11f;
             } else if (active) {
                 if (kSuper) {
                     // More than one ray per pixel: the running colour sum lives in this thread's scratch frame in shared memory,

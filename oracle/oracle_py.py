@@ -255,6 +255,26 @@ class RefGPU(_Ref):
         self.lib.refgpu_render.argtypes = [C.c_char_p, C.POINTER(RefView)] + [C.c_void_p] * 4 + \
             [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
 
+    def render_window(self, text, view, x0, y0, ww, wh):
+        """The reference kernels at the full size of `view`; only the window [x0, x0+ww) x [y0, y0+wh) comes back (a Frame of
+        ww x wh pixels, .ms_kernels = the time of the two kernels over the whole grid)."""
+        if isinstance(text, str):
+            text = text.encode()
+        self.lib.refgpu_render_window.argtypes = [C.c_char_p, C.POINTER(RefView)] + [C.c_int] * 4 + [C.c_void_p] * 4 + \
+            [C.POINTER(C.c_float), C.c_char_p, C.c_int]
+        fr = Frame(ww, wh)
+        ms = C.c_float()
+        err = C.create_string_buffer(512)
+        rv = view.ref()
+        rc = self.lib.refgpu_render_window(text, C.byref(rv), x0, y0, ww, wh, _p(fr.hit), _p(fr.prim), _p(fr.t), _p(fr.rgba),
+                                           C.byref(ms), err, 512)
+        if rc == 1:
+            raise ParseError(err.value.decode())
+        if rc:
+            raise RuntimeError("refgpu_render_window: " + err.value.decode())
+        fr.ms_kernels = ms.value
+        return fr
+
     def render(self, text, view, warmup=0, iters=1, shipped=False, outputs=True):
         if isinstance(text, str):
             text = text.encode()

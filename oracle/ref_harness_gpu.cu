@@ -220,4 +220,68 @@ int refgpu_render(const char* text, const ref_view* v,
     return 0;
 }
 
+/* The unmodified reference kernels at the FULL size of `v` (e.g. the 30720 x 17280 virtual grid of BASELINE.json configs[4]:
+ * 19 GB of RayHit + 8.5 GB of float4 on the device), of which only the window [x0, x0 + ww) x [y0, y0 + wh) is copied out:
+ * rgba (ww * wh float4), hit / prim / t (ww * wh each; any may be NULL).  Lets a test compare a supersampled frame with the
+ * reference sample by sample without moving the whole grid to the host. */
+int refgpu_render_window(const char* text, const ref_view* v, int x0, int y0, int ww, int wh,
+                         uint8_t* hit, int32_t* prim, float* t, float* rgba, float* ms_kernels, char* err, int errlen)
+{
+    CSGTree tree;
+    try {
+        tree = CSGTree::Parse(text);
+    } catch (const std::exception& e) {
+        fill_err(err, errlen, e.what());
+        return 1;
+    }
+    const int w = v->width, h = v->height;
+    if (x0 < 0 || y0 < 0 || ww < 1 || wh < 1 || x0 + ww > w || y0 + wh > h) { fill_err(err, errlen, "window outside the frame"); return 2; }
+    const size_t npx = (size_t)w * h;
+    Camera cam = make_camera(v);
+    DirectionalLight light = make_light(v);
+    CudaCSGTree ct;
+    RayHit* dHits = nullptr;
+    float4* dOut = nullptr;
+    CK(cudaMalloc(&ct.nodes, tree.nodes.size() * sizeof(CSGNode)));
+    CK(cudaMalloc(&ct.primitives, tree.primitives.primitives.size() * sizeof(Primitive)));
+    CK(cudaMemcpy(ct.nodes, tree.nodes.data(), tree.nodes.size() * sizeof(CSGNode), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ct.primitives, tree.primitives.primitives.data(),
+                  tree.primitives.primitives.size() * sizeof(Primitive), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&dHits, npx * sizeof(RayHit)));
+    CK(cudaMalloc(&dOut, npx * sizeof(float4)));
+    CK(cudaMemset(dHits, 0, npx * sizeof(RayHit)));
+    dim3 block(BLOCKXSIZE, BLOCKYSIZE);
+    dim3 grid((w + block.x - 1) / block.x, (h + block.y - 1) / block.y);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    RaycastKernel<<<grid, block>>>(cam, ct, dHits, (float)w, (float)h);
+    LightningKernel<<<grid, block>>>(cam, dHits, ct.primitives, dOut, light.getLightDir(), (float)w, (float)h);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    if (ms_kernels) CK(cudaEventElapsedTime(ms_kernels, e0, e1));
+    if (rgba)
+        CK(cudaMemcpy2D(rgba, (size_t)ww * sizeof(float4), dOut + (size_t)y0 * w + x0, (size_t)w * sizeof(float4), (size_t)ww * sizeof(float4), wh,
+                        cudaMemcpyDeviceToHost));
+    if (hit || prim || t) {
+        std::vector<RayHit> hh((size_t)ww * wh);
+        CK(cudaMemcpy2D((void*)hh.data(), (size_t)ww * sizeof(RayHit), dHits + (size_t)y0 * w + x0, (size_t)w * sizeof(RayHit), (size_t)ww * sizeof(RayHit), wh,
+                        cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < hh.size(); ++i) {
+            if (hit) hit[i] = hh[i].hit ? 1 : 0;
+            if (prim) prim[i] = hh[i].hit ? hh[i].primitiveIdx : -1;
+            if (t) t[i] = hh[i].hit ? hh[i].t : -1.0f;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(dHits);
+    cudaFree(dOut);
+    cudaFree(ct.nodes);
+    cudaFree(ct.primitives);
+    return 0;
+}
+
 }  // extern "C"
