@@ -24,6 +24,8 @@ for mode, name in ((1, "flat"), (2, "walk"), (0, "off")):
             sc = g.Scene.parse(txt)
             ctx = sc.upload_shard(bench.WIDTH, bench.HEIGHT, 0, rank, count)
             ctx.set_pruning(mode)
+            fb = torch.empty(bench.WIDTH * bench.HEIGHT * 4, dtype=torch.uint8, device="cuda")
+            ctx.set_gather_target(fb.data_ptr())   # a plain local buffer: no start gate / join with the (absent) other shards
             ms = []
             for k in range(frames + 5):
                 flush.zero_()
