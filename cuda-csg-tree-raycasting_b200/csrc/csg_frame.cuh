@@ -115,9 +115,10 @@ constexpr uint32_t kSearchMark = 0xfffffffeu;
 template <bool COUNT>
 __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, const float4* __restrict__ prims,
                                         const uint32_t* __restrict__ table, const uint32_t stack,
-                                        const uint32_t stack_stride, const Ray& r, const bool root_is_leaf, const bool root_pure, const bool root_gated, int& iters)
+                                        const uint32_t stack_stride, const int& stack_levels, const Ray& r, const bool root_is_leaf, const bool root_pure,
+                                        const bool root_gated, int& iters)
 {
-    enum { ST_ENTER = 0, ST_SEARCH = 1, ST_LOOPL = 2, ST_LOOPR = 3, ST_COMPUTE = 4, ST_RETURN = 5, ST_DONE = 6 };
+    enum { ST_ENTER = 0, ST_SEARCH = 1, ST_LOOPL = 2, ST_LOOPR = 3, ST_COMPUTE = 4, ST_RETURN = 5, ST_DONE = 6, ST_FLAT = 7 };
     Hit L = make_miss(), R = make_miss();      // ST_SEARCH: L = nearest Enter so far, R.t = limit
     float tmin = 0.0f;                        // :466
     if (root_is_leaf) {
@@ -135,7 +136,8 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     sts128(sp, make_uint4(0u, 0u, 0u, 0xffffffffu)); // sentinel frame: popping it ends the traversal (no base pointer to keep)
     sp += stack_stride;
     int st = ST_ENTER;
-    if (root_pure) {                           // the whole scene is one pure subtree
+    if (*reinterpret_cast<const uint32_t*>(tree + 28) & kMetaFlat) st = ST_FLAT;   // the whole (tile) tree is one flat Union of spheres
+    else if (root_pure) {                      // the whole scene is one pure subtree
         sts128(sp, make_uint4(0u, 0u, 0u, kSearchMark));
         sp += stack_stride;
         R.t = INFINITY;
@@ -143,6 +145,14 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     }
     while (st != ST_DONE) {
         if (COUNT) iters += (st == ST_SEARCH) ? (1 << 20) : (st == ST_ENTER) ? (1 << 10) : 1;   // packed: search visits | frame-machine visits | other iterations
+        if (st == ST_FLAT) {
+            // n is a flat operand (a Union over a few spheres) the machine was about to descend into; the frame that takes its
+            // result is pushed.  Its result follows from the spheres' roots (flat_eval; the frames above sp are free and hold its
+            // list): return it as if the descent had happened — or, when flat_eval gives up, descend after all.
+            const uint2 fe = flat_eval(tree, n, r, tmin, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
+            if (fe.y != kFlatGaveUp) { L.t = __uint_as_float(fe.x); L.m = fe.y; R = L; st = ST_RETURN; }
+            else st = ST_ENTER;
+        }
         if (st <= ST_LOOPR) {
             const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
             const uint32_t op = meta & 7u;
@@ -159,8 +169,14 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                 st = ST_RETURN;
             } else {
                 if (st != ST_LOOPL) eval_child(tree, prims, cr, r, tmin, st <= ST_SEARCH, b, goB, tnB, mB);
-                if (st == ST_LOOPL) { L = a; st = ST_COMPUTE; }
-                else if (st == ST_LOOPR) { R = b; st = ST_COMPUTE; }
+                if (st == ST_LOOPL) {
+                    // the operand Compute loops into is a primitive (re-intersected just now) or a flat Union whose box the ray meets
+                    if (goA) { sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride; n = cl; st = ST_FLAT; }
+                    else { L = a; st = ST_COMPUTE; }
+                } else if (st == ST_LOOPR) {
+                    if (goB) { sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride; n = cr; st = ST_FLAT; }
+                    else { R = b; st = ST_COMPUTE; }
+                }
                 else if (st == ST_SEARCH) {
                     // leaf results are candidates; an Exit or a tie for the nearest hit ends the search
                     bool abort = false;
@@ -220,13 +236,14 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                             if (op == 0u && !is_miss(R)) lim = R.t;
                         } else {                                                           // :568-574
                             const bool right_first = (op == 0u) && (tnB < tnA);
-                            const uint32_t pend_pure = ((right_first ? mA : mB) >> 6) & 1u;
+                            const uint32_t pend_pure = ((right_first ? mA : mB) >> 6) & 3u;   // bit 0: the pending operand is pure, bit 1: flat
                             sts128(sp, make_uint4(__float_as_uint(tmin), (right_first ? F_FIRST_RGH : F_FIRST_LFT) | pend_pure,
                                              __float_as_uint(right_first ? tnA : tnB), n));
                             first = right_first ? cr : cl; fm = right_first ? mB : mA; ftn = right_first ? tnB : tnA;
                         }
                         sp += stack_stride; n = first;
-                        if ((fm & kMetaPure) && ftn > tmin) {   // pure subtree ahead of tmin: nearest-Enter search
+                        if (fm & kMetaFlat) st = ST_FLAT;
+                        else if ((fm & kMetaPure) && ftn > tmin) {   // pure subtree ahead of tmin: nearest-Enter search
                             sts128(sp, make_uint4(0u, 0u, first, kSearchMark));
                             sp += stack_stride;
                             L = make_miss(); R.t = lim; st = ST_SEARCH;
@@ -284,7 +301,8 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                             sib = n + 32u;
                         }
                         sp += stack_stride; n = sib; st = ST_ENTER;
-                        if ((f.y & 1u) && ptn > tmin) {
+                        if (f.y & 2u) st = ST_FLAT;
+                        else if ((f.y & 1u) && ptn > tmin) {
                             const float lim = (pop != 2u && !miss) ? L.t : INFINITY;
                             sts128(sp, make_uint4(0u, 0u, sib, kSearchMark));
                             sp += stack_stride;
@@ -343,7 +361,13 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     gate_enter(p.gate);   // sharded frames: nothing of this frame happens before the root GPU has started it
     const uint32_t my_stack = (uint32_t)__cvta_generic_to_shared(s_stack + tid);   // frames are addressed in the shared window: 32-bit
     // per-warp copy of the current tile's tree (when it fits): traversal then reads shared memory instead of L1/L2
-    const uint32_t my_tree_off = 128u + 16u * (uint32_t)((p.stack_levels + 3) * kThreads + (tid >> 5) * (2 * p.warp_tree_nodes));   // bytes from smem_raw
+    // bytes from smem_raw to this warp's tree copy.  Worked out where it is used, once per tile, from a thread id the compiler
+    // cannot hoist (volatile): kept across the traversal it is the one value too many for 80 registers (it was spilled)
+    auto my_tree_off = [&p]() {
+        uint32_t t;
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+        return 128u + 16u * (uint32_t)((p.stack_levels + 3) * kThreads + (int)(t >> 5) * (2 * p.warp_tree_nodes));
+    };
     const float* s_light = reinterpret_cast<const float*>(s_table + 28);
     // supersampling: one more 16-byte frame per thread behind the traversal stack (colour accumulators)
     const uint32_t my_scratch = my_stack + (uint32_t)((p.stack_levels + 2) * kThreads) * 16u;
@@ -504,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             }
             make_ray(tx0 + (lane & 7), ty0 + (lane >> 3), r0);
             if (tree_fits) {
-                uint4* my_tree = reinterpret_cast<uint4*>(smem_raw + my_tree_off);
+                uint4* my_tree = reinterpret_cast<uint4*>(smem_raw + my_tree_off());
                 __syncwarp();   // everybody is done with the previous tile's copy
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
@@ -515,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                 tree = reinterpret_cast<const unsigned char*>(my_tree);
             }
         } else if (tree_fits) {
-            uint4* my_tree = reinterpret_cast<uint4*>(smem_raw + my_tree_off);
+            uint4* my_tree = reinterpret_cast<uint4*>(smem_raw + my_tree_off());
             __syncwarp();   // everybody is done with the previous tile's copy
             for (uint32_t i = lane; i < 2u * td.y; i += 32u) my_tree[i] = __ldg(p.pool + 2 * (size_t)td.x + i);
             __syncwarp();
@@ -559,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                         const int sy = sp ? (sl >> (sp >> 1)) : s / ss;
                         const int sx = sp ? (sl & (ss - 1)) : s - sy * ss;
                         make_ray(x * ss + sx, y * ss + sy, r);
-                        res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u,
+                        res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), p.stack_levels, r, (td.z & kTileRootLeaf) != 0u,
                                                         (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
                         if (MODE != OUT_AOV) {
                             const float4 c = shade_pixel(res, r, p.prims, p, s_light);
@@ -572,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                     accx = __uint_as_float(a.x); accy = __uint_as_float(a.y); accz = __uint_as_float(a.z);
                 } else {
                     r.dx = r0.dx; r.dy = r0.dy; r.dz = r0.dz; r.ix = r0.ix; r.iy = r0.iy; r.iz = r0.iz;
-                    res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), r, (td.z & kTileRootLeaf) != 0u,
+                    res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), p.stack_levels, r, (td.z & kTileRootLeaf) != 0u,
                                                     (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
                     if (lane == __ffs(amask) - 1)   // the tile is traced: ask for the next ticket now
                         next = atomicAdd(p.tile_counter, 1u) - p.counter_base;

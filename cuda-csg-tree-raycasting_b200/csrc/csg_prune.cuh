@@ -414,7 +414,9 @@ constexpr int kFlatPreferNodes = 2048;  // above this the tree-walking kernel is
 struct FlatTileSmem {                  // followed by uint16_t A[n_pad], S[n_pad]
     float box[kSlotMax][6];            // culling box of every record of the tile's tree, origin-relative
     uint32_t meta[kSlotMax];           // kind | right operand (record index) << 8
-    unsigned char flg[kSlotMax];       // bit0 pure, bit1 bounded
+    unsigned char flg[kSlotMax];       // bit0 pure, bit1 bounded, bit2 spheres and Unions only
+    unsigned char cnt[kSlotMax];       // primitives below (saturating), for the flat flag
+    uint32_t lmask[kSlotMax];          // bit j: record i + j of this subtree is a primitive (meaningful up to 32 records: 16 primitives)
     unsigned char done[kSlotMax];      // box and flags are final
     unsigned int wsum[kFlatThreadsMax / 32];
     float plane[5][4];                 // the tile's frustum
@@ -599,7 +601,9 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { w.box[i][c] = lo[c]; w.box[i][3 + c] = hi[c]; }
                 w.meta[i] = kind;
-                w.flg[i] = (unsigned char)(((kind == 3u || kind == 5u) ? 1u : 0u) | ((kind != 4u) ? 2u : 0u));
+                w.flg[i] = (unsigned char)(((kind == 3u || kind == 5u) ? 1u : 0u) | ((kind != 4u) ? 2u : 0u) | ((kind == 3u) ? 4u : 0u));
+                w.cnt[i] = 1;
+                w.lmask[i] = 1u;
                 w.done[i] = 1;
             } else {
                 const uint32_t ri = Sv[(tp.x >> 8) - 1u];   // survivors before the right subtree = record of the right operand
@@ -638,7 +642,9 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
                         for (int c = 0; c < 6; ++c) bo[c] = bs[c];
                     }
                     const uint32_t fl = w.flg[a], fr = w.flg[b];
-                    w.flg[i] = (unsigned char)(((kind == 0u) ? (fl & fr & 1u) : 0u) | (fl & fr & 2u));
+                    w.flg[i] = (unsigned char)(((kind == 0u) ? (fl & fr & 5u) : 0u) | (fl & fr & 2u));
+                    w.cnt[i] = (unsigned char)min((int)w.cnt[a] + (int)w.cnt[b], 255);
+                    w.lmask[i] = (w.lmask[a] << 1) | (w.lmask[b] << ((2u * w.cnt[a]) & 31u));   // the left subtree holds 2 cnt - 1 records, behind this one
                     now |= 1u << k;
                 }
                 __syncwarp();
@@ -655,11 +661,16 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
             const uint32_t m = w.meta[i], kind = m & 7u;
             if (kind >= 3u) continue;
             const uint32_t ri = m >> 8, f = w.flg[i];
-            const uint32_t meta = kind | (ri << 8) | ((w.meta[i + 1] & 7u) >= 3u ? kMetaLeftLeaf : 0u) | ((w.meta[ri] & 7u) >= 3u ? kMetaRightLeaf : 0u) |
-                                  ((f & 2u) ? kMetaBounded : 0u) | ((f & 1u) ? kMetaPure : 0u);
+            // flat: a Union over at most flat_max spheres (flat_eval).  Compute re-evaluates a flat operand on the spot when it loops
+            // into it, like a primitive: the leaf bits of the parent cover it
+            const uint32_t fmax = (uint32_t)min(q.flat_max, kFlatLeavesMax);
+            const bool flat = (f & 4u) && w.cnt[i] <= fmax;   // spheres-only is set on Unions (and spheres) only
+            const bool lflat = (w.flg[i + 1] & 4u) && w.cnt[i + 1] <= fmax, rflat = (w.flg[ri] & 4u) && w.cnt[ri] <= fmax;   // a sphere: cnt 1, fmax 0 = off
+            const uint32_t meta = kind | (ri << 8) | (((w.meta[i + 1] & 7u) >= 3u || lflat) ? kMetaLeftLeaf : 0u) | (((w.meta[ri] & 7u) >= 3u || rflat) ? kMetaRightLeaf : 0u) |
+                                  ((f & 2u) ? kMetaBounded : 0u) | ((f & 1u) ? kMetaPure : 0u) | (flat ? kMetaFlat : 0u);
             const float* bo = w.box[i];
             dst[2 * i] = make_uint4(__float_as_uint(bo[0]), __float_as_uint(bo[1]), __float_as_uint(bo[2]), __float_as_uint(bo[3]));
-            dst[2 * i + 1] = make_uint4(__float_as_uint(bo[4]), __float_as_uint(bo[5]), 0u, meta);
+            dst[2 * i + 1] = make_uint4(__float_as_uint(bo[4]), __float_as_uint(bo[5]), flat ? (w.lmask[i] >> 1) : 0u, meta);   // flat: which of the following records are its spheres
         }
         const uint32_t rk = w.meta[0] & 7u;
         flags = (rk >= 3u ? kTileRootLeaf : 0u) | ((rk < 3u && (w.flg[0] & 1u)) ? kTileRootPure : 0u);

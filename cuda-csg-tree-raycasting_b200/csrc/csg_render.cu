@@ -149,6 +149,7 @@ struct csg_context {
     int last_mode = 0;           // shard mode of the last frame (csg_prune_stats)
     bool shard_sync = true;      // sharded frames are started and joined on the device (SyncWords); csg_set_gather_target(pointer) turns it off
     bool view_cache = false;     // csg_set_view_cache
+    int flat_leaves = 16;        // Unions over at most this many spheres are evaluated flat (flat_eval); 0: never
     bool external_target = false;   // csg_set_gather_target: pixels go to a buffer that is not rank 0's own framebuffer
     bool prune_alloc = false;    // tile slots were allocated at upload
     int last_rm[4] = {0, 0, 0, 0};   // traced macro-tile rectangle of the last frame (x0, y0, w, h)
@@ -189,8 +190,10 @@ int launch_one(csg_context* c, Shard& s, const FrameParams& fp)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = c->ss > 1 ? cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, true>, fp)
-                              : cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false>, fp);
+    cudaError_t e;
+    if constexpr (MODE == OUT_AOV) e = cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false>, fp);   // per primary ray: enqueue_frame refuses ss > 1
+    else e = c->ss > 1 ? cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, true>, fp)
+                       : cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false>, fp);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return CSG_OK;
@@ -209,9 +212,9 @@ int launch_mode(csg_context* c, Shard& s, const FrameParams& fp)
 template <int MODE, int T>
 int configure_one(size_t smem, int* blocks_per_sm)
 {
-    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if constexpr (MODE != OUT_AOV) CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, T, true>, T, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, T, false>, T, smem));
     return CSG_OK;
 }
 
@@ -425,7 +428,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.lists = s.d_lists; q.order = s.d_order;
             // (heaviest-first hand-out also pays on a frame sharded over 8 GPUs, 2-3 tiles per warp: the slowest of the eight shards
             // takes 63.9 us with it and 67.3 us with the natural order, although shard 0 alone is 3 us faster without the ordering pass)
-            q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes;
+            q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes; q.flat_max = c->flat_leaves;
             q.slots_off32 = (uint32_t)fp.n_nodes; q.full_flags = c->full_flags;
             // view cache (opt-in): same camera, size, sampling and tile set as the trees this shard already holds -> keep them
             // (compared before the gate goes in: its sequence number changes with every frame)
@@ -569,6 +572,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         const char* force_flat = std::getenv("CSG_B200_PRUNE_FLAT");   // tuning aid: the flat kernel whenever it fits
         c->flat_ok = n <= (size_t)((force_flat && force_flat[0] == '1') ? kFlatMaxNodes : kFlatPreferNodes);
         c->flat_smem = sizeof(FlatTileSmem) + 2 * ((n + 7) & ~(size_t)7) * sizeof(unsigned short);
+        if (const char* fl = std::getenv("CSG_B200_FLAT_LEAVES")) c->flat_leaves = std::min(std::max(std::atoi(fl), 0), kFlatLeavesMax);   // tuning aid
         const char* walk = std::getenv("CSG_B200_PRUNE_WALK");   // tuning aid: the tree-walking kernel instead
         c->prune_flat = !(walk && walk[0] == '1');
     }
