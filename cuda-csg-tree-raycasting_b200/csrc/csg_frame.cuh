@@ -169,14 +169,8 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                 st = ST_RETURN;
             } else {
                 if (st != ST_LOOPL) eval_child(tree, prims, cr, r, tmin, st <= ST_SEARCH, b, goB, tnB, mB);
-                if (st == ST_LOOPL) {
-                    // the operand Compute loops into is a primitive (re-intersected just now) or a flat Union whose box the ray meets
-                    if (goA) { sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride; n = cl; st = ST_FLAT; }
-                    else { L = a; st = ST_COMPUTE; }
-                } else if (st == ST_LOOPR) {
-                    if (goB) { sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride; n = cr; st = ST_FLAT; }
-                    else { R = b; st = ST_COMPUTE; }
-                }
+                if (st == ST_LOOPL) { L = a; st = ST_COMPUTE; }
+                else if (st == ST_LOOPR) { R = b; st = ST_COMPUTE; }
                 else if (st == ST_SEARCH) {
                     // leaf results are candidates; an Exit or a tie for the nearest hit ends the search
                     bool abort = false;
@@ -264,11 +258,17 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
             } else if (o == O_LOOPL) {                                                 // :640-646
                 tmin = L.t;
                 if (meta & kMetaLeftLeaf) st = ST_LOOPL;
-                else { sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride; n = n + 32u; st = ST_ENTER; }
+                else {   // into an operator: a flat one (word 6 of this record says so) is evaluated from its spheres' roots
+                    sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride;
+                    st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6LeftFlat) ? ST_FLAT : ST_ENTER; n = n + 32u;
+                }
             } else if (o == O_LOOPR) {                                                 // :647-653
                 tmin = R.t;
                 if (meta & kMetaRightLeaf) st = ST_LOOPR;
-                else { sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride; n = (meta >> 8) << 5; st = ST_ENTER; }
+                else {
+                    sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride;
+                    st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6RightFlat) ? ST_FLAT : ST_ENTER; n = (meta >> 8) << 5;
+                }
             } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
         }
         if (st == ST_RETURN) {                  // action = actionStack.pop(); node = GetParent() (:624-625 etc.); L == R == result

@@ -27,7 +27,7 @@ __device__ __forceinline__ void stage_record(const uint4 ua, const uint4 ub, flo
         a.w = __fsub_rn(a.w, ox); b.x = __fsub_rn(b.x, oy); b.y = __fsub_rn(b.y, oz);
     }
     oa = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
-    ob = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), ub.z, ub.w);
+    ob = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), (ub.w & 7u) < 3u ? 0u : ub.z, ub.w);   // operators: no flat-evaluation flags (word 6, csg_scene.h)
 }
 
 // culling box of a node relative to the origin: operators, cubes, cylinders carry it; spheres: centre +- r, padded like the host does
@@ -661,16 +661,16 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
             const uint32_t m = w.meta[i], kind = m & 7u;
             if (kind >= 3u) continue;
             const uint32_t ri = m >> 8, f = w.flg[i];
-            // flat: a Union over at most flat_max spheres (flat_eval).  Compute re-evaluates a flat operand on the spot when it loops
-            // into it, like a primitive: the leaf bits of the parent cover it
+            // flat: a Union over at most flat_max spheres (flat_eval); word 6 also tells Compute which operands are flat operators
             const uint32_t fmax = (uint32_t)min(q.flat_max, kFlatLeavesMax);
             const bool flat = (f & 4u) && w.cnt[i] <= fmax;   // spheres-only is set on Unions (and spheres) only
-            const bool lflat = (w.flg[i + 1] & 4u) && w.cnt[i + 1] <= fmax, rflat = (w.flg[ri] & 4u) && w.cnt[ri] <= fmax;   // a sphere: cnt 1, fmax 0 = off
-            const uint32_t meta = kind | (ri << 8) | (((w.meta[i + 1] & 7u) >= 3u || lflat) ? kMetaLeftLeaf : 0u) | (((w.meta[ri] & 7u) >= 3u || rflat) ? kMetaRightLeaf : 0u) |
+            const bool lleaf = (w.meta[i + 1] & 7u) >= 3u, rleaf = (w.meta[ri] & 7u) >= 3u;
+            const bool lflat = !lleaf && (w.flg[i + 1] & 4u) && w.cnt[i + 1] <= fmax, rflat = !rleaf && (w.flg[ri] & 4u) && w.cnt[ri] <= fmax;
+            const uint32_t meta = kind | (ri << 8) | (lleaf ? kMetaLeftLeaf : 0u) | (rleaf ? kMetaRightLeaf : 0u) |
                                   ((f & 2u) ? kMetaBounded : 0u) | ((f & 1u) ? kMetaPure : 0u) | (flat ? kMetaFlat : 0u);
             const float* bo = w.box[i];
             dst[2 * i] = make_uint4(__float_as_uint(bo[0]), __float_as_uint(bo[1]), __float_as_uint(bo[2]), __float_as_uint(bo[3]));
-            dst[2 * i + 1] = make_uint4(__float_as_uint(bo[4]), __float_as_uint(bo[5]), flat ? (w.lmask[i] >> 1) : 0u, meta);   // flat: which of the following records are its spheres
+            dst[2 * i + 1] = make_uint4(__float_as_uint(bo[4]), __float_as_uint(bo[5]), (flat ? ((w.lmask[i] >> 1) & kW6SphereMask) : 0u) | (lflat ? kW6LeftFlat : 0u) | (rflat ? kW6RightFlat : 0u), meta);   // flat: which of the following records are its spheres
         }
         const uint32_t rk = w.meta[0] & 7u;
         flags = (rk >= 3u ? kTileRootLeaf : 0u) | ((rk < 3u && (w.flg[0] & 1u)) ? kTileRootPure : 0u);

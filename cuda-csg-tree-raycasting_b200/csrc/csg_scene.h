@@ -29,7 +29,7 @@ static_assert(sizeof(RefNode) == 44 && sizeof(RefPrim) == 48, "reference layouts
 // One 32-byte record per node, preorder (left child of operator n is n+1):
 //   word 7 (all kinds)   kind | leftIsLeaf<<3 | rightIsLeaf<<4 | bounded<<5 | pure<<6 | flat<<7 | idx<<8   idx = right child (operator) / primitive id (leaf)
 //                        bounded = no cylinder below: the culling box really bounds every hit of the subtree (allows pruning)
-//   operator   w0..5 = culling box (min xyz, max xyz),  w6 = parent node (-1 at the root)
+//   operator   w0..5 = culling box (min xyz, max xyz),  w6 = parent node (-1 at the root) as uploaded; staged / tile trees: flat-evaluation word (kMetaFlat below)
 //   sphere     w0..2 = centre, w3 = radius, w4..6 = centre again (staging turns w0..2 into origin-centre and w3 into r*r - |origin-centre|^2)
 //   cube       w0..5 = lb, rt  (centre -/+ size/2, rounded like the reference rounds them)
 //   cylinder   w0..5 = the reference's own leaf box (centre -/+ max(h/2, r)), which gates the primitive (Q6)
@@ -45,9 +45,11 @@ constexpr uint32_t kMetaPure = 1u << 6;
 // flat (per-tile trees only, set by csg_prune_flat_kernel) = a Union over at most PruneParams::flat_max spheres and nothing else:
 // its result at any tmin follows from the spheres' roots alone (flat_eval, csg_kernel.cuh).  Word 6 of such a record = bit mask of
 // the spheres among the records that follow it (bit j: record n + 1 + j; a subtree of k spheres is 2k - 1 records, so k <= 16);
-// its parent carries the leftIsLeaf / rightIsLeaf bit for it.
+// bits 30 / 31 of word 6 of ANY operator record of a tile tree say that its left / right operand is such a flat operator (Compute
+// looks there when it loops into an operand).  Records staged from the uploaded tree carry 0 in word 6.
 constexpr uint32_t kMetaFlat = 1u << 7;
 constexpr int kFlatLeavesMax = 16;
+constexpr uint32_t kW6LeftFlat = 1u << 30, kW6RightFlat = 1u << 31, kW6SphereMask = 0x3fffffffu;
 
 // Per-primitive data kept in global memory (read on accepted hits / cylinder + cube tests / shading): 5 x float4.
 struct PrimRec {

@@ -10,6 +10,8 @@ import bench
 txt, _ = bench.scene_bytes()
 count = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 sc = g.Scene.parse(txt); ctx = sc.upload_shard(bench.WIDTH, bench.HEIGHT, 0, 0, count)
+fb = torch.empty(bench.WIDTH * bench.HEIGHT * 4, dtype=torch.uint8, device="cuda")
+ctx.set_gather_target(fb.data_ptr())   # a plain local buffer: no start gate / join with the (absent) other shards
 cam, light = g.Camera(), g.Light()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 names = ["start", "frustum", "leaf tests", "scan1+counts", "scan2", "emission", "refit", "op records", "desc+done atomic", "concat (last CTA)"]
