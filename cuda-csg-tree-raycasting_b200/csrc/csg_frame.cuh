@@ -16,6 +16,7 @@ constexpr int min_blocks_for(int threads) { return threads >= 768 ? 1 : threads 
 constexpr int kWarpTileW = 8, kWarpTileH = 4;   // one warp = one 8x4 pixel tile (Raycaster.cuh:7-8 uses the same shape)
 constexpr int kMacroW = 64, kMacroH = 32;       // sharding unit: 8x8 warp tiles
 constexpr int kWarpTreeMax = 64;                // records of the largest per-warp shared-memory tree copy
+constexpr int kSmemHead = 128;                  // bytes before the stack: outcome table + light (csg_render.cu sizes the launch with it)
 
 // Hit details + Phong (sphere/cylinder/cubeHitDetails :183-200/:338-372/:436-457 and LightningKernel :49-111).
 __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const float4* __restrict__ prims, const FrameParams& p, const float* __restrict__ s_light)
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     // KB; a warp copies the tree of its current tile into shared memory when it fits, and reads it through L1 otherwise.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_table = reinterpret_cast<uint32_t*>(smem_raw);
-    uint4* s_stack = reinterpret_cast<uint4*>(smem_raw + 128);
+    uint4* s_stack = reinterpret_cast<uint4*>(smem_raw + kSmemHead);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const float ox = p.cam_pos[0], oy = p.cam_pos[1], oz = p.cam_pos[2];
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         s_light[0] = p.light[0] * il; s_light[1] = p.light[1] * il; s_light[2] = p.light[2] * il;
     }
     __syncthreads();
-    gate_enter(p.gate);   // sharded frames: nothing of this frame happens before the root GPU has started it
+    gate_enter(p.gate, 2);   // sharded frames: nothing of this frame happens before the root GPU has started it
     const uint32_t my_stack = (uint32_t)__cvta_generic_to_shared(s_stack + tid);   // frames are addressed in the shared window: 32-bit
     // per-warp copy of the current tile's tree (when it fits): traversal then reads shared memory instead of L1/L2
     // bytes from smem_raw to this warp's tree copy.  Worked out where it is used, once per tile, from a thread id the compiler
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     auto my_tree_off = [&p]() {
         uint32_t t;
         asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
-        return 128u + 16u * (uint32_t)((p.stack_levels + 3) * kThreads + (int)(t >> 5) * (2 * p.warp_tree_nodes));
+        return (uint32_t)kSmemHead + 16u * (uint32_t)((p.stack_levels + 3) * kThreads + (int)(t >> 5) * (2 * p.warp_tree_nodes));
     };
     const float* s_light = reinterpret_cast<const float*>(s_table + 28);
     // supersampling: one more 16-byte frame per thread behind the traversal stack (colour accumulators)
@@ -679,10 +680,12 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             const unsigned int before = atomicAdd(p.gate.exit_counter, 1u);
             if (before == gridDim.x - 1u) {
                 *p.gate.exit_counter = 0u;   // ready for the next frame
+                SPROBE(4);
                 __threadfence_system();
                 if (p.gate.role == GATE_PEER) st_release_sys(&p.gate.words->done[p.gate.rank], p.gate.seq);
                 else
                     for (int r = 1; r < p.gate.n_shards; ++r) wait_seq(&p.gate.words->done[r], p.gate.seq, p.gate.err);
+                SPROBE(5);
             }
         }
     }

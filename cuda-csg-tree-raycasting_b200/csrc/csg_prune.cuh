@@ -661,16 +661,16 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
             const uint32_t m = w.meta[i], kind = m & 7u;
             if (kind >= 3u) continue;
             const uint32_t ri = m >> 8, f = w.flg[i];
-            // flat: a Union over at most flat_max spheres (flat_eval); word 6 also tells Compute which operands are flat operators
-            const uint32_t fmax = (uint32_t)min(q.flat_max, kFlatLeavesMax);
-            const bool flat = (f & 4u) && w.cnt[i] <= fmax;   // spheres-only is set on Unions (and spheres) only
-            const bool lleaf = (w.meta[i + 1] & 7u) >= 3u, rleaf = (w.meta[ri] & 7u) >= 3u;
-            const bool lflat = !lleaf && (w.flg[i + 1] & 4u) && w.cnt[i + 1] <= fmax, rflat = !rleaf && (w.flg[ri] & 4u) && w.cnt[ri] <= fmax;
-            const uint32_t meta = kind | (ri << 8) | (lleaf ? kMetaLeftLeaf : 0u) | (rleaf ? kMetaRightLeaf : 0u) |
+            // flat: a Union over a few spheres (flat_eval, csg_scene.h); word 6 also tells Compute which operands are flat operators
+            const int fmax = min(q.flat_max, kFlatLeavesMax);
+            auto is_flat = [&w, fmax](uint32_t x) { return (w.meta[x] & 7u) == 0u && (w.flg[x] & 4u) && (int)w.cnt[x] <= fmax; };   // spheres-only Unions
+            const bool flat = is_flat((uint32_t)i);
+            const uint32_t meta = kind | (ri << 8) | ((w.meta[i + 1] & 7u) >= 3u ? kMetaLeftLeaf : 0u) | ((w.meta[ri] & 7u) >= 3u ? kMetaRightLeaf : 0u) |
                                   ((f & 2u) ? kMetaBounded : 0u) | ((f & 1u) ? kMetaPure : 0u) | (flat ? kMetaFlat : 0u);
+            const uint32_t w6 = (flat ? ((w.lmask[i] >> 1) & kW6SphereMask) : 0u) | (is_flat((uint32_t)i + 1u) ? kW6LeftFlat : 0u) | (is_flat(ri) ? kW6RightFlat : 0u);
             const float* bo = w.box[i];
             dst[2 * i] = make_uint4(__float_as_uint(bo[0]), __float_as_uint(bo[1]), __float_as_uint(bo[2]), __float_as_uint(bo[3]));
-            dst[2 * i + 1] = make_uint4(__float_as_uint(bo[4]), __float_as_uint(bo[5]), (flat ? ((w.lmask[i] >> 1) & kW6SphereMask) : 0u) | (lflat ? kW6LeftFlat : 0u) | (rflat ? kW6RightFlat : 0u), meta);   // flat: which of the following records are its spheres
+            dst[2 * i + 1] = make_uint4(__float_as_uint(bo[4]), __float_as_uint(bo[5]), w6, meta);
         }
         const uint32_t rk = w.meta[0] & 7u;
         flags = (rk >= 3u ? kTileRootLeaf : 0u) | ((rk < 3u && (w.flg[0] & 1u)) ? kTileRootPure : 0u);

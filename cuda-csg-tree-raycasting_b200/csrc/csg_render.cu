@@ -149,7 +149,7 @@ struct csg_context {
     int last_mode = 0;           // shard mode of the last frame (csg_prune_stats)
     bool shard_sync = true;      // sharded frames are started and joined on the device (SyncWords); csg_set_gather_target(pointer) turns it off
     bool view_cache = false;     // csg_set_view_cache
-    int flat_leaves = 16;        // Unions over at most this many spheres are evaluated flat (flat_eval); 0: never
+    int flat_leaves = kFlatLeavesMax;   // Unions over at most this many spheres are evaluated flat (flat_eval); 0: never
     bool external_target = false;   // csg_set_gather_target: pixels go to a buffer that is not rank 0's own framebuffer
     bool prune_alloc = false;    // tile slots were allocated at upload
     int last_rm[4] = {0, 0, 0, 0};   // traced macro-tile rectangle of the last frame (x0, y0, w, h)
@@ -550,7 +550,7 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     CUC(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, devices[0]));
     CUC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devices[0]));
     const size_t tree_bytes = c->tree.nodes.size() * sizeof(NodeRec);
-    const size_t table_bytes = 32 * sizeof(uint32_t);
+    const size_t table_bytes = kSmemHead;   // outcome table, light
     {
         // per-tile pruning: a slot holds up to kSlotMax records (8 KB)
         const size_t n = c->tree.nodes.size();
@@ -1355,6 +1355,13 @@ int csg_fp32_peak_tflops(int device, float* tflops)
 }
 
 #ifdef CSG_FRAME_PROBE
+int csg_debug_sync_probe(int device, void* out8)
+{
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out8, g_sync_probe, sizeof(unsigned long long) * 8));
+    return CSG_OK;
+}
 int csg_debug_frame_probe(void* out, size_t bytes)
 {
     CU(cudaDeviceSynchronize());

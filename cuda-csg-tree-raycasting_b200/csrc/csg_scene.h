@@ -42,14 +42,16 @@ constexpr uint32_t kMetaLeftLeaf = 1u << 3, kMetaRightLeaf = 1u << 4, kMetaBound
 // pure = a Union whose subtree holds only Unions, spheres and cubes (every leaf convex and truly bounded by its box):
 // such a subtree may be evaluated as a nearest-Enter search (csg_render.cu, ST_SEARCH)
 constexpr uint32_t kMetaPure = 1u << 6;
-// flat (per-tile trees only, set by csg_prune_flat_kernel) = a Union over at most PruneParams::flat_max spheres and nothing else:
-// its result at any tmin follows from the spheres' roots alone (flat_eval, csg_kernel.cuh).  Word 6 of such a record = bit mask of
-// the spheres among the records that follow it (bit j: record n + 1 + j; a subtree of k spheres is 2k - 1 records, so k <= 16);
-// bits 30 / 31 of word 6 of ANY operator record of a tile tree say that its left / right operand is such a flat operator (Compute
-// looks there when it loops into an operand).  Records staged from the uploaded tree carry 0 in word 6.
+// flat (per-tile trees only, set by csg_prune_flat_kernel) = a Union over at most PruneParams::flat_max (<= kFlatLeavesMax) spheres
+// and nothing else: its result at any tmin follows from the spheres' roots alone (flat_eval, csg_kernel.cuh).  Word 6 of such a
+// record, bits 0-28: the spheres among the records that follow it (bit j: record n + 1 + j; a subtree of k spheres is 2k - 1
+// records).  Bits 30 / 31 of word 6 of ANY operator record of a tile tree say that its left / right operand is a flat operator
+// (Compute looks there when it loops into an operand).  Records staged from the uploaded tree carry 0 in word 6.
+// (Measured, round 2: flat Unions of up to 30 spheres — two flat operands scanned as one — are slower than two of 15 under an
+// ordinary Union, whose box tests skip half the spheres: 0.170 against 0.166 ms per frame.)
 constexpr uint32_t kMetaFlat = 1u << 7;
-constexpr int kFlatLeavesMax = 16;
-constexpr uint32_t kW6LeftFlat = 1u << 30, kW6RightFlat = 1u << 31, kW6SphereMask = 0x3fffffffu;
+constexpr int kFlatLeavesMax = 15;
+constexpr uint32_t kW6LeftFlat = 1u << 30, kW6RightFlat = 1u << 31, kW6SphereMask = (1u << 29) - 1u;
 
 // Per-primitive data kept in global memory (read on accepted hits / cylinder + cube tests / shading): 5 x float4.
 struct PrimRec {

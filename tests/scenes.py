@@ -29,6 +29,38 @@ INLINE = {
 }
 
 
+def _sphere_chain(seed, n, wrap="Difference\nCube 0 0 0 FFD000 5\n"):
+    """`wrap` around a balanced Union of n overlapping spheres scattered along and around the view axis: long tunnels through
+    the cube, many run extensions — the inputs of the flat evaluation of sphere unions (flat_eval, csg_kernel.cuh)."""
+    import random
+    rnd = random.Random(seed)
+    leaves = [f"Sphere {rnd.uniform(-1.2, 1.2):.4f} {rnd.uniform(-1.2, 1.2):.4f} {rnd.uniform(-3.0, 3.0):.4f} 30A0F0 {rnd.uniform(0.3, 0.9):.4f}"
+              for _ in range(n)]
+
+    def union(xs):
+        if len(xs) == 1:
+            return xs[0]
+        h = len(xs) // 2
+        return "Union\n" + union(xs[:h]) + "\n" + union(xs[h:])
+    return wrap + union(leaves) + "\n"
+
+
+INLINE.update({
+    "sphere_chain_12": _sphere_chain(1, 12),                    # one simple flat Union under a Difference
+    "sphere_chain_26": _sphere_chain(2, 26),                    # a composite flat Union (2 x 13)
+    "sphere_chain_40": _sphere_chain(3, 40),                    # flat Unions below ordinary ones
+    "sphere_union_root": _sphere_chain(4, 14, wrap=""),         # the whole tree is one flat Union
+    "cube_and_spheres": _sphere_chain(5, 18, wrap="Intersection\nCube 0 0 0 FFD000 3\n"),
+    "spheres_minus_sphere": "Difference\n" + _sphere_chain(6, 10, wrap="") + "Sphere 0 0 0 FF0000 1.1\n",   # flat left operand
+})
+
+
+# duplicated and concentric spheres inside a chain: exact ties between roots of different primitives (flat_eval gives up).  Not
+# in INLINE: with exact ties the re-balanced tree (optimize = 1) is not the reference's tree (DESIGN.md 4.3.6); used with optimize = 0.
+DUP_CHAIN = ("Difference\nCube 0 0 0 FFD000 5\nUnion\nUnion\nSphere 0 0 2 FF0000 0.8\nSphere 0 0 2 00FF00 0.8\nUnion\nUnion\n"
+             "Sphere 0 0 1 0000FF 0.8\nSphere 0 0 1 0000FF 0.5\nUnion\nSphere 0.1 0 0.2 FF00FF 0.8\nSphere 0.1 0 0.2 FFFF00 0.8\n")
+
+
 def corpus_names():
     d = oracle_py.SCENES_DIR
     if not os.path.isdir(d):

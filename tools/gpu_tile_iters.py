@@ -8,7 +8,7 @@ import csg_b200 as g
 from oracle_py import scene_text
 W, H = 3840, 2160
 out = {}
-for fl in (0, 16):
+for fl in (0, 30):
     os.environ["CSG_B200_FLAT_LEAVES"] = str(fl)
     sc = g.Scene.parse(scene_text("testCheese512"), optimize=1)
     ctx = sc.upload(W, H)
