@@ -515,6 +515,47 @@ def bench_ours(args):
     barrier()
     e2e_frame = host.arr.copy().reshape(HEIGHT, WIDTH, 4) if rank == 0 else None
 
+    # ---- diagnostic next to e2e: the same device->host copies with no rendering at all (every rank moves its own rows of the
+    # frame from its framebuffer into the shared host frame, all ranks at once) — what the PCIe links and the host memory take
+    d2h_only_s = None
+    try:
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        rt.cudaMemcpy2D.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
+        rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        fb = ctx.framebuffer()
+        row_bytes, n_macro = 32 * WIDTH * 4, (HEIGHT + 31) // 32
+        mine = list(range(rank, n_macro, world))
+        full = [m for m in mine if (m + 1) * 32 <= HEIGHT]
+        ragged = [m for m in mine if (m + 1) * 32 > HEIGHT]
+        spans = []
+        for k in range(8):
+            barrier()
+            host.spin_barrier()
+            t0 = time.monotonic_ns()
+            rc = 0
+            if full:
+                off = full[0] * row_bytes
+                rc |= rt.cudaMemcpy2D(host.ptr + off, world * row_bytes, fb + off, world * row_bytes, row_bytes, len(full), 2)
+            for m in ragged:
+                off = m * row_bytes
+                rc |= rt.cudaMemcpy(host.ptr + off, fb + off, (HEIGHT - m * 32) * WIDTH * 4, 2)
+            t1 = time.monotonic_ns()
+            if rc:
+                raise RuntimeError(f"cudaMemcpy2D failed ({rc})")
+            if k >= 3:
+                spans.append((t0, t1))
+        tt = torch.tensor(spans, dtype=torch.int64, device=env.dev)
+        c0, c1 = tt[:, 0].clone(), tt[:, 1].clone()
+        if dist is not None:
+            dist.all_reduce(c0, op=dist.ReduceOp.MIN)
+            dist.all_reduce(c1, op=dist.ReduceOp.MAX)
+        d2h_only_s = float((c1 - c0).double().mean().item()) * 1e-9
+    except Exception as e:   # diagnostic only
+        d2h_only_s = None
+        if rank == 0:
+            print(f"bench.py: d2h-only diagnostic skipped ({type(e).__name__}: {e})", file=sys.stderr)
+
     # ---- parity of the N-GPU frames with the frame one GPU renders alone (outside the timed regions)
     gathered = job.gathered_frame()
     parity_n = None
@@ -656,6 +697,10 @@ def bench_ours(args):
                    "wall_ms_per_step_incl_flush_and_barriers": wall_ms},
         "e2e": {"value": nrays / e2e_s, "unit": "rays/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 256 * world,
                 "d2h_bytes_per_step": nrays * 4, "steps": e2e_steps, "ms_per_step_slowest_rank_own_call": e2e_own_s * 1e3,
+                "d2h_only_ms": None if d2h_only_s is None else d2h_only_s * 1e3,
+                "d2h_only_note": "diagnostic: the same device->host copies (every rank its own rows, all ranks at once) with no rendering — the PCIe / "
+                                 "host-memory floor of e2e on this box",
+
                 "what": "csg_render() into one page-locked host RGBA8 frame (N > 1: shared memory registered in every rank): camera/light as kernel "
                         "parameters, the frame dealt out in rows of 64x32 tiles, every GPU renders its rows in bands and copies each band D2H over its "
                         "own PCIe link while the next band renders; time = first rank's call -> last rank's return (CLOCK_MONOTONIC)"},

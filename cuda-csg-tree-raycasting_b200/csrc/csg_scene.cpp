@@ -303,6 +303,7 @@ struct Work {  // working tree node
     Box box;
     bool has_cylinder = false;  // some cylinder below: the box only GATES (Q6), it does not bound the hits
     bool pure = false;          // leaf: sphere or cube; operator: Union of two pure subtrees
+    int depth = 0;              // operator levels below and including this node (a primitive: 0)
 };
 
 // Culling box of a leaf.  Culling boxes only decide whether a subtree is skipped; the proof that any box
@@ -351,9 +352,12 @@ float cube_normal_threshold(float half, float level)
     return std::isfinite(a) ? a : 0.0f;
 }
 
+constexpr int kFullOccupancyLevels = 13;   // (13 + 3) frames x 16 B x 768 threads + tree copies = one SM's shared memory (csg_render.cu)
+
 struct Builder {
     const Scene& s;
     std::vector<Work> w;
+    int slack = 2;              // build_union: levels a rebuilt Union subtree may be taller than the shortest tree over its operands
     explicit Builder(const Scene& sc) : s(sc) {}
 
     int add(int type, int prim, int l, int r)
@@ -361,6 +365,7 @@ struct Builder {
         Work n{type, prim, l, r, Box{}, false};
         n.has_cylinder = prim != -1 ? type == kCylinder : (w[l].has_cylinder || w[r].has_cylinder);
         n.pure = prim != -1 ? (type == kSphere || type == kCube) : (type == kUnion && w[l].pure && w[r].pure);
+        n.depth = prim != -1 ? 0 : 1 + std::max(w[l].depth, w[r].depth);
         w.push_back(n);
         return (int)w.size() - 1;
     }
@@ -402,24 +407,68 @@ struct Builder {
         built.reserve(items.size());
         for (int it : items) built.push_back(build_optimized(it));
         for (int b : built) compute_box(b);
-        return build_union(built, 0, (int)built.size());
+        // height budget of the rebuilt subtree: the traversal keeps one frame per operator level in shared memory, so a tall tree
+        // costs resident warps (4096-primitive synthetic scene: 30 levels and 12 warps per SM with count-balanced splits, 12.5 ms;
+        // 12 levels, 24 warps, 8.9 ms as parsed).  The shortest tree over operands of heights d_i has ceil(log2(sum 2^d_i)) levels
+        // (Kraft); `slack` more are allowed so that splits can follow space.
+        int budget = 0;
+        while (std::ldexp(1.0, budget) < kraft(built, 0, (int)built.size())) ++budget;
+        return build_union(built, 0, (int)built.size(), budget + slack);
     }
 
-    // Spatial median split of the operands (largest centroid extent), like a BVH build.
-    int build_union(std::vector<int>& v, int lo, int hi)
+    // sum of 2^height over the operands v[lo, hi): they fit under `levels` operator levels iff this is at most 2^levels
+    double kraft(const std::vector<int>& v, int lo, int hi) const
+    {
+        double k = 0;
+        for (int i = lo; i < hi; ++i) k += std::ldexp(1.0, std::min(w[v[i]].depth, 1000));
+        return k;
+    }
+
+    // Spatial split of the operands like a BVH build: along the axis of largest centroid extent, as close to the median as the
+    // height budget allows (both sides must fit under budget - 1 levels); when no axis has such a position, the operands are dealt
+    // out by height instead (tallest first, to the lighter side), which always fits.
+    int build_union(std::vector<int>& v, int lo, int hi, int budget)
     {
         if (hi - lo == 1) return v[lo];
         float cmn[3] = {INFINITY, INFINITY, INFINITY}, cmx[3] = {-INFINITY, -INFINITY, -INFINITY};
         auto cen = [&](int id, int ax) { return 0.5f * (w[id].box.mn[ax] + w[id].box.mx[ax]); };
         for (int i = lo; i < hi; ++i)
             for (int a = 0; a < 3; ++a) { cmn[a] = std::min(cmn[a], cen(v[i], a)); cmx[a] = std::max(cmx[a], cen(v[i], a)); }
-        int ax = 0;
-        for (int a = 1; a < 3; ++a) if (cmx[a] - cmn[a] > cmx[ax] - cmn[ax]) ax = a;
-        int mid = (lo + hi) / 2;
-        std::nth_element(v.begin() + lo, v.begin() + mid, v.begin() + hi,
-                         [&](int a, int b) { float ca = cen(a, ax), cb = cen(b, ax); return ca < cb || (ca == cb && a < b); });
-        int l = build_union(v, lo, mid);
-        int r = build_union(v, mid, hi);
+        int axes[3] = {0, 1, 2};
+        std::sort(axes, axes + 3, [&](int a, int b) { const float ea = cmx[a] - cmn[a], eb = cmx[b] - cmn[b]; return ea > eb || (ea == eb && a < b); });
+        const double half = std::ldexp(1.0, std::max(budget - 1, 0));
+        const int n = hi - lo, want = (lo + hi) / 2;
+        int mid = -1;
+        std::vector<double> pre((size_t)n + 1);
+        for (int t = 0; t < 3 && mid < 0; ++t) {
+            const int ax = axes[t];
+            std::sort(v.begin() + lo, v.begin() + hi, [&](int a, int b) { float ca = cen(a, ax), cb = cen(b, ax); return ca < cb || (ca == cb && a < b); });
+            pre[0] = 0;
+            for (int i = 0; i < n; ++i) pre[(size_t)i + 1] = pre[(size_t)i] + std::ldexp(1.0, std::min(w[v[lo + i]].depth, 1000));
+            for (int d = 0; d < n && mid < 0; ++d)                       // positions by distance from the median
+                for (int sgn = -1; sgn <= 1 && mid < 0; sgn += 2) {
+                    const int m = want + sgn * d;
+                    if (m <= lo || m >= hi || (d == 0 && sgn == 1)) continue;
+                    if (pre[(size_t)(m - lo)] <= half && pre[(size_t)n] - pre[(size_t)(m - lo)] <= half) mid = m;
+                }
+        }
+        if (mid < 0) {
+            // by height: tallest first, each to the side that is lighter so far (weights are powers of two: both sides end up
+            // within `half` whenever the whole range fits the budget); then the left side's operands first in v
+            std::sort(v.begin() + lo, v.begin() + hi, [&](int a, int b) { return w[a].depth > w[b].depth || (w[a].depth == w[b].depth && a < b); });
+            std::vector<int> left, right;
+            double wl = 0, wr = 0;
+            for (int i = lo; i < hi; ++i) {
+                const double k = std::ldexp(1.0, std::min(w[v[i]].depth, 1000));
+                if (wl <= wr) { left.push_back(v[i]); wl += k; } else { right.push_back(v[i]); wr += k; }
+            }
+            if (right.empty()) { right.push_back(left.back()); left.pop_back(); }
+            std::copy(left.begin(), left.end(), v.begin() + lo);
+            std::copy(right.begin(), right.end(), v.begin() + lo + (long)left.size());
+            mid = lo + (int)left.size();
+        }
+        int l = build_union(v, lo, mid, budget - 1);
+        int r = build_union(v, mid, hi, budget - 1);
         int id = add(kUnion, -1, l, r);
         compute_box_shallow(id);
         return id;
@@ -457,8 +506,21 @@ void flatten(const Scene& s, int optimize, FlatTree& out)
     out.leaf_boxes.clear();
     out.subtree_end.clear();
     if (s.nodes.empty()) return;
+    // optimize >= 1: Union subtrees rebuilt spatially under a height budget; of the slacks 2, 1, 0 the largest that keeps the whole
+    // tree within kFullOccupancyLevels operator levels (up to there the frame kernel keeps 24 warps per SM), else the shortest tree
     Builder b(s);
-    int root = optimize >= 1 ? b.build_optimized(0) : b.copy(0);
+    int root = -1;
+    if (optimize >= 1) {
+        for (int slack = 2; slack >= 0; --slack) {
+            Builder t(s);
+            t.slack = slack;
+            const int r = t.build_optimized(0);
+            if (root < 0 || t.w[r].depth < b.w[root].depth) { b.w = t.w; b.slack = slack; root = r; }
+            if (b.w[root].depth <= kFullOccupancyLevels) break;
+        }
+    } else {
+        root = b.copy(0);
+    }
     b.compute_box(root);
 
     // primitive records
