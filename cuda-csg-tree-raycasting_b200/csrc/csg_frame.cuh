@@ -150,7 +150,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
             // n is a flat operand (a Union over a few spheres) the machine was about to descend into; the frame that takes its
             // result is pushed.  Its result follows from the spheres' roots (flat_eval; the frames above sp are free and hold its
             // list): return it as if the descent had happened — or, when flat_eval gives up, descend after all.
-            const uint2 fe = flat_eval(tree, n, r, tmin, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
+            const uint2 fe = flat_eval((uint32_t)__cvta_generic_to_shared(tree), n, r, tmin, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
             if (fe.y != kFlatGaveUp) { L.t = __uint_as_float(fe.x); L.m = fe.y; R = L; st = ST_RETURN; }
             else st = ST_ENTER;
         }

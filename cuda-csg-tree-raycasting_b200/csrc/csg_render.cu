@@ -428,7 +428,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.lists = s.d_lists; q.order = s.d_order;
             // (heaviest-first hand-out also pays on a frame sharded over 8 GPUs, 2-3 tiles per warp: the slowest of the eight shards
             // takes 63.9 us with it and 67.3 us with the natural order, although shard 0 alone is 3 us faster without the ordering pass)
-            q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes; q.flat_max = c->flat_leaves;
+            q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes; q.flat_max = c->flat_leaves; q.flat_tree_max = fp.warp_tree_nodes;
             q.slots_off32 = (uint32_t)fp.n_nodes; q.full_flags = c->full_flags;
             // view cache (opt-in): same camera, size, sampling and tile set as the trees this shard already holds -> keep them
             // (compared before the gate goes in: its sequence number changes with every frame)
