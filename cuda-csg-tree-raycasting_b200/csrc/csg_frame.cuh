@@ -146,14 +146,6 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     }
     while (st != ST_DONE) {
         if (COUNT) iters += (st == ST_SEARCH) ? (1 << 20) : (st == ST_ENTER) ? (1 << 10) : 1;   // packed: search visits | frame-machine visits | other iterations
-        if (st == ST_FLAT) {
-            // n is a flat operand (a Union over a few spheres) the machine was about to descend into; the frame that takes its
-            // result is pushed.  Its result follows from the spheres' roots (flat_eval; the frames above sp are free and hold its
-            // list): return it as if the descent had happened — or, when flat_eval gives up, descend after all.
-            const uint2 fe = flat_eval((uint32_t)__cvta_generic_to_shared(tree), n, r, tmin, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
-            if (fe.y != kFlatGaveUp) { L.t = __uint_as_float(fe.x); L.m = fe.y; R = L; st = ST_RETURN; }
-            else st = ST_ENTER;
-        }
         if (st <= ST_LOOPR) {
             const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
             const uint32_t op = meta & 7u;
@@ -246,6 +238,15 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                     }
                 }
             }
+        }
+        if (st == ST_FLAT) {
+            // (Behind the operator visit, so that a descent decided there is evaluated in the same round.)
+            // n is a flat operand (a Union over a few spheres) the machine was about to descend into; the frame that takes its
+            // result is pushed.  Its result follows from the spheres' roots (flat_eval; the frames above sp are free and hold its
+            // list): return it as if the descent had happened — or, when flat_eval gives up, descend after all.
+            const uint2 fe = flat_eval((uint32_t)__cvta_generic_to_shared(tree), n, r, tmin, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
+            if (fe.y != kFlatGaveUp) { L.t = __uint_as_float(fe.x); L.m = fe.y; R = L; st = ST_RETURN; }
+            else st = ST_ENTER;
         }
         if (st == ST_COMPUTE) {                                                        // Compute :597-661
             const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);

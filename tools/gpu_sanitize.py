@@ -29,6 +29,10 @@ print(go(g.Scene.generate_text(300, 5), 256, 144))
 print(go(g.Scene.generate_text(300, 5), 256, 144, walk=True))
 print(go(scenes.INLINE["nested"], 200, 120, walk=True))
 print(go(g.Scene.generate_text(300, 5), 256, 144, marks=True, opt=0))
+for name in ("sphere_chain_12", "sphere_chain_40", "sphere_union_root", "spheres_minus_sphere"):   # flat evaluation of sphere unions (flat_eval)
+    print(go(scenes.INLINE[name], 256, 144))
+print(go(scenes.INLINE["sphere_chain_26"], 128, 72, ss=2))
+print(go(scenes.DUP_CHAIN, 160, 90, opt=0))
 if "testCheese256" in scenes.corpus_names():
     print(go(scenes.text_of("corpus:testCheese256"), 320, 180))
 print("done")
