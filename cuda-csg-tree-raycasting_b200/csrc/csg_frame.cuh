@@ -248,31 +248,6 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
             if (fe.y != kFlatGaveUp) { L.t = __uint_as_float(fe.x); L.m = fe.y; R = L; st = ST_RETURN; }
             else st = ST_ENTER;
         }
-        if (st == ST_COMPUTE) {                                                        // Compute :597-661
-            const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
-            const uint32_t op = meta & 7u;
-            const uint32_t e = table[op * 9u + (L.m & H_CLS) * 3u + (R.m & H_CLS)];
-            const uint32_t o = (L.t < R.t) ? (e & 7u) : (L.t > R.t) ? ((e >> 3) & 7u) : ((e >> 6) & 7u);
-            if (o == O_RETL) { R = L; st = ST_RETURN; }
-            else if (o == O_RETR || o == O_RETR_FLIP) {
-                if (o == O_RETR_FLIP) R.m ^= (H_FLIP | 1u);                            // :629-635 toggles Flip and Enter<->Exit
-                L = R; st = ST_RETURN;
-            } else if (o == O_LOOPL) {                                                 // :640-646
-                tmin = L.t;
-                if (meta & kMetaLeftLeaf) st = ST_LOOPL;
-                else {   // into an operator: a flat one (word 6 of this record says so) is evaluated from its spheres' roots
-                    sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride;
-                    st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6LeftFlat) ? ST_FLAT : ST_ENTER; n = n + 32u;
-                }
-            } else if (o == O_LOOPR) {                                                 // :647-653
-                tmin = R.t;
-                if (meta & kMetaRightLeaf) st = ST_LOOPR;
-                else {
-                    sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride;
-                    st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6RightFlat) ? ST_FLAT : ST_ENTER; n = (meta >> 8) << 5;
-                }
-            } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
-        }
         if (st == ST_RETURN) {                  // action = actionStack.pop(); node = GetParent() (:624-625 etc.); L == R == result
             sp -= stack_stride;
             const uint4 f = lds128(sp);
@@ -313,6 +288,32 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                     }
                 }
             }
+        }
+        if (st == ST_COMPUTE) {                                                        // Compute :597-661
+            const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
+            const uint32_t op = meta & 7u;
+            const uint32_t e = table[op * 9u + (L.m & H_CLS) * 3u + (R.m & H_CLS)];
+            const uint32_t o = (L.t < R.t) ? (e & 7u) : (L.t > R.t) ? ((e >> 3) & 7u) : ((e >> 6) & 7u);
+            if (o == O_RETL) { R = L; st = ST_RETURN; }
+            else if (o == O_RETR || o == O_RETR_FLIP) {
+                if (o == O_RETR_FLIP) R.m ^= (H_FLIP | 1u);                            // :629-635 toggles Flip and Enter<->Exit
+                L = R; st = ST_RETURN;
+            } else if (o == O_LOOPL) {                                                 // :640-646
+                tmin = L.t;
+                if (meta & kMetaLeftLeaf) st = ST_LOOPL;
+                else {   // into an operator: a flat one (word 6 of this record says so) is evaluated from its spheres' roots
+                    sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride;
+                    st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6LeftFlat) ? ST_FLAT : ST_ENTER; n = n + 32u;
+                }
+            } else if (o == O_LOOPR) {                                                 // :647-653
+                tmin = R.t;
+                if (meta & kMetaRightLeaf) st = ST_LOOPR;
+                else {
+                    sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride;
+                    st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6RightFlat) ? ST_FLAT : ST_ENTER; n = (meta >> 8) << 5;
+                }
+            } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
+            if (st == ST_RETURN && sp == stack + stack_stride) st = ST_DONE;           // only the sentinel is left: this is the root's result (L == R)
         }
     }
     return L;                                   // :511
