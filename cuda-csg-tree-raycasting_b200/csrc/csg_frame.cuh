@@ -137,7 +137,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     sts128(sp, make_uint4(0u, 0u, 0u, 0xffffffffu)); // sentinel frame: popping it ends the traversal (no base pointer to keep)
     sp += stack_stride;
     int st = ST_ENTER;
-    if (*reinterpret_cast<const uint32_t*>(tree + 28) & kMetaFlat) st = ST_FLAT;   // the whole (tile) tree is one flat Union of spheres
+    if (*reinterpret_cast<const uint32_t*>(tree + 28) & kMetaFlat) { R.t = INFINITY; st = ST_FLAT; }   // the whole (tile) tree is one flat Union of spheres
     else if (root_pure) {                      // the whole scene is one pure subtree
         sts128(sp, make_uint4(0u, 0u, 0u, kSearchMark));
         sp += stack_stride;
@@ -229,7 +229,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                             first = right_first ? cr : cl; fm = right_first ? mB : mA; ftn = right_first ? tnB : tnA;
                         }
                         sp += stack_stride; n = first;
-                        if (fm & kMetaFlat) st = ST_FLAT;
+                        if (fm & kMetaFlat) { R.t = lim; st = ST_FLAT; }   // R is free here: saved in the frame, or a Miss (as for the search below)
                         else if ((fm & kMetaPure) && ftn > tmin) {   // pure subtree ahead of tmin: nearest-Enter search
                             sts128(sp, make_uint4(0u, 0u, first, kSearchMark));
                             sp += stack_stride;
@@ -244,7 +244,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
             // n is a flat operand (a Union over a few spheres) the machine was about to descend into; the frame that takes its
             // result is pushed.  Its result follows from the spheres' roots (flat_eval; the frames above sp are free and hold its
             // list): return it as if the descent had happened — or, when flat_eval gives up, descend after all.
-            const uint2 fe = flat_eval((uint32_t)__cvta_generic_to_shared(tree), n, r, tmin, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
+            const uint2 fe = flat_eval((uint32_t)__cvta_generic_to_shared(tree), n, r, tmin, R.t, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
             if (fe.y != kFlatGaveUp) { L.t = __uint_as_float(fe.x); L.m = fe.y; R = L; st = ST_RETURN; }
             else st = ST_ENTER;
         }
@@ -278,9 +278,9 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                             sib = n + 32u;
                         }
                         sp += stack_stride; n = sib; st = ST_ENTER;
-                        if (f.y & 2u) st = ST_FLAT;
+                        const float lim = (pop != 2u && !miss) ? L.t : INFINITY;
+                        if (f.y & 2u) { R.t = lim; st = ST_FLAT; }
                         else if ((f.y & 1u) && ptn > tmin) {
-                            const float lim = (pop != 2u && !miss) ? L.t : INFINITY;
                             sts128(sp, make_uint4(0u, 0u, sib, kSearchMark));
                             sp += stack_stride;
                             L = make_miss(); R.t = lim; st = ST_SEARCH;
@@ -304,6 +304,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                 else {   // into an operator: a flat one (word 6 of this record says so) is evaluated from its spheres' roots
                     sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride;
                     st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6LeftFlat) ? ST_FLAT : ST_ENTER; n = n + 32u;
+                    R.t = INFINITY;   // flat_eval's limit: none (R is saved in the frame)
                 }
             } else if (o == O_LOOPR) {                                                 // :647-653
                 tmin = R.t;
@@ -311,6 +312,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                 else {
                     sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride;
                     st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6RightFlat) ? ST_FLAT : ST_ENTER; n = (meta >> 8) << 5;
+                    R.t = INFINITY;   // flat_eval's limit: none (R is what gets re-evaluated)
                 }
             } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
             if (st == ST_RETURN && sp == stack + stack_stride) st = ST_DONE;           // only the sentinel is left: this is the root's result (L == R)

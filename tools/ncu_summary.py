@@ -86,6 +86,10 @@ if frame:
     out["dram_bytes_per_launch"] = (rd or 0) + (wr or 0)
     out["note"] = ("dram bytes are per launch of csg_frame_kernel; the 33 MB RGBA8 framebuffer is written into the 126 MB L2 and is "
                    "not evicted to HBM within the launch, so DRAM traffic is far below the 33 MB of algorithmic output bytes")
+# the kernel sources this capture was taken from (bench.py compares it with the sources it runs: roofline.executed.profile_matches_source)
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+out["source_hash"] = bench.source_hash()
 with open(os.path.join(dst, f"{tag}_ncu_summary.json"), "w") as f:
     json.dump(out, f, indent=1)
 shutil.copy(os.path.join(dst, f"{tag}_ncu_summary.json"), os.path.join(dst, "ncu_summary.json"))
