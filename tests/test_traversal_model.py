@@ -609,10 +609,9 @@ def test_prototype_interval_evaluation_of_pure_subtrees_equals_the_reference_mac
     assert checked > 200
 
 
-# ---- PROTOTYPE (measured on the GPU and rejected): flat evaluation of small sphere-only union subtrees -----------
+# ---- flat evaluation of small sphere-only union subtrees: the CPU model of flat_eval (csrc/csg_kernel.cuh) ----------------------
 # A pure subtree of at most FLAT_MAX_LEAVES spheres treated as ONE operand: its result at tmin is worked out from the
-# spheres' roots alone, in passes over the leaves, no tree walk and no stack (the interval semantics of the prototype above, but
-# nothing is re-tested through the machine):
+# spheres' roots alone, in passes over the leaves, no tree walk and no stack:
 #   every sphere the ray meets has a near root t1 and a far root t2 (sphereHit's own values);
 #   t1 > tmin: an Enter ahead.  Without a run it is a candidate for the nearest Enter; with a run that reaches beyond it, it is
 #              part of the run and its far root extends the run;
@@ -620,11 +619,12 @@ def test_prototype_interval_evaluation_of_pure_subtrees_equals_the_reference_mac
 #   passes repeat until the run stops growing.  No run: the nearest Enter (or Miss).  Run: the Exit that ends it.
 # It gives up — and the subtree is evaluated by the frame machine as before — on every exact tie that involves the run's end or
 # the nearest Enter, and on every abnormal classification (a near root that is not an Enter, a far root that is not an Exit).
-# RESULT: exact (the test below: Cheese256/512, sphere chains, duplicated spheres — bit-identical to the reference machine, the
-# tie cases give up as intended), and on the B200 also bit-identical over all GPU tests — but SLOWER than the tree machine: a warp
-# runs a sphere's full path as soon as one of its 32 rays meets it, so a pass costs ~k x the full test, while the machine's box
-# culling and the search's limit touch 2-3 spheres per ray (Cheese512 @ 4K frame kernel: 0.155 ms -> 0.164 ms with every flat
-# subtree evaluated this way, 0.172 ms when only subtrees entered with tmin inside them are).  Kept as a record of the semantics.
+# This is the semantics the kernel's flat_eval implements (round 2; there the roots are computed once and kept in a list, the
+# nearest Enter is found during the scan, spheres beyond the caller's limit are dropped early, and flat operands hold at most 15
+# spheres).  The test below pins it to the reference machine on the CPU: Cheese256/512, sphere chains, duplicated spheres —
+# bit-identical, the tie cases give up as intended; tests/test_gpu_parity.py::test_flat_evaluation_of_sphere_unions_is_exact does
+# the same for the kernel.  (A first GPU version that recomputed the roots in every pass was slower than the tree machine and had
+# been recorded as rejected; the list is what made it pay.)
 FLAT_MAX_LEAVES = 24
 GIVE_UP = "give up"
 
