@@ -20,6 +20,6 @@ P
   tail -2 gpurun_out/l_bench_$TAG.err | cut -c1-300
 }
 run 8 8 --steps 20
-CSG_B200_FLAT_LEAVES=0 run 8 8_noflat --steps 20 --no-configs
-run 4 4 --steps 20 --no-configs
-run 2 2 --steps 20 --no-configs
+run 4 4 --steps 20
+run 2 2 --steps 20
+

@@ -21,7 +21,7 @@ src = [r[1].strip() for r in L]
 tot = sum(c)
 exits = [k for k, s in enumerate(src) if s.split()[-1] == "EXIT" or s == "EXIT"]
 main_end = exits[-1]
-hot = [k for k in range(main_end) if c[k] > 2.5 * c[0] * 24]          # executed far more often than once per warp and ticket: the traversal loop
+hot = [k for k in range(main_end) if c[k] > 2.2 * max(c[:main_end][600:1100] or [1])]          # executed far more often than once per warp and ticket: the traversal loop
 def line(name, a, b):
     n = sum(c[a:b + 1])
     print(f"{name:34s} instr {a:5d}-{b:5d}  {n:11d} warp instructions  {100 * n / tot:5.1f} %")
