@@ -285,3 +285,49 @@ def test_prefix_sum_pruning_equals_the_recursive_collapse(scene_id, optimize, cs
                 assert i + 1 < ri < len(got)
     if scene_id == "inline:nested":
         assert saw_rounds >= 2    # an Intersection / Difference that went away took primitives from its ancestors
+
+
+def _operator_levels(rec):
+    meta = rec[:, 7]
+    kind = meta & 7
+
+    def walk(i):
+        if int(kind[i]) >= 3:
+            return 0, [int(meta[i] >> 8)]
+        dl, pl = walk(i + 1)
+        dr, pr = walk(int(meta[i] >> 8))
+        return 1 + max(dl, dr), pl + pr
+    return walk(0)
+
+
+@pytest.mark.parametrize("n_prims,seed", [(4096, 1234), (1000, 7), (200, 13), (37, 3)])
+def test_rebalancing_respects_the_height_budget(n_prims, seed, csg):
+    """Load-time re-balancing (csg_scene.cpp build_union) rebuilds Union subtrees spatially under a height budget: the frame
+    kernel keeps one 16-byte frame per operator level in shared memory, so a tall tree costs resident warps (the 4096-primitive
+    synthetic tree: 30 levels and 12 warps per SM with count-balanced splits, 12 levels and 24 warps now).  The rebuilt tree never
+    needs more than 13 levels when the parsed one fits in 13, keeps every primitive, and only re-associates Unions."""
+    import sys
+    sys.setrecursionlimit(20000)
+    txt = csg.Scene.generate_text(n_prims, seed=seed)
+    rec0, _, depth0, nn, npr = flat(csg, txt, 0)
+    rec1, _, depth1, _, _ = flat(csg, txt, 1)
+    lv0, prims0 = _operator_levels(rec0)
+    lv1, prims1 = _operator_levels(rec1)
+    assert (lv0, lv1) == (depth0, depth1)
+    assert sorted(prims0) == sorted(prims1) == list(range(npr))
+    assert depth1 <= max(13, depth0), f"re-balanced tree has {depth1} levels, the parsed one {depth0}"
+    kinds0 = np.bincount(rec0[:, 7] & 7, minlength=6)
+    kinds1 = np.bincount(rec1[:, 7] & 7, minlength=6)
+    assert (kinds0 == kinds1).all()                                         # same operators, same primitives
+
+
+def test_rebalancing_keeps_a_chain_of_unions_short(csg):
+    """A left-deep chain of 300 Unions over spheres (depth 300 as parsed) comes out balanced: ceil(log2 301) + slack levels."""
+    import sys
+    sys.setrecursionlimit(20000)
+    leaves = [f"Sphere {0.1 * k:.3f} 0 0 FF0000 0.3" for k in range(301)]
+    txt = ("Union\n" * 300 + leaves[0] + "\n" + "\n".join(leaves[1:]) + "\n").encode()
+    rec0, _, depth0, _, _ = flat(csg, txt, 0)
+    rec1, _, depth1, _, _ = flat(csg, txt, 1)
+    assert depth0 == 300
+    assert 9 <= depth1 <= 11
