@@ -27,7 +27,7 @@ EXPORTS = [
     "csg_launch_count", "csg_framebuffer", "csg_framebuffer_ipc_handle", "csg_set_gather_target_ipc",
     "csg_set_gather_target", "csg_read_framebuffer", "csg_device_tan_half_fov", "csg_fp32_peak_tflops", "csg_context_info",
     "csg_last_error", "csg_version", "csg_cube_normal_threshold", "csg_shard_tile",
-    "csg_pin_host_buffer", "csg_unpin_host_buffer", "csg_set_gather_root",
+    "csg_pin_host_buffer", "csg_unpin_host_buffer", "csg_set_gather_root", "csg_stream",
 ]
 
 
@@ -85,6 +85,7 @@ def _load():
         "csg_sync": (i, [vp]),
         "csg_last_frame_ms": (i, [vp, C.POINTER(f)]),
         "csg_launch_count": (C.c_uint64, [vp]),
+        "csg_stream": (i, [vp, C.POINTER(vp)]),
         "csg_framebuffer": (i, [vp, C.POINTER(vp)]),
         "csg_framebuffer_ipc_handle": (i, [vp, vp]),
         "csg_set_gather_target_ipc": (i, [vp, vp]),
@@ -354,6 +355,12 @@ class Context:
 
     def launch_count(self):
         return int(lib.csg_launch_count(self.h))
+
+    def stream(self):
+        """cudaStream_t (as an integer) the root GPU's share of a frame is enqueued on (csg_stream)."""
+        p = C.c_void_p()
+        _check(lib.csg_stream(self.h, C.byref(p)))
+        return p.value or 0
 
     def framebuffer(self):
         p = C.c_void_p()

@@ -103,24 +103,20 @@ __device__ __forceinline__ uint32_t to_u8(float c)
 //   * when the first child returns a hit at t and the pending sibling's box starts beyond t, the sibling cannot change
 //     the outcome (Union: every cell with a farther Enter or a Miss on the other side returns this hit; Difference: same
 //     for the right operand) and is skipped;
-//   * nearest-Enter search (ST_SEARCH): a "pure" subtree (Unions over spheres/cubes only) whose box lies ahead of tmin is
-//     evaluated as a closest-hit BVH search with a shrinking limit instead of the frame machine.  With every leaf result an
-//     Enter or a Miss, each Union of the subtree returns the nearer Enter (EE lt/gt, EM, ME cells), i.e. the subtree returns
-//     its globally nearest Enter; the search aborts — and the subtree is re-evaluated by the frame machine — as soon as a
-//     leaf reports an Exit or two leaves tie for the nearest hit (the only inputs on which the cells differ from "min").
-//     The limit starts at the hit already known on the other side of the parent when every farther Enter (or a Miss) of
-//     this side gives the same parent outcome (Union either side, Difference right side): such results are equivalent, so
-//     subtrees beyond the limit need not be looked at.
-constexpr uint32_t kSearchMark = 0xfffffffeu;
+//   * flat operands (ST_FLAT): a Union over a few spheres is evaluated from the spheres' roots (flat_eval, csg_kernel.cuh).
+// (Rounds 1-2 also had a nearest-Enter search for pure union subtrees — a closest-hit descent with a shrinking limit that fell back
+// to the frame machine on an Exit or a tie.  With per-tile trees, sibling pruning and flat operands it had become a loss on every
+// BASELINE config — Cheese512 0.1499 -> 0.1436 ms, configs[4] 8.91 -> 8.17 ms without it — and was removed; the pure flag of the
+// tree records remains.)
 
 template <bool COUNT>
 __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, const float4* __restrict__ prims,
                                         const uint32_t* __restrict__ table, const uint32_t stack,
-                                        const uint32_t stack_stride, const int& stack_levels, const Ray& r, const bool root_is_leaf, const bool root_pure,
+                                        const uint32_t stack_stride, const int& stack_levels, const Ray& r, const bool root_is_leaf,
                                         const bool root_gated, int& iters)
 {
-    enum { ST_ENTER = 0, ST_SEARCH = 1, ST_LOOPL = 2, ST_LOOPR = 3, ST_COMPUTE = 4, ST_RETURN = 5, ST_DONE = 6, ST_FLAT = 7 };
-    Hit L = make_miss(), R = make_miss();      // ST_SEARCH: L = nearest Enter so far, R.t = limit
+    enum { ST_ENTER = 0, ST_LOOPL = 1, ST_LOOPR = 2, ST_COMPUTE = 3, ST_RETURN = 4, ST_DONE = 5, ST_FLAT = 6 };
+    Hit L = make_miss(), R = make_miss();      // ST_FLAT: R.t = the limit beyond which an Enter need not be found
     float tmin = 0.0f;                        // :466
     if (root_is_leaf) {
         // The scene's root is a primitive: GoTo's leaf branch on the virtual root, no box test (:582-594, Q7).
@@ -138,14 +134,8 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
     sp += stack_stride;
     int st = ST_ENTER;
     if (*reinterpret_cast<const uint32_t*>(tree + 28) & kMetaFlat) { R.t = INFINITY; st = ST_FLAT; }   // the whole (tile) tree is one flat Union of spheres
-    else if (root_pure) {                      // the whole scene is one pure subtree
-        sts128(sp, make_uint4(0u, 0u, 0u, kSearchMark));
-        sp += stack_stride;
-        R.t = INFINITY;
-        st = ST_SEARCH;
-    }
     while (st != ST_DONE) {
-        if (COUNT) iters += (st == ST_SEARCH) ? (1 << 20) : (st == ST_ENTER) ? (1 << 10) : 1;   // packed: search visits | frame-machine visits | other iterations
+        if (COUNT) iters += (st == ST_ENTER) ? (1 << 10) : 1;   // packed: (bits 20+: unused since the search is gone) | operator visits | other iterations
         if (st <= ST_LOOPR) {
             const uint32_t meta = *reinterpret_cast<const uint32_t*>(tree + n + 28);
             const uint32_t op = meta & 7u;
@@ -154,54 +144,17 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
             bool goA = false, goB = false;
             float tnA = -INFINITY, tnB = -INFINITY;
             uint32_t mA = 0u, mB = 0u;
-            if (st != ST_LOOPR) eval_child(tree, prims, cl, r, tmin, st <= ST_SEARCH, a, goA, tnA, mA);
+            if (st != ST_LOOPR) eval_child(tree, prims, cl, r, tmin, st == ST_ENTER, a, goA, tnA, mA);
             if (st == ST_ENTER && op != 0u && !goA && is_miss(a)) {
                 // left operand of a Difference/Intersection already missed: the node's result is Miss whatever the right
                 // operand does (all M* cells of both tables, :670-677) — skip the right subtree (Q8)
                 L = a; R = a;
                 st = ST_RETURN;
             } else {
-                if (st != ST_LOOPL) eval_child(tree, prims, cr, r, tmin, st <= ST_SEARCH, b, goB, tnB, mB);
+                if (st != ST_LOOPL) eval_child(tree, prims, cr, r, tmin, st == ST_ENTER, b, goB, tnB, mB);
                 if (st == ST_LOOPL) { L = a; st = ST_COMPUTE; }
                 else if (st == ST_LOOPR) { R = b; st = ST_COMPUTE; }
-                else if (st == ST_SEARCH) {
-                    // leaf results are candidates; an Exit or a tie for the nearest hit ends the search
-                    bool abort = false;
-                    float lim = R.t;
-                    if (!is_miss(a)) {
-                        if ((a.m & H_CLS) == H_EXIT) abort = true;
-                        else if (a.t < lim) { L = a; lim = a.t; }
-                        else if (a.t == lim) { if (is_miss(L)) L = a; else abort = true; }
-                    }
-                    if (!is_miss(b)) {
-                        if ((b.m & H_CLS) == H_EXIT) abort = true;
-                        else if (b.t < lim) { L = b; lim = b.t; }
-                        else if (b.t == lim) { if (is_miss(L)) L = b; else abort = true; }
-                    }
-                    R.t = lim;
-                    if (abort) {                 // back to the subtree's root, this time through the frame machine
-                        uint4 f;
-                        do { sp -= stack_stride; f = lds128(sp); } while (f.w != kSearchMark);
-                        n = f.z; st = ST_ENTER;
-                    } else {
-                        goA = goA && !(tnA > lim);
-                        goB = goB && !(tnB > lim);
-                        if (goA && goB) {
-                            const bool right_first = tnB < tnA;
-                            sts128(sp, make_uint4(__float_as_uint(right_first ? tnA : tnB), 0u, 0u, right_first ? cl : cr));
-                            sp += stack_stride; n = right_first ? cr : cl;
-                        } else if (goA) { n = cl; }
-                        else if (goB) { n = cr; }
-                        else {
-                            for (;;) {
-                                sp -= stack_stride;
-                                const uint4 f = lds128(sp);
-                                if (f.w == kSearchMark) { R = L; st = ST_RETURN; break; }   // the subtree's result: nearest Enter or Miss
-                                if (!(__uint_as_float(f.x) > lim)) { n = f.w; break; }
-                            }
-                        }
-                    }
-                } else {
+                else {
                     L = a; R = b;
                     // sibling pruning against a leaf hit that is already known
                     if (op != 2u) {
@@ -212,29 +165,24 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                         st = ST_COMPUTE;                                                   // :578
                     } else {
                         uint32_t first, fm;   // subtree to descend into now, and its meta word
-                        float ftn, lim = INFINITY;
+                        float lim = INFINITY;
                         if (!goA) {                                                        // :556-561
                             sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n));
-                            first = cr; fm = mB; ftn = tnB;
+                            first = cr; fm = mB;
                             if (op != 2u && !is_miss(L)) lim = L.t;
                         } else if (!goB) {                                                 // :562-567
                             sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n));
-                            first = cl; fm = mA; ftn = tnA;
+                            first = cl; fm = mA;
                             if (op == 0u && !is_miss(R)) lim = R.t;
                         } else {                                                           // :568-574
                             const bool right_first = (op == 0u) && (tnB < tnA);
-                            const uint32_t pend_pure = ((right_first ? mA : mB) >> 6) & 3u;   // bit 0: the pending operand is pure, bit 1: flat
-                            sts128(sp, make_uint4(__float_as_uint(tmin), (right_first ? F_FIRST_RGH : F_FIRST_LFT) | pend_pure,
+                            const uint32_t pend_flat = ((right_first ? mA : mB) >> 6) & 2u;   // bit 1: the pending operand is flat
+                            sts128(sp, make_uint4(__float_as_uint(tmin), (right_first ? F_FIRST_RGH : F_FIRST_LFT) | pend_flat,
                                              __float_as_uint(right_first ? tnA : tnB), n));
-                            first = right_first ? cr : cl; fm = right_first ? mB : mA; ftn = right_first ? tnB : tnA;
+                            first = right_first ? cr : cl; fm = right_first ? mB : mA;
                         }
                         sp += stack_stride; n = first;
-                        if (fm & kMetaFlat) { R.t = lim; st = ST_FLAT; }   // R is free here: saved in the frame, or a Miss (as for the search below)
-                        else if ((fm & kMetaPure) && ftn > tmin) {   // pure subtree ahead of tmin: nearest-Enter search
-                            sts128(sp, make_uint4(0u, 0u, first, kSearchMark));
-                            sp += stack_stride;
-                            L = make_miss(); R.t = lim; st = ST_SEARCH;
-                        }
+                        if (fm & kMetaFlat) { R.t = lim; st = ST_FLAT; }   // R is free here: saved in the frame, or a Miss
                     }
                 }
             }
@@ -280,11 +228,6 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                         sp += stack_stride; n = sib; st = ST_ENTER;
                         const float lim = (pop != 2u && !miss) ? L.t : INFINITY;
                         if (f.y & 2u) { R.t = lim; st = ST_FLAT; }
-                        else if ((f.y & 1u) && ptn > tmin) {
-                            sts128(sp, make_uint4(0u, 0u, sib, kSearchMark));
-                            sp += stack_stride;
-                            L = make_miss(); R.t = lim; st = ST_SEARCH;
-                        }
                     }
                 }
             }
@@ -455,9 +398,14 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     // one warp, and the per-ticket set-up (descriptor, tree copy) is still shared by a few passes.
     const int sp = kSuper ? p.sp_shift : 0, gp = kSuper ? p.sp_group : 0;
     // RaycastKernel :11-27 + Ray ctor (Ray.cuh:12-18): direction of the ray through virtual pixel (vx, vy)
-    auto make_ray = [&p](int vx, int vy, Ray& ray) {
-        const float u = __fdiv_rn(__fadd_rn((float)vx, 0.5f), p.wm1);
-        const float v = __fdiv_rn(__fadd_rn((float)vy, 0.5f), p.hm1);
+    // (x + 0.5) / (w - 1), (y + 0.5) / (h - 1): numerators in [0.5, 2^24]; with divisors in [1, 2^24] (uv_fast, uniform) the IEEE
+    // quotients come from refined reciprocals of the two frame constants (div_shared, csg_kernel.cuh) — same bits as __fdiv_rn
+    const bool uv_fast = p.wm1 >= 1.0f && p.wm1 <= 16777216.0f && p.hm1 >= 1.0f && p.hm1 <= 16777216.0f;
+    auto make_ray = [&p, uv_fast](int vx, int vy, Ray& ray) {
+        const float un = __fadd_rn((float)vx, 0.5f), vn = __fadd_rn((float)vy, 0.5f);
+        float u, v;
+        if (uv_fast) { u = div_shared(un, p.wm1, rcp_refined(p.wm1)); v = div_shared(vn, p.hm1, rcp_refined(p.hm1)); }
+        else { u = __fdiv_rn(un, p.wm1); v = __fdiv_rn(vn, p.hm1); }
         const float nx = __fmul_rn(__fmul_rn(p.aspect, __fmaf_rn(u, 2.0f, -1.0f)), p.tan_half_fov);
         const float ny = __fmul_rn(__fsub_rn(1.0f, __fadd_rn(v, v)), p.tan_half_fov);
         float cx = __fadd_rn(p.forward[0], __fmaf_rn(p.right[0], nx, __fmul_rn(p.up[0], ny)));
@@ -589,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                         const int sx = sp ? (sl & (ss - 1)) : s - sy * ss;
                         make_ray(x * ss + sx, y * ss + sy, r);
                         res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), p.stack_levels, r, (td.z & kTileRootLeaf) != 0u,
-                                                        (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
+                                                        p.root_is_leaf == 0, iters);
                         if (MODE != OUT_AOV) {
                             const float4 c = shade_pixel(res, r, p.prims, p, s_light);
                             const uint4 a = lds128(my_scratch);
@@ -602,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                 } else {
                     r.dx = r0.dx; r.dy = r0.dy; r.dz = r0.dz; r.ix = r0.ix; r.iy = r0.iy; r.iz = r0.iz;
                     res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), p.stack_levels, r, (td.z & kTileRootLeaf) != 0u,
-                                                    (td.z & kTileRootPure) != 0u, p.root_is_leaf == 0, iters);
+                                                    p.root_is_leaf == 0, iters);
                     if (lane == __ffs(amask) - 1)   // the tile is traced: ask for the next ticket now
                         next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
                     if (MODE != OUT_AOV) {

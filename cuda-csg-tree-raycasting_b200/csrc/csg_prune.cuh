@@ -26,8 +26,11 @@ __device__ __forceinline__ void stage_record(const uint4 ua, const uint4 ub, flo
         a.x = __fsub_rn(a.x, ox); a.y = __fsub_rn(a.y, oy); a.z = __fsub_rn(a.z, oz);
         a.w = __fsub_rn(a.w, ox); b.x = __fsub_rn(b.x, oy); b.y = __fsub_rn(b.y, oz);
     }
+    uint32_t meta = ub.w;
+    if ((meta & 7u) == 5u && div_safe(a.x) && div_safe(a.y) && div_safe(a.z) && div_safe(a.w) && div_safe(b.x) && div_safe(b.y))
+        meta |= kMetaCubeSafe;   // cube_isect may divide through shared reciprocals
     oa = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
-    ob = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), (ub.w & 7u) < 3u ? 0u : ub.z, ub.w);   // operators: no flat-evaluation flags (word 6, csg_scene.h)
+    ob = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), (ub.w & 7u) < 3u ? 0u : ub.z, meta);   // operators: no flat-evaluation flags (word 6, csg_scene.h)
 }
 
 // culling box of a node relative to the origin: operators, cubes, cylinders carry it; spheres: centre +- r, padded like the host does

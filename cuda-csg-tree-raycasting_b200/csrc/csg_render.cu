@@ -394,7 +394,6 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
     for (size_t k = c->shards.size(); k-- > 0;) {
         Shard& s = c->shards[k];
         CU(cudaSetDevice(s.device));
-        if (&s == &root && c->band_m0 == 0) CU(cudaEventRecord(root.ev_start, root.stream));   // later bands of a banded frame keep the first band's start mark
         FrameParams fp;
         fill_params(c, s, cam, light, shard_mode, fp);
         if (&s == &root) { c->last_rm[0] = fp.rm_x0; c->last_rm[1] = fp.rm_y0; c->last_rm[2] = fp.rm_h ? fp.rm_w : 0; c->last_rm[3] = fp.rm_h; }
@@ -437,6 +436,9 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             s.last_q_valid = true;
             q.gate = gate;
             const int stage_ctas = std::max(1, std::min(64, (fp.n_nodes + kPruneThreads - 1) / kPruneThreads));
+            // the frame's start mark goes in right in front of its first launch (all host-side preparation is done by now: on an
+            // idle GPU whatever the host does between the two calls would show up as device time)
+            if (&s == &root && c->band_m0 == 0) CU(cudaEventRecord(root.ev_start, root.stream));   // later bands of a banded frame keep the first band's start mark
             if (!cached) {
                 if (c->prune_flat && c->flat_ok) {
                     // CTA size by the number of tiles: with few tiles per SM the per-tile latency is what the frame waits for
@@ -951,6 +953,13 @@ int csg_last_frame_ms(csg_context* ctx, float* ms)
         if (rc) return rc;
     }
     *ms = ctx->last_ms;
+    return CSG_OK;
+}
+
+int csg_stream(csg_context* ctx, void** cuda_stream)
+{
+    if (!ctx || !cuda_stream || ctx->shards.empty()) return fail(CSG_ERR_ARG, "null argument");
+    *cuda_stream = (void*)ctx->shards[0].stream;
     return CSG_OK;
 }
 

@@ -157,6 +157,11 @@ int csg_sync(csg_context* ctx);
 /* CUDA-event time (ms) of the last completed csg_render_enqueue / csg_render* call: first kernel start to
  * framebuffer complete on the root device. */
 int csg_last_frame_ms(csg_context* ctx, float* ms);
+/* The CUDA stream (a cudaStream_t, on the context's root device) that csg_render_enqueue puts the root GPU's share of a frame on.
+ * Work a caller queues there itself — unmapping a GL buffer as RenderManager.cpp:58-84 does around Raycast, a post-process, a
+ * benchmark's cache flush — is ordered against the frames on the device, without a host round trip; with work queued ahead of
+ * it a frame's launches are already waiting when the GPU gets to them (the steady state of a render loop). */
+int csg_stream(csg_context* ctx, void** cuda_stream);
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 uint64_t csg_launch_count(const csg_context* ctx);
 /* Device pointer of the context's own RGBA8 framebuffer (valid until csg_free_context). */

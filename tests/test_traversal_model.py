@@ -2,8 +2,8 @@
 
 `traverse()` (csrc/csg_frame.cuh) is the reference's action machine (CSGRayCast / GoTo / Compute, RaycastingKernels.cu:459-661)
 re-expressed as an explicit-frame evaluation with result-preserving additions: nearer-child-first unions, sibling pruning
-against a known hit, the Difference/Intersection short-circuit (Q8), the nearest-Enter search of pure union subtrees with exact
-fallback, tighter culling boxes, load-time re-balancing.  This file restates THAT CONTROL FLOW in Python, on the flattened tree
+against a known hit, the Difference/Intersection short-circuit (Q8), tighter culling boxes, load-time re-balancing (the
+nearest-Enter search of rounds 1-2 is gone from the kernel and from this model).  This file restates THAT CONTROL FLOW in Python, on the flattened tree
 `csg_scene_flatten` produces, with the primitive tests taken from the oracle (orc_hit_primitive: the reference's intersectors),
 and checks it against the oracle's restatement of the reference machine, ray by ray: hit mask, primitive id and every bit of t.
 
@@ -127,17 +127,12 @@ class Model:
         meta = self.meta
         if (int(meta[0]) & 7) >= 3:                      # the scene is one primitive: no box test (Q7)
             return self.leaf(0, d, 0.0, False)
-        ST_ENTER, ST_SEARCH, ST_LOOPL, ST_LOOPR, ST_COMPUTE, ST_RETURN, ST_DONE = range(7)
+        ST_ENTER, ST_LOOPL, ST_LOOPR, ST_COMPUTE, ST_RETURN, ST_DONE = range(6)
         L, R = Hit(), Hit()
-        lim = INF                                        # ST_SEARCH: L = nearest Enter so far, lim = search limit (R.t in the kernel)
         tmin = 0.0
         n = 0
         stack = [("sentinel",)]
         st = ST_ENTER
-        if int(meta[0]) & PURE:
-            stack.append(("mark", 0))
-            lim = INF
-            st = ST_SEARCH
         rounds = 0
         while st != ST_DONE:
             rounds += 1
@@ -156,13 +151,13 @@ class Model:
                 tnA = tnB = -INF
                 mA = mB = 0
                 if st != ST_LOOPR:
-                    a, goA, tnA, mA = self.eval_child(cl, d, dd, tmin, st <= ST_SEARCH)
+                    a, goA, tnA, mA = self.eval_child(cl, d, dd, tmin, st == ST_ENTER)
                 if st == ST_ENTER and op != K_UNION and not goA and a.miss:
                     L, R = a.copy(), a.copy()            # Q8: left operand of a Difference/Intersection missed
                     st = ST_RETURN
                 else:
                     if st != ST_LOOPL:
-                        b, goB, tnB, mB = self.eval_child(cr, d, dd, tmin, st <= ST_SEARCH)
+                        b, goB, tnB, mB = self.eval_child(cr, d, dd, tmin, st == ST_ENTER)
                     if st == ST_LOOPL:
                         if goA:                           # a flat subtree that gave up: descend into it like into any operator
                             stack.append(("load_r", R.copy(), n))
@@ -177,46 +172,6 @@ class Model:
                         else:
                             R = b
                             st = ST_COMPUTE
-                    elif st == ST_SEARCH:
-                        abort = False
-                        for h in (a, b):
-                            if h.miss:
-                                continue
-                            if h.cls == EXIT:
-                                abort = True
-                            elif h.t < lim:
-                                L, lim = h, h.t
-                            elif h.t == lim:
-                                if L.miss:
-                                    L = h
-                                else:
-                                    abort = True
-                        if abort:                         # back to the subtree's root, through the frame machine this time
-                            while stack[-1][0] != "mark":
-                                stack.pop()
-                            n = stack.pop()[1]
-                            st = ST_ENTER
-                        else:
-                            goA = goA and not (tnA > lim)
-                            goB = goB and not (tnB > lim)
-                            if goA and goB:
-                                right_first = tnB < tnA
-                                stack.append(("pending", tnA if right_first else tnB, cl if right_first else cr))
-                                n = cr if right_first else cl
-                            elif goA:
-                                n = cl
-                            elif goB:
-                                n = cr
-                            else:
-                                while True:
-                                    fr = stack.pop()
-                                    if fr[0] == "mark":
-                                        R = L.copy()
-                                        st = ST_RETURN
-                                        break
-                                    if not (fr[1] > lim):
-                                        n = fr[2]
-                                        break
                     else:                                 # ST_ENTER
                         L, R = a, b
                         if op != K_INTER:                 # sibling pruning against a leaf hit that is already known
@@ -227,27 +182,17 @@ class Model:
                         if not goA and not goB:
                             st = ST_COMPUTE
                         else:
-                            slim = INF
                             if not goA:
                                 stack.append(("load_l", L.copy(), n))
-                                first, fm, ftn = cr, mB, tnB
-                                if op != K_INTER and not L.miss:
-                                    slim = L.t
+                                first = cr
                             elif not goB:
                                 stack.append(("load_r", R.copy(), n))
-                                first, fm, ftn = cl, mA, tnA
-                                if op == K_UNION and not R.miss:
-                                    slim = R.t
+                                first = cl
                             else:
                                 right_first = op == K_UNION and tnB < tnA
-                                pend_pure = bool((mA if right_first else mB) & PURE)
-                                stack.append(("first_r" if right_first else "first_l", tmin, pend_pure, tnA if right_first else tnB, n))
-                                first, fm, ftn = (cr, mB, tnB) if right_first else (cl, mA, tnA)
+                                stack.append(("first_r" if right_first else "first_l", tmin, tnA if right_first else tnB, n))
+                                first = cr if right_first else cl
                             n = first
-                            if (fm & PURE) and ftn > tmin:   # pure subtree ahead of tmin: nearest-Enter search
-                                stack.append(("mark", first))
-                                L, lim = Hit(), slim
-                                st = ST_SEARCH
             if st == ST_COMPUTE:
                 m = int(meta[n])
                 e = TABLE[m & 7][L.cls][R.cls]
@@ -287,7 +232,7 @@ class Model:
                 elif fr[0] == "load_r":
                     R, n, st = fr[1], fr[2], ST_COMPUTE
                 else:                                     # first_l / first_r: the other operand is still pending (SaveLft)
-                    _, tmin, pend_pure, ptn, n = fr
+                    _, tmin, ptn, n = fr
                     pm = int(meta[n])
                     pop = pm & 7
                     miss = L.miss
@@ -301,11 +246,6 @@ class Model:
                             stack.append(("load_r", R.copy(), n))
                             sib = n + 1
                         n, st = sib, ST_ENTER
-                        if pend_pure and ptn > tmin:
-                            slim = L.t if (pop != K_INTER and not miss) else INF
-                            stack.append(("mark", sib))
-                            L, lim = Hit(), slim
-                            st = ST_SEARCH
         return L
 
 
