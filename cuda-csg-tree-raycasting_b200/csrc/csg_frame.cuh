@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t to_u8(float c)
 //   * when the first child returns a hit at t and the pending sibling's box starts beyond t, the sibling cannot change
 //     the outcome (Union: every cell with a farther Enter or a Miss on the other side returns this hit; Difference: same
 //     for the right operand) and is skipped;
-//   * flat operands (ST_FLAT): a Union over a few spheres is evaluated from the spheres' roots (flat_eval, csg_kernel.cuh).
+//   * flat operands (ST_FLAT): a Union over a few spheres is evaluated from the spheres' roots (flat_spheres, csg_kernel.cuh).
 // (Rounds 1-2 also had a nearest-Enter search for pure union subtrees — a closest-hit descent with a shrinking limit that fell back
 // to the frame machine on an Exit or a tie.  With per-tile trees, sibling pruning and flat operands it had become a loss on every
 // BASELINE config — Cheese512 0.1499 -> 0.1436 ms, configs[4] 8.91 -> 8.17 ms without it — and was removed; the pure flag of the
@@ -190,9 +190,9 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
         if (st == ST_FLAT) {
             // (Behind the operator visit, so that a descent decided there is evaluated in the same round.)
             // n is a flat operand (a Union over a few spheres) the machine was about to descend into; the frame that takes its
-            // result is pushed.  Its result follows from the spheres' roots (flat_eval; the frames above sp are free and hold its
-            // list): return it as if the descent had happened — or, when flat_eval gives up, descend after all.
-            const uint2 fe = flat_eval((uint32_t)__cvta_generic_to_shared(tree), n, r, tmin, R.t, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
+            // result is pushed.  Its result follows from the spheres' roots (flat_spheres; the frames above sp are free and hold its
+            // list): return it as if the descent had happened — or, when flat_spheres gives up, descend after all.
+            const uint2 fe = flat_spheres((uint32_t)__cvta_generic_to_shared(tree), n, r, tmin, R.t, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
             if (fe.y != kFlatGaveUp) { L.t = __uint_as_float(fe.x); L.m = fe.y; R = L; st = ST_RETURN; }
             else st = ST_ENTER;
         }
@@ -247,7 +247,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                 else {   // into an operator: a flat one (word 6 of this record says so) is evaluated from its spheres' roots
                     sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride;
                     st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6LeftFlat) ? ST_FLAT : ST_ENTER; n = n + 32u;
-                    R.t = INFINITY;   // flat_eval's limit: none (R is saved in the frame)
+                    R.t = INFINITY;   // flat_spheres's limit: none (R is saved in the frame)
                 }
             } else if (o == O_LOOPR) {                                                 // :647-653
                 tmin = R.t;
@@ -255,7 +255,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                 else {
                     sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride;
                     st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6RightFlat) ? ST_FLAT : ST_ENTER; n = (meta >> 8) << 5;
-                    R.t = INFINITY;   // flat_eval's limit: none (R is what gets re-evaluated)
+                    R.t = INFINITY;   // flat_spheres's limit: none (R is what gets re-evaluated)
                 }
             } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
             if (st == ST_RETURN && sp == stack + stack_stride) st = ST_DONE;           // only the sentinel is left: this is the root's result (L == R)
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         // fill_stride/fill_first: a single GPU or the root of a sharded frame fills every background tile itself (local
         // stores); the other shards fill none — only traced pixels cross NVLink
         for (int m = gw * p.fill_stride + p.fill_first; m < total_macros; m += GW * p.fill_stride) {
-            const int my = p.div_magic ? (int)__umulhi((unsigned int)m, p.div_magic) : m / p.macro_x;
+            const int my = p.div_magic ? (int)__umulhi((unsigned int)m, p.div_magic) : m;   // div_magic == 0: one macro tile per row
             const int mx = m - my * p.macro_x;
             if (my < p.band_m0 || my >= p.band_m1) continue;                                                   // another band of this frame
             if (p.shard_mode && my % p.shard_count != p.shard_rank) continue;                                  // another shard's row

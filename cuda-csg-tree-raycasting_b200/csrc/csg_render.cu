@@ -149,7 +149,7 @@ struct csg_context {
     int last_mode = 0;           // shard mode of the last frame (csg_prune_stats)
     bool shard_sync = true;      // sharded frames are started and joined on the device (SyncWords); csg_set_gather_target(pointer) turns it off
     bool view_cache = false;     // csg_set_view_cache
-    int flat_leaves = kFlatLeavesMax;   // Unions over at most this many spheres are evaluated flat (flat_eval); 0: never
+    int flat_leaves = kFlatLeavesMax;   // Unions over at most this many spheres are evaluated flat (flat_spheres); 0: never
     bool external_target = false;   // csg_set_gather_target: pixels go to a buffer that is not rank 0's own framebuffer
     bool prune_alloc = false;    // tile slots were allocated at upload
     int last_rm[4] = {0, 0, 0, 0};   // traced macro-tile rectangle of the last frame (x0, y0, w, h)
@@ -521,6 +521,9 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     if (!scene || !out) return fail(CSG_ERR_ARG, "null argument");
     if (width < 2 || height < 2) return fail(CSG_ERR_ARG, "width and height must be >= 2");  // (w-1),(h-1) divisors, Q1
     if ((long long)width * height >= (1ll << 31)) return fail(CSG_ERR_ARG, "width*height must be below 2^31");
+    // the kernels number macro tiles with a multiply-high division that is exact below 2^20 tiles of fewer than 4096 per row
+    if ((width + kMacroW - 1) / kMacroW >= 4096 || (long long)((width + kMacroW - 1) / kMacroW) * ((height + kMacroH - 1) / kMacroH) >= (1ll << 20))
+        return fail(CSG_ERR_LIMIT, "frame too large: at most 4095 x 64 pixels wide and 2^20 tiles of 64x32 pixels");
     if (scene->scene.nodes.empty()) return fail(CSG_ERR_ARG, "empty scene");
     if (int rc = scene_within_limits(scene->scene)) return rc;
     int ndev = 0;
