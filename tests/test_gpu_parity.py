@@ -287,7 +287,7 @@ def test_deep_tree_limit_is_an_error_not_a_crash(csg):
 def test_frame_size_limit_is_an_error(csg):
     # the kernels number 64x32-pixel tiles with a multiply-high division that is exact below 4096 tiles per row and 2^20 tiles
     sc = csg.Scene.parse("Sphere 0 0 0 FF0000 1\n")
-    for w, h in ((4096 * 64, 8), (64 * 2048, 32 * 600)):
+    for w, h in ((4096 * 64, 8), (8, 32 * (1 << 20))):
         with pytest.raises(csg.CsgError) as e:
             sc.upload(w, h)
         assert e.value.code == csg.CSG_ERR_LIMIT
