@@ -19,6 +19,7 @@ constexpr int kWarpTreeMax = 64;                // records of the largest per-wa
 constexpr int kSmemHead = 128;                  // bytes before the stack: outcome table + light (csg_render.cu sizes the launch with it)
 
 // Hit details + Phong (sphere/cylinder/cubeHitDetails :183-200/:338-372/:436-457 and LightningKernel :49-111).
+template <bool kCyl>
 __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const float4* __restrict__ prims, const FrameParams& p, const float* __restrict__ s_light)
 {
     if (is_miss(res)) return make_float4(0.08f, 0.08f, 0.11f, 1.0f);   // :109
@@ -28,7 +29,7 @@ __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const flo
     const float4 pc = __ldg(&prims[id * 5 + 1]);
     const float t = res.t;
     const float px = __fmaf_rn(t, r.dx, r.ox), py = __fmaf_rn(t, r.dy, r.oy), pz = __fmaf_rn(t, r.dz, r.oz);
-    float nx, ny, nz;
+    float nx = 0.0f, ny = 0.0f, nz = 0.0f;
     if (kind == 3u) {                                   // sphereHitDetails :189-195
         nx = px - pc.x; ny = py - pc.y; nz = pz - pc.z;
     } else if (kind == 5u) {                            // cubeHitDetails :446-451
@@ -36,7 +37,7 @@ __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const flo
         nx = cube_normal_component(__fsub_rn(px, pc.x), pc.w, th.x, th.y);
         ny = cube_normal_component(__fsub_rn(py, pc.y), pc.w, th.x, th.y);
         nz = cube_normal_component(__fsub_rn(pz, pc.z), pc.w, th.x, th.y);
-    } else {                                            // cylinderHitDetails :345-365
+    } else if (kCyl) {                                  // cylinderHitDetails :345-365
         const float4 pb = __ldg(&prims[id * 5 + 2]);
         const float4 pv = __ldg(&prims[id * 5 + 3]);
         if (res.m & H_FLAG1) { nx = -pv.x; ny = -pv.y; nz = -pv.z; }
@@ -103,13 +104,13 @@ __device__ __forceinline__ uint32_t to_u8(float c)
 //   * when the first child returns a hit at t and the pending sibling's box starts beyond t, the sibling cannot change
 //     the outcome (Union: every cell with a farther Enter or a Miss on the other side returns this hit; Difference: same
 //     for the right operand) and is skipped;
-//   * flat operands (ST_FLAT): a Union over a few spheres is evaluated from the spheres' roots (flat_spheres, csg_kernel.cuh).
+//   * flat operands (ST_FLAT): a Union over a few spheres is evaluated from the spheres' roots (eval_flat_union, csg_kernel.cuh).
 // (Rounds 1-2 also had a nearest-Enter search for pure union subtrees — a closest-hit descent with a shrinking limit that fell back
 // to the frame machine on an Exit or a tie.  With per-tile trees, sibling pruning and flat operands it had become a loss on every
 // BASELINE config — Cheese512 0.1499 -> 0.1436 ms, configs[4] 8.91 -> 8.17 ms without it — and was removed; the pure flag of the
 // tree records remains.)
 
-template <bool COUNT>
+template <bool COUNT, bool kCyl>
 __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, const float4* __restrict__ prims,
                                         const uint32_t* __restrict__ table, const uint32_t stack,
                                         const uint32_t stack_stride, const int& stack_levels, const Ray& r, const bool root_is_leaf,
@@ -125,7 +126,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
         bool go;
         float tn;
         uint32_t cm;
-        eval_child(tree, prims, 0u, r, tmin, root_gated, L, go, tn, cm);
+        eval_child<kCyl>(tree, prims, 0u, r, tmin, root_gated, L, go, tn, cm);
         return L;
     }
     uint32_t n = 0u;                           // byte offset of the current operator's record
@@ -144,14 +145,14 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
             bool goA = false, goB = false;
             float tnA = -INFINITY, tnB = -INFINITY;
             uint32_t mA = 0u, mB = 0u;
-            if (st != ST_LOOPR) eval_child(tree, prims, cl, r, tmin, st == ST_ENTER, a, goA, tnA, mA);
+            if (st != ST_LOOPR) eval_child<kCyl>(tree, prims, cl, r, tmin, st == ST_ENTER, a, goA, tnA, mA);
             if (st == ST_ENTER && op != 0u && !goA && is_miss(a)) {
                 // left operand of a Difference/Intersection already missed: the node's result is Miss whatever the right
                 // operand does (all M* cells of both tables, :670-677) — skip the right subtree (Q8)
                 L = a; R = a;
                 st = ST_RETURN;
             } else {
-                if (st != ST_LOOPL) eval_child(tree, prims, cr, r, tmin, st == ST_ENTER, b, goB, tnB, mB);
+                if (st != ST_LOOPL) eval_child<kCyl>(tree, prims, cr, r, tmin, st == ST_ENTER, b, goB, tnB, mB);
                 if (st == ST_LOOPL) { L = a; st = ST_COMPUTE; }
                 else if (st == ST_LOOPR) { R = b; st = ST_COMPUTE; }
                 else {
@@ -190,9 +191,9 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
         if (st == ST_FLAT) {
             // (Behind the operator visit, so that a descent decided there is evaluated in the same round.)
             // n is a flat operand (a Union over a few spheres) the machine was about to descend into; the frame that takes its
-            // result is pushed.  Its result follows from the spheres' roots (flat_spheres; the frames above sp are free and hold its
-            // list): return it as if the descent had happened — or, when flat_spheres gives up, descend after all.
-            const uint2 fe = flat_spheres((uint32_t)__cvta_generic_to_shared(tree), n, r, tmin, R.t, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
+            // result is pushed.  Its result follows from the spheres' roots (eval_flat_union; the frames above sp are free and hold its
+            // list): return it as if the descent had happened — or, when eval_flat_union gives up, descend after all.
+            const uint2 fe = eval_flat_union((uint32_t)__cvta_generic_to_shared(tree), n, r, tmin, R.t, sp, stack_stride, stack + (uint32_t)(stack_levels + 2) * stack_stride);
             if (fe.y != kFlatGaveUp) { L.t = __uint_as_float(fe.x); L.m = fe.y; R = L; st = ST_RETURN; }
             else st = ST_ENTER;
         }
@@ -247,7 +248,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                 else {   // into an operator: a flat one (word 6 of this record says so) is evaluated from its spheres' roots
                     sts128(sp, make_uint4(__float_as_uint(R.t), R.m | F_LOAD_RGH, 0u, n)); sp += stack_stride;
                     st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6LeftFlat) ? ST_FLAT : ST_ENTER; n = n + 32u;
-                    R.t = INFINITY;   // flat_spheres's limit: none (R is saved in the frame)
+                    R.t = INFINITY;   // eval_flat_union's limit: none (R is saved in the frame)
                 }
             } else if (o == O_LOOPR) {                                                 // :647-653
                 tmin = R.t;
@@ -255,7 +256,7 @@ __device__ __forceinline__ Hit traverse(const unsigned char* __restrict__ tree, 
                 else {
                     sts128(sp, make_uint4(__float_as_uint(L.t), L.m | F_LOAD_LFT, 0u, n)); sp += stack_stride;
                     st = (*reinterpret_cast<const uint32_t*>(tree + n + 24) & kW6RightFlat) ? ST_FLAT : ST_ENTER; n = (meta >> 8) << 5;
-                    R.t = INFINITY;   // flat_spheres's limit: none (R is what gets re-evaluated)
+                    R.t = INFINITY;   // eval_flat_union's limit: none (R is what gets re-evaluated)
                 }
             } else { L = R = make_miss(); st = ST_RETURN; }                            // :654-660
             if (st == ST_RETURN && sp == stack + stack_stride) st = ST_DONE;           // only the sentinel is left: this is the root's result (L == R)
@@ -272,7 +273,7 @@ __device__ __forceinline__ unsigned long long probe_now() { unsigned long long t
 #define FPROBE(k, v) do { } while (0)
 #endif
 
-template <int MODE, int kThreads, bool kSuper>   // kSuper: more than one ray per pixel (keeps the sample loop and its accumulators out of the common case)
+template <int MODE, int kThreads, bool kSuper, bool kCyl>   // kSuper: more than one ray per pixel (keeps the sample loop and its accumulators out of the common case); kCyl: the scene has cylinders
 __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_kernel(const __grid_constant__ FrameParams p)
 {
     // shared memory: [outcome table 128 B][stack: (levels+2) x kThreads x 16 B][scratch frame: kThreads x 16 B][per-warp tree copy: warp_tree_nodes x 32 B].
@@ -536,10 +537,10 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                         const int sy = sp ? (sl >> (sp >> 1)) : s / ss;
                         const int sx = sp ? (sl & (ss - 1)) : s - sy * ss;
                         make_ray(x * ss + sx, y * ss + sy, r);
-                        res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), p.stack_levels, r, (td.z & kTileRootLeaf) != 0u,
+                        res = traverse<MODE == OUT_AOV, kCyl>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), p.stack_levels, r, (td.z & kTileRootLeaf) != 0u,
                                                         p.root_is_leaf == 0, iters);
                         if (MODE != OUT_AOV) {
-                            const float4 c = shade_pixel(res, r, p.prims, p, s_light);
+                            const float4 c = shade_pixel<kCyl>(res, r, p.prims, p, s_light);
                             const uint4 a = lds128(my_scratch);
                             sts128(my_scratch, make_uint4(__float_as_uint(__uint_as_float(a.x) + c.x), __float_as_uint(__uint_as_float(a.y) + c.y),
                                                           __float_as_uint(__uint_as_float(a.z) + c.z), a.w));
@@ -549,12 +550,12 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
                     accx = __uint_as_float(a.x); accy = __uint_as_float(a.y); accz = __uint_as_float(a.z);
                 } else {
                     r.dx = r0.dx; r.dy = r0.dy; r.dz = r0.dz; r.ix = r0.ix; r.iy = r0.iy; r.iz = r0.iz;
-                    res = traverse<MODE == OUT_AOV>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), p.stack_levels, r, (td.z & kTileRootLeaf) != 0u,
+                    res = traverse<MODE == OUT_AOV, kCyl>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), p.stack_levels, r, (td.z & kTileRootLeaf) != 0u,
                                                     p.root_is_leaf == 0, iters);
                     if (lane == __ffs(amask) - 1)   // the tile is traced: ask for the next ticket now
                         next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
                     if (MODE != OUT_AOV) {
-                        const float4 c = shade_pixel(res, r, p.prims, p, s_light);
+                        const float4 c = shade_pixel<kCyl>(res, r, p.prims, p, s_light);
                         accx = c.x; accy = c.y; accz = c.z;
                     }
                 }

@@ -664,8 +664,8 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
             const uint32_t m = w.meta[i], kind = m & 7u;
             if (kind >= 3u) continue;
             const uint32_t ri = m >> 8, f = w.flg[i];
-            // flat: a Union over a few spheres (flat_spheres, csg_scene.h); word 6 also tells Compute which operands are flat operators
-            const int fmax = (int)kept <= q.flat_tree_max ? min(q.flat_max, kFlatLeavesMax) : 0;   // flat_spheres reads the warp's shared-memory copy of the tree
+            // flat: a Union over a few spheres (eval_flat_union, csg_scene.h); word 6 also tells Compute which operands are flat operators
+            const int fmax = (int)kept <= q.flat_tree_max ? min(q.flat_max, kFlatLeavesMax) : 0;   // eval_flat_union reads the warp's shared-memory copy of the tree
             auto is_flat = [&w, fmax](uint32_t x) { return (w.meta[x] & 7u) == 0u && (w.flg[x] & 4u) && (int)w.cnt[x] <= fmax; };   // spheres-only Unions
             const bool flat = is_flat((uint32_t)i);
             const uint32_t meta = kind | (ri << 8) | ((w.meta[i + 1] & 7u) >= 3u ? kMetaLeftLeaf : 0u) | ((w.meta[ri] & 7u) >= 3u ? kMetaRightLeaf : 0u) |

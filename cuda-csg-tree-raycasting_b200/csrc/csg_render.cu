@@ -131,6 +131,7 @@ struct csg_context {
     int shard_count = 1;
     bool multi_process = false;
     FlatTree tree;
+    bool has_cyl = true;         // the scene holds at least one cylinder: frame kernels with cylinder code (kCyl)
     bool prune = true;           // per-tile pruned trees, rebuilt every frame
     bool prune_flat = true;      // by csg_prune_flat_kernel (prefix sums over the preorder layout); false: csg_prune_kernel (tree walk)
     bool flat_ok = false;        // the tree is small enough for csg_prune_flat_kernel
@@ -149,7 +150,7 @@ struct csg_context {
     int last_mode = 0;           // shard mode of the last frame (csg_prune_stats)
     bool shard_sync = true;      // sharded frames are started and joined on the device (SyncWords); csg_set_gather_target(pointer) turns it off
     bool view_cache = false;     // csg_set_view_cache
-    int flat_leaves = kFlatLeavesMax;   // Unions over at most this many spheres are evaluated flat (flat_spheres); 0: never
+    int flat_leaves = kFlatLeavesMax;   // Unions over at most this many spheres are evaluated flat (eval_flat_union); 0: never
     bool external_target = false;   // csg_set_gather_target: pixels go to a buffer that is not rank 0's own framebuffer
     bool prune_alloc = false;    // tile slots were allocated at upload
     int last_rm[4] = {0, 0, 0, 0};   // traced macro-tile rectangle of the last frame (x0, y0, w, h)
@@ -191,9 +192,14 @@ int launch_one(csg_context* c, Shard& s, const FrameParams& fp)
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e;
-    if constexpr (MODE == OUT_AOV) e = cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false>, fp);   // per primary ray: enqueue_frame refuses ss > 1
-    else e = c->ss > 1 ? cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, true>, fp)
-                       : cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false>, fp);
+    // kernels without cylinder code for scenes without cylinders (instruction-cache footprint, csg_kernel.cuh eval_flat_union)
+    if constexpr (MODE == OUT_AOV) {   // per primary ray: enqueue_frame refuses ss > 1
+        e = c->has_cyl ? cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false, true>, fp) : cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false, false>, fp);
+    } else if (c->ss > 1) {
+        e = c->has_cyl ? cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, true, true>, fp) : cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, true, false>, fp);
+    } else {
+        e = c->has_cyl ? cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false, true>, fp) : cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false, false>, fp);
+    }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return CSG_OK;
@@ -212,9 +218,13 @@ int launch_mode(csg_context* c, Shard& s, const FrameParams& fp)
 template <int MODE, int T>
 int configure_one(size_t smem, int* blocks_per_sm)
 {
-    if constexpr (MODE != OUT_AOV) CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, T, false>, T, smem));
+    if constexpr (MODE != OUT_AOV) {
+        CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, T, false, true>, T, smem));
     return CSG_OK;
 }
 
@@ -543,6 +553,8 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
     c->multi_process = multi_process;
     c->scene_copy.scene = scene->scene;
     flatten(scene->scene, scene->scene.optimize, c->tree);
+    c->has_cyl = false;
+    for (const NodeRec& nr : c->tree.nodes) c->has_cyl = c->has_cyl || (nr.meta & 7u) == (uint32_t)kCylinder;
     c->stack_levels = std::max(1, c->tree.depth);
     c->root_box_valid = c->tree.root_box_valid;
     for (int i = 0; i < 6; ++i) c->root_box[i] = c->tree.root_box[i];

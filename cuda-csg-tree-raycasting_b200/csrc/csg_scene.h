@@ -43,7 +43,7 @@ constexpr uint32_t kMetaLeftLeaf = 1u << 3, kMetaRightLeaf = 1u << 4, kMetaBound
 // such a subtree may be evaluated as a nearest-Enter search (csg_render.cu, ST_SEARCH)
 constexpr uint32_t kMetaPure = 1u << 6;
 // flat (per-tile trees only, set by csg_prune_flat_kernel) = a Union over at most PruneParams::flat_max (<= kFlatLeavesMax) spheres
-// and nothing else: its result at any tmin follows from the spheres' roots alone (flat_spheres, csg_kernel.cuh).  Word 6 of such a
+// and nothing else: its result at any tmin follows from the spheres' roots alone (eval_flat_union, csg_kernel.cuh).  Word 6 of such a
 // record, bits 0-28: the spheres among the records that follow it (bit j: record n + 1 + j; a subtree of k spheres is 2k - 1
 // records).  Bits 30 / 31 of word 6 of ANY operator record of a tile tree say that its left / right operand is a flat operator
 // (Compute looks there when it loops into an operand).  Records staged from the uploaded tree carry 0 in word 6.
