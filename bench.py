@@ -291,16 +291,18 @@ class Job:
 
     def frame_device(self, k=0, prequeued=False, idle_start=False):
         """One frame, device-resident; returns this rank's CUDA-event span (rank 0: the whole sharded frame).
-        Default: the L2 flush of the step (a 256 MiB memset) is queued on the context's own stream (csg_stream) and the frame
-        right behind it, so the frame's launches are already waiting when the GPU gets to them — the steady state of a render
-        loop, and the usual way of timing queued kernels with CUDA events.  idle_start (a diagnostic): the flush has been waited
+        Default: on the root the L2 flush of the step (a 256 MiB memset) is queued on the context's own stream (csg_stream) and the
+        frame right behind it, so the frame's launches are already waiting when the GPU gets to them — the steady state of a render
+        loop, and the usual way of timing queued kernels with CUDA events.  The other ranks have flushed before the barrier and
+        enqueue their share at once: their kernels wait on the device for the root's start word (two memsets on two GPUs do not end
+        together, and a peer whose flush ended after the root's would be late for a reason that has nothing to do with the frame).  idle_start (a diagnostic): the flush has been waited
         for and the frame is enqueued on an idle GPU; whatever the host then takes between the start event and the first launch
         shows up as device time.  prequeued (a diagnostic): the peers enqueue first — their kernels wait on the device for the
         root's start word — and the root enqueues once they have."""
         import torch
         env = self.env
         env.spin()
-        if not idle_start:
+        if not idle_start and env.rank == 0:
             with torch.cuda.stream(self.stream):
                 env.flush.zero_()
         if prequeued and env.rank == 0:
@@ -319,7 +321,7 @@ class Job:
             if k == warmup:
                 env.barrier()
                 t0 = time.perf_counter()
-            if idle_start:
+            if idle_start or env.rank != 0:
                 env.flush.zero_()
             env.barrier()
             t = self.frame_device(k, prequeued, idle_start)
@@ -701,8 +703,8 @@ def bench_ours(args):
         "config": config_of(world),
         "timing": {"what": "rank 0's CUDA events: frame started on the root GPU -> framebuffer complete on the root GPU; peers' kernels are gated on "
                            "the root's start word and the root's last kernel joins every peer's done word (device-side, over NVLink); every "
-                           "step = [L2 flush, start event, the frame's kernels, done event] queued on the context's stream (csg_stream), "
-                           "then waited for",
+                           "step = [L2 flush, start event, the frame's kernels, done event] queued on the root's stream (csg_stream), then waited "
+                           "for; the other ranks flush before the step's barrier and enqueue their share while the root's flush runs",
                    "ms_per_step_min": float(ms.min()), "ms_per_step_max": float(ms.max()),
                    "ms_per_step_idle_start": idle_ms,
                    "idle_start_note": "diagnostic: the same frames enqueued on an idle GPU (the flush waited for first): the root's span then also "
