@@ -56,19 +56,21 @@ __device__ __noinline__ float4 shade_pixel(const Hit res, const Ray r, const flo
             nz = __fmaf_rn(-pv.z, m, pz - cz);
         }
     }
-    if (!((res.m & (H_FLAG1 | H_FLAG2)) && kind == 4u)) {   // caps carry the unit axis as is; everything else is normalised
-        const float inv = __frcp_rn(__fsqrt_rn(dot_ref(nx, ny, nz, nx, ny, nz)));
-        nx *= inv; ny *= inv; nz *= inv;
-    }
+    // the normal (caps carry the unit axis as is; everything else is normalised) and the view vector of LightningKernel :78-103
+    // are normalised side by side: one range check for both squared lengths, then two independent chains (inv_len_fast)
+    const bool unit = (res.m & (H_FLAG1 | H_FLAG2)) && kind == 4u;
+    float vx = p.cam_pos[0] - px, vy = p.cam_pos[1] - py, vz = p.cam_pos[2] - pz;
+    const float nn = unit ? 1.0f : dot_ref(nx, ny, nz, nx, ny, nz), vv = dot_ref(vx, vy, vz, vx, vy, vz);
+    float inv, iv;
+    if (len2_safe(nn) && len2_safe(vv)) { inv = inv_len_fast(nn); iv = inv_len_fast(vv); }
+    else { inv = inv_len_exact_path(nn); iv = inv_len_exact_path(vv); }
+    if (!unit) { nx *= inv; ny *= inv; nz *= inv; }
     if (res.m & H_FLIP) { nx = -nx; ny = -ny; nz = -nz; }
     if ((res.m & H_CLS) == H_EXIT) { nx = -nx; ny = -ny; nz = -nz; }
 
-    // LightningKernel :78-103
     const float Lx = s_light[0], Ly = s_light[1], Lz = s_light[2];   // normalize(lightDir), once per CTA
-    float vx = p.cam_pos[0] - px, vy = p.cam_pos[1] - py, vz = p.cam_pos[2] - pz;
-    const float iv = __frcp_rn(__fsqrt_rn(dot_ref(vx, vy, vz, vx, vy, vz)));
     vx *= iv; vy *= iv; vz *= iv;
-    const float in = __frcp_rn(__fsqrt_rn(dot_ref(nx, ny, nz, nx, ny, nz)));   // reflect() re-normalises n
+    const float in = inv_len(dot_ref(nx, ny, nz, nx, ny, nz));       // reflect() re-normalises n
     const float ux = nx * in, uy = ny * in, uz = nz * in;
     // dot(-L, n) of reflect(): the reference's SASS rounds the x product first here (FMUL Lx*nx; FFMA -Ly,ny,-that; FFMA -Lz,nz,.),
     // not the y product as in every other dot of the path
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         float cz = __fadd_rn(p.forward[2], __fmaf_rn(p.right[2], nx, __fmul_rn(p.up[2], ny)));
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep) {   // normalize() then the Ray ctor normalises again (Q3)
-            const float inv = __frcp_rn(__fsqrt_rn(dot_ref(cx, cy, cz, cx, cy, cz)));
+            const float inv = inv_len(dot_ref(cx, cy, cz, cx, cy, cz));
             cx = __fmul_rn(inv, cx); cy = __fmul_rn(inv, cy); cz = __fmul_rn(inv, cz);
         }
         ray.dx = cx; ray.dy = cy; ray.dz = cz;
