@@ -27,8 +27,8 @@ __device__ __forceinline__ void stage_record(const uint4 ua, const uint4 ub, flo
         a.w = __fsub_rn(a.w, ox); b.x = __fsub_rn(b.x, oy); b.y = __fsub_rn(b.y, oz);
     }
     uint32_t meta = ub.w;
-    if ((meta & 7u) == 5u && div_safe(a.x) && div_safe(a.y) && div_safe(a.z) && div_safe(a.w) && div_safe(b.x) && div_safe(b.y))
-        meta |= kMetaCubeSafe;   // cube_isect may divide through shared reciprocals
+    if ((meta & 7u) >= 4u && div_safe(a.x) && div_safe(a.y) && div_safe(a.z) && div_safe(a.w) && div_safe(b.x) && div_safe(b.y))
+        meta |= kMetaBoxSafe;   // cube_isect / gate_box_exact may divide through shared reciprocals
     oa = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
     ob = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), (ub.w & 7u) < 3u ? 0u : ub.z, meta);   // operators: no flat-evaluation flags (word 6, csg_scene.h)
 }

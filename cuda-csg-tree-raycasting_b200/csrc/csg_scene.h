@@ -50,9 +50,10 @@ constexpr uint32_t kMetaPure = 1u << 6;
 // (Measured, round 2: flat Unions of up to 30 spheres — two flat operands scanned as one — are slower than two of 15 under an
 // ordinary Union, whose box tests skip half the spheres: 0.170 against 0.166 ms per frame.)
 constexpr uint32_t kMetaFlat = 1u << 7;
-// cube records of a staged / tile tree only (bit 3 means leftIsLeaf on operators): the six origin-relative bounds are all within
-// [2^-30, 2^30] in magnitude, so cube_isect may form its IEEE quotients from shared refined reciprocals (csg_kernel.cuh div_shared)
-constexpr uint32_t kMetaCubeSafe = 1u << 3;
+// cube and cylinder records of a staged / tile tree only (bit 3 means leftIsLeaf on operators): the six origin-relative bounds of
+// the box are all within [2^-30, 2^30] in magnitude, so cube_isect / gate_box_exact may form their IEEE quotients from shared refined
+// reciprocals (csg_kernel.cuh div_shared)
+constexpr uint32_t kMetaBoxSafe = 1u << 3;
 constexpr int kFlatLeavesMax = 15;
 constexpr uint32_t kW6LeftFlat = 1u << 30, kW6RightFlat = 1u << 31, kW6SphereMask = (1u << 29) - 1u;
 
