@@ -275,7 +275,7 @@ __device__ __forceinline__ unsigned long long probe_now() { unsigned long long t
 #define FPROBE(k, v) do { } while (0)
 #endif
 
-template <int MODE, int kThreads, bool kSuper, bool kCyl>   // kSuper: more than one ray per pixel (keeps the sample loop and its accumulators out of the common case); kCyl: the scene has cylinders
+template <int MODE, int kThreads, bool kSuper, bool kCyl, bool kPair>   // kSuper: more than one ray per pixel (keeps the sample loop and its accumulators out of the common case); kCyl: the scene has cylinders; kPair: tickets of two warp tiles (one ray per pixel only)
 __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_kernel(const __grid_constant__ FrameParams p)
 {
     // shared memory: [outcome table 128 B][stack: (levels+2) x kThreads x 16 B][scratch frame: kThreads x 16 B][per-warp tree copy: warp_tree_nodes x 32 B].
@@ -428,6 +428,120 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         pr_t0 = probe_now();
         const unsigned int pr_ticket = ticket;
 #endif
+        if constexpr (!kSuper && kPair) {
+            // ---- one ray per pixel, plenty of tickets (one GPU at 4K: csg_render.cu picks the kPair kernels when there are 12 warp
+            // tiles per warp of the grid or more).  A ticket is TWO warp tiles, horizontal neighbours inside one macro tile (Morton
+            // order: k and k + 1), so that the ticket's set-up — the atomic's and the ordered list's round trips, tile and tree
+            // look-up, the tree copy — is paid once per 64 pixels.  When tickets are scarce (a frame sharded over several GPUs) the
+            // fine hand-out decides the length of the frame: those launches take the one-tile path below.
+            constexpr int ps = 1;
+            const unsigned int macro = ticket >> (6 - ps);
+            const int k = (int)((ticket << ps) & 63u);
+            uint4 td = make_uint4(0u, (uint32_t)p.n_nodes, p.full_flags, 0u);
+            int tile_no = (int)macro;
+            if (p.order) {   // heaviest first (see below); an entry carries the tile's descriptor
+                td = __ldg(p.order + macro);
+                tile_no = (int)td.w;
+            }
+            int mx, my;
+            shard_tile_coords(tile_no, p.shard_mode, p.shard_rank, p.shard_count, p.rm_x0, p.rm_y0, p.rm_w, p.rm_magic, p.row_first, mx, my);
+            const int kx = (k & 1) | ((k >> 1) & 2) | ((k >> 2) & 4);        // Morton order inside the macro tile
+            const int ky = ((k >> 1) & 1) | ((k >> 2) & 2) | ((k >> 3) & 4);
+            const int tx0 = mx * kMacroW + kx * kWarpTileW, ty0 = my * kMacroH + ky * kWarpTileH;   // corner of the first warp tile
+            ticket = 0xffffffffu;   // placeholder; the real value is broadcast at the end of the iteration
+            if (!p.order && p.desc) {   // natural order: the descriptor is looked up by position
+                const int slot = slot_of_macro(p.shard_mode, mx, my, p.macro_x, p.shard_count);
+                td = __ldg(reinterpret_cast<const uint4*>(p.desc) + slot);
+            }
+            // nothing to trace anywhere in the ticket: no primitive reachable from the macro tile, or all of it outside the frame /
+            // the screen-space bound of the root box (every ray is a Miss, :109 background colour)
+            const bool span_empty = td.y == 0u || tx0 >= p.width || ty0 >= p.height || tx0 > p.rect_x1 || tx0 + (kWarpTileW << ps) - 1 < p.rect_x0 ||
+                                    ty0 > p.rect_y1 || ty0 + (kWarpTileH - 1) < p.rect_y0;
+            const unsigned char* tree = reinterpret_cast<const unsigned char*>(p.pool + 2 * (size_t)td.x);
+            const bool tree_fits = !span_empty && td.y <= (uint32_t)p.warp_tree_nodes;
+            if (tree_fits) {
+                // the tile's tree goes to this warp's shared-memory slice with asynchronous copies (no registers in between): up to
+                // four 16-byte pieces per lane, in flight while the first ray is generated
+                static_assert(kWarpTreeMax == 64, "four copies per lane cover 64 records");
+                const uint32_t slice = (uint32_t)__cvta_generic_to_shared(smem_raw + my_tree_off());
+                __syncwarp();   // everybody is done with the previous tile's copy
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint32_t i = (uint32_t)lane + 32u * q4;
+                    if (i < 2u * td.y) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(slice + 16u * i), "l"(p.pool + 2 * (size_t)td.x + i) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                tree = smem_raw + my_tree_off();
+            }
+            unsigned int next = 0;
+            int req_lane = -1;   // lane that has asked for the next ticket (-1: nobody yet)
+#pragma unroll 1
+            for (int half = 0; half < (1 << ps); ++half) {
+                const int tx = tx0 + half * kWarpTileW;
+                const int x = tx + (lane & 7), y = ty0 + (lane >> 3);   // this lane's pixel
+                const bool active = x < p.width && y < p.height;
+                const uint32_t pix = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;   // :33 (csg_upload keeps width*height below 2^31)
+                const unsigned int amask = __ballot_sync(0xffffffffu, active);
+                if (amask == 0u) continue;
+                const bool tile_empty = span_empty || tx > p.rect_x1 || tx + (kWarpTileW - 1) < p.rect_x0;
+                Hit res = make_miss();
+                int iters = 0;
+                float accx = 0.08f, accy = 0.08f, accz = 0.11f;
+                if (!tile_empty) {
+                    Ray r;
+                    r.ox = ox; r.oy = oy; r.oz = oz;
+                    make_ray(x, y, r);
+                    if (tree_fits) {   // (nothing pending in the second half: the wait falls through)
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        __syncwarp();
+                    }
+                    if (active) {
+                        res = traverse<MODE == OUT_AOV, kCyl>(tree, p.prims, s_table, my_stack, (uint32_t)(kThreads * sizeof(uint4)), p.stack_levels, r, (td.z & kTileRootLeaf) != 0u,
+                                                              p.root_is_leaf == 0, iters);
+                        // the last tile of the ticket is traced: ask for the next ticket now, so that the atomic's round trip hides behind
+                        // the shading — not earlier: a ticket held during a heavy tile would sit with this warp while others run dry
+                        if (half == (1 << ps) - 1 && lane == __ffs(amask) - 1) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+                        if (MODE != OUT_AOV) {
+                            const float4 c = shade_pixel<kCyl>(res, r, p.prims, p, s_light);
+                            accx = c.x; accy = c.y; accz = c.z;
+                        }
+                    }
+                    if (half == (1 << ps) - 1) req_lane = __ffs(amask) - 1;
+                }
+                if (MODE == OUT_AOV) {
+                    if (active) {
+                        const bool hit = !is_miss(res);
+                        if (p.aov_hit) p.aov_hit[pix] = hit ? 1 : 0;
+                        if (p.aov_prim) p.aov_prim[pix] = hit ? (int32_t)((res.m & H_META_MASK) >> H_ID_SHIFT) : -1;
+                        if (p.aov_t) p.aov_t[pix] = hit ? res.t : -1.0f;
+                        if (p.aov_iters) p.aov_iters[pix] = iters;
+                    }
+                } else if (MODE == OUT_F32) {
+                    if (active) reinterpret_cast<float4*>(p.out)[pix] = make_float4(accx, accy, accz, 1.0f);
+                } else {
+                    const uint32_t px8 = to_u8(accx) | (to_u8(accy) << 8) | (to_u8(accz) << 16) | 0xFF000000u;
+                    // four horizontally adjacent pixels -> one 16-byte store
+                    const uint32_t p1 = __shfl_down_sync(0xffffffffu, px8, 1);
+                    const uint32_t p2 = __shfl_down_sync(0xffffffffu, px8, 2);
+                    const uint32_t p3 = __shfl_down_sync(0xffffffffu, px8, 3);
+                    if ((p.width & 3) == 0) {
+                        if (active && (lane & 3) == 0) reinterpret_cast<uint4*>(p.out)[pix >> 2] = make_uint4(px8, p1, p2, p3);
+                    } else if (active) {
+                        reinterpret_cast<uint32_t*>(p.out)[pix] = px8;
+                    }
+                }
+            }
+#ifdef CSG_FRAME_PROBE
+            { const unsigned long long d = probe_now() - pr_t0; ++pr_tiles; if (d > pr_longest) { pr_longest = d; pr_longest_ticket = pr_ticket; } }
+#endif
+            if (req_lane < 0) {   // the last tile of the ticket was not traced (empty, or outside the frame)
+                if (lane == 0) next = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+                req_lane = 0;
+            }
+            ticket = __shfl_sync(0xffffffffu, next, req_lane);
+            continue;
+        }
+        // ---- one warp tile per ticket, and supersampling (kSuper)
         const int ts = kSuper ? p.sp_tshift : 0;   // = sp - gp, precomputed: a plain parameter load is rematerialised, a difference kept alive across the tile spilled
         const unsigned int cur = ticket >> ts;
         const int pass0 = (int)(ticket & ((1u << ts) - 1u)) << gp;

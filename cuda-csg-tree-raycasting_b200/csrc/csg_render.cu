@@ -192,13 +192,18 @@ int launch_one(csg_context* c, Shard& s, const FrameParams& fp)
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e;
-    // kernels without cylinder code for scenes without cylinders (instruction-cache footprint, csg_kernel.cuh eval_flat_union)
+    // kernels without cylinder code for scenes without cylinders (instruction-cache footprint, csg_kernel.cuh eval_flat_union);
+    // one ray per pixel: tickets of two warp tiles (kPair) when fill_params found plenty of them
+    const bool pair = fp.pair_shift != 0;
+    auto go = [&](auto kernel) { return cudaLaunchKernelEx(&cfg, kernel, fp); };
     if constexpr (MODE == OUT_AOV) {   // per primary ray: enqueue_frame refuses ss > 1
-        e = c->has_cyl ? cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false, true>, fp) : cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false, false>, fp);
+        e = c->has_cyl ? (pair ? go(csg_frame_kernel<MODE, T, false, true, true>) : go(csg_frame_kernel<MODE, T, false, true, false>))
+                       : (pair ? go(csg_frame_kernel<MODE, T, false, false, true>) : go(csg_frame_kernel<MODE, T, false, false, false>));
     } else if (c->ss > 1) {
-        e = c->has_cyl ? cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, true, true>, fp) : cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, true, false>, fp);
+        e = c->has_cyl ? go(csg_frame_kernel<MODE, T, true, true, false>) : go(csg_frame_kernel<MODE, T, true, false, false>);
     } else {
-        e = c->has_cyl ? cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false, true>, fp) : cudaLaunchKernelEx(&cfg, csg_frame_kernel<MODE, T, false, false>, fp);
+        e = c->has_cyl ? (pair ? go(csg_frame_kernel<MODE, T, false, true, true>) : go(csg_frame_kernel<MODE, T, false, true, false>))
+                       : (pair ? go(csg_frame_kernel<MODE, T, false, false, true>) : go(csg_frame_kernel<MODE, T, false, false, false>));
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
@@ -218,13 +223,16 @@ int launch_mode(csg_context* c, Shard& s, const FrameParams& fp)
 template <int MODE, int T>
 int configure_one(size_t smem, int* blocks_per_sm)
 {
+    const int sm = (int)smem;
     if constexpr (MODE != OUT_AOV) {
-        CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     }
-    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, T, false, true>, T, smem));
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CU(cudaFuncSetAttribute(csg_frame_kernel<MODE, T, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, csg_frame_kernel<MODE, T, false, true, false>, T, smem));
     return CSG_OK;
 }
 
@@ -357,6 +365,15 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
     }
     fp.sp_tshift = fp.sp_shift - fp.sp_group;
     fp.n_local_warp_tiles = (int)((mine * 64) << fp.sp_tshift);
+    fp.pair_shift = 0;
+    if (c->ss == 1) {
+        // one ray per pixel: tickets of two warp tiles while there are plenty of them (12 warp tiles per warp of the grid or more: one
+        // GPU at 4K), single warp tiles when they are scarce (sharded frames)
+        const long long warps = (long long)s.grid * (c->threads / 32);
+        fp.pair_shift = mine * 64 >= 12 * warps ? 1 : 0;
+        if (const char* e = std::getenv("CSG_B200_PAIR")) fp.pair_shift = std::atoi(e) ? 1 : 0;   // tuning aid
+        fp.n_local_warp_tiles = (int)((mine * 64) >> fp.pair_shift);
+    }
     fp.rm_magic = (fp.rm_w > 1 && fp.rm_w < 4096 && traced < (1ll << 20)) ? (unsigned int)((1ull << 32) / (unsigned long long)fp.rm_w + 1ull) : 0u;
     if (fp.rm_w == 0) fp.rm_w = 1;   // never divide by zero; n_local_warp_tiles is 0 anyway
 }
@@ -428,7 +445,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.width = fp.width; q.height = fp.height; q.macro_x = fp.macro_x;
             q.rm_x0 = fp.rm_x0; q.rm_y0 = fp.rm_y0; q.rm_w = fp.rm_w; q.rm_magic = fp.rm_magic;
             q.shard_rank = fp.shard_rank; q.shard_count = fp.shard_count; q.shard_mode = fp.shard_mode; q.row_first = fp.row_first;
-            q.n_tiles = c->prune ? (fp.n_local_warp_tiles >> (fp.sp_shift - fp.sp_group)) / 64 : 0;
+            q.n_tiles = c->prune ? (int)(((long long)fp.n_local_warp_tiles << fp.pair_shift) >> fp.sp_tshift) / 64 : 0;
             q.nodes = s.d_nodes; q.n_nodes = fp.n_nodes; q.parent = s.d_parent;
             q.leaf_boxes = s.d_leaf_boxes; q.n_leaves = (int)(c->tree.leaf_boxes.size() / 8);
             q.mark_words = c->mark_words; q.marks_first = c->marks_first;

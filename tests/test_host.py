@@ -301,10 +301,10 @@ def test_bench_ours_refuses_to_run_without_a_gpu():
 
 
 def test_sass_has_no_local_memory_in_any_kernel(csg):
-    """The traversal stack lives in shared memory and nothing spills: no LDL/STL in the SASS of any of the 30 frame kernel
-    instantiations (three CTA shapes x three output modes x {one ray per pixel, supersampling} x {scenes with, without
-    cylinders}; the AOV mode is per primary ray and has no supersampling variant), in eval_flat_union and the other device
-    functions they call, nor in the pruning kernels; everything is built for sm_100a."""
+    """The traversal stack lives in shared memory and nothing spills: no LDL/STL in the SASS of any of the 48 frame kernel
+    instantiations (three CTA shapes x three output modes x {one ray per pixel with tickets of one / of two warp tiles,
+    supersampling} x {scenes with, without cylinders}; the AOV mode is per primary ray and has no supersampling variant), in
+    eval_flat_union and the other device functions they call, nor in the pruning kernels; everything is built for sm_100a."""
     import shutil
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not on PATH")
@@ -323,8 +323,8 @@ def test_sass_has_no_local_memory_in_any_kernel(csg):
         if fn and re.match(r"\s*/\*[0-9a-f]{4}\*/", line):
             per_fn[fn][1] += 1
     frame = {f: v for f, v in per_fn.items() if "csg_frame_kernel" in f}
-    assert len(frame) == 30                                            # 3 CTA shapes x (3 output modes at 1 ray + 2 with supersampling) x (with, without cylinder code)
-    assert len([f for f in frame if "ELb0ELb" in f]) == 18 and len([f for f in frame if "ELb1ELb" in f]) == 12
+    assert len(frame) == 48                                            # 3 CTA shapes x (3 modes x 2 ticket sizes at 1 ray + 2 modes with supersampling) x (with, without cylinder code)
+    assert len([f for f in frame if re.search(r"ELb0ELb[01]ELb[01]E", f)]) == 36 and len([f for f in frame if re.search(r"ELb1ELb[01]ELb0E", f)]) == 12
     for f, (local_ops, n) in frame.items():
         assert local_ops == 0, f"{f}: {local_ops} local-memory instructions"
         assert n > 1000
