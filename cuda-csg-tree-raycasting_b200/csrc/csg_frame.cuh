@@ -16,7 +16,7 @@ constexpr int min_blocks_for(int threads) { return threads >= 768 ? 1 : threads 
 constexpr int kWarpTileW = 8, kWarpTileH = 4;   // one warp = one 8x4 pixel tile (Raycaster.cuh:7-8 uses the same shape)
 constexpr int kMacroW = 64, kMacroH = 32;       // sharding unit: 8x8 warp tiles
 constexpr int kWarpTreeMax = 64;                // records of the largest per-warp shared-memory tree copy
-constexpr int kSmemHead = 128;                  // bytes before the stack: outcome table + light (csg_render.cu sizes the launch with it)
+constexpr int kSmemHead = 384;                  // bytes before the stack: outcome table + light (128 B), first positions of the 64 cost buckets (256 B); csg_render.cu sizes the launch with it
 
 // Hit details + Phong (sphere/cylinder/cubeHitDetails :183-200/:338-372/:436-457 and LightningKernel :49-111).
 // (Inlined: every kernel has one call site, and out of line the call cost ~20 instructions of argument moves per shaded warp tile:
@@ -387,6 +387,37 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     FPROBE(1, probe_now());
     cudaGridDependencySynchronize();
     FPROBE(2, probe_now());
+    // Hand-out order of the traced tiles: heaviest first (tiles whose pruned tree is larger come first, so that the expensive tiles
+    // are not the ones still running when the ticket counter runs dry).  The pruning kernel leaves one list of tile descriptors per
+    // cost bucket and the bucket sizes; position m of the order is entry m - start[k] of bucket 63 - k, k the largest with
+    // start[k] <= m, where start[] = exclusive prefix sums of the sizes, heaviest bucket first — worked out here by the first warp
+    // of every CTA (one load, five shuffles) instead of an ordering pass by the last CTA of the pruning kernel, which the whole
+    // frame used to wait 2-3 us for.
+    unsigned int* s_start = reinterpret_cast<unsigned int*>(smem_raw + 128);
+    // (the first ticket is asked for before the bucket sizes are read: the two round trips overlap)
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u) - p.counter_base;
+    if (p.lists) {
+        // every warp works the prefix sums out (no divergent shuffles), the first one stores them
+        const unsigned int c0 = __ldcg(&p.hist[63 - lane]), c1 = __ldcg(&p.hist[31 - lane]);   // lane l owns k = l and k = 32 + l
+        unsigned int i0 = c0, i1 = c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+            if (lane >= o) { i0 += t0; i1 += t1; }
+        }
+        const unsigned int first_half = __shfl_sync(0xffffffffu, i0, 31);
+        if (tid < 32) {
+            s_start[lane] = i0 - c0;
+            s_start[32 + lane] = first_half + i1 - c1;
+        }
+        __syncthreads();
+    }
+    // position m of the hand-out order -> the tile's descriptor (offset32, n_nodes, flags, tile number); called by whole warps
+    auto ordered_tile = [&p, s_start, lane](unsigned int m) {
+        const unsigned int k = (unsigned int)(__popc(__ballot_sync(0xffffffffu, s_start[lane] <= m)) + __popc(__ballot_sync(0xffffffffu, s_start[32 + lane] <= m))) - 1u;
+        return __ldg(p.lists + (size_t)(63u - k) * (unsigned int)p.list_stride + (m - s_start[k]));
+    };
 
     // ---- phase 2: dynamic tile scheduling over the macro tiles that touch the bound: one ticket per warp tile.  With one
     // ray per pixel the next ticket is requested when the traversal of the current tile is over, so that the atomic's round
@@ -394,8 +425,6 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     // others run dry (with few tiles per warp, e.g. a frame sharded over 8 GPUs, that decided the length of the frame).
     // With supersampling a ticket is a few passes of a warp tile and there are plenty: it is requested up front.
     // Ticket t -> macro tile number (t >> 6) * shard_count + shard_rank of the rm_w x rm_h macro rectangle, warp tile t & 63.
-    unsigned int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u) - p.counter_base;
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
     // Supersampling with 4 or 16 rays per pixel (sp = log2 of that): the samples of a pixel sit in neighbouring lanes instead
     // of being looped over by one lane: a warp pass covers 8 / 2 pixels of one row with one ray per lane, and a warp tile is
@@ -441,8 +470,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             const int k = (int)((ticket << ps) & 63u);
             uint4 td = make_uint4(0u, (uint32_t)p.n_nodes, p.full_flags, 0u);
             int tile_no = (int)macro;
-            if (p.order) {   // heaviest first (see below); an entry carries the tile's descriptor
-                td = __ldg(p.order + macro);
+            if (p.lists) {   // heaviest first; an entry carries the tile's descriptor
+                td = ordered_tile(macro);
                 tile_no = (int)td.w;
             }
             int mx, my;
@@ -451,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
             const int ky = ((k >> 1) & 1) | ((k >> 2) & 2) | ((k >> 3) & 4);
             const int tx0 = mx * kMacroW + kx * kWarpTileW, ty0 = my * kMacroH + ky * kWarpTileH;   // corner of the first warp tile
             ticket = 0xffffffffu;   // placeholder; the real value is broadcast at the end of the iteration
-            if (!p.order && p.desc) {   // natural order: the descriptor is looked up by position
+            if (!p.lists && p.desc) {   // natural order: the descriptor is looked up by position
                 const int slot = slot_of_macro(p.shard_mode, mx, my, p.macro_x, p.shard_count);
                 td = __ldg(reinterpret_cast<const uint4*>(p.desc) + slot);
             }
@@ -559,8 +588,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
         // the tile's descriptor, so the tile and its tree are known after one load
         uint4 td = make_uint4(0u, (uint32_t)p.n_nodes, p.full_flags, 0u);
         int tile_no = (int)(cur >> 6);
-        if (p.order) {
-            td = __ldg(p.order + (cur >> 6));
+        if (p.lists) {
+            td = ordered_tile(cur >> 6);
             tile_no = (int)td.w;
         }
         int mx, my;
@@ -577,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
 
         // this macro tile's pruned tree (csg_prune_kernel): only the primitives its rays can reach, operators whose other
         // operand cannot be reached collapsed away.  n_nodes == 0: every ray of the tile is a Miss.
-        if (!p.order && p.desc) {   // natural order: the descriptor is looked up by position
+        if (!p.lists && p.desc) {   // natural order: the descriptor is looked up by position
             const int slot = slot_of_macro(p.shard_mode, mx, my, p.macro_x, p.shard_count);
             td = __ldg(reinterpret_cast<const uint4*>(p.desc) + slot);
         }

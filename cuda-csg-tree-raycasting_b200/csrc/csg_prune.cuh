@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
     const int tile_ctas = (q.n_tiles + kPruneWarps - 1) / kPruneWarps;
     cudaTriggerProgrammaticLaunchCompletion();   // the frame kernel may be scheduled now; it waits for this grid before it reads our output
     gate_enter(q.gate);
+    if (blockIdx.x == 0 && tid < kCostBuckets && q.hist_next) q.hist_next[tid] = 0u;   // the bucket counters of the NEXT pruned frame (this frame's: q.hist)
 
     if ((int)blockIdx.x >= tile_ctas) {
         // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
@@ -336,52 +337,18 @@ __global__ void __launch_bounds__(kPruneThreads) csg_prune_kernel(const __grid_c
         const uint32_t rk = w.lkind[r0] & 7u;
         flags = (rk >= 3u ? kTileRootLeaf : 0u) | ((rk < 3u && (w.flg[r0] & 1u)) ? kTileRootPure : 0u);
     }
-    // ---- descriptor; heavy tiles (more nodes) are handed out first by the frame kernel: bucket lists, then one ordered list
+    // ---- descriptor; heavy tiles (more nodes) are handed out first by the frame kernel: one list per cost bucket, which the frame
+    // kernel reads through the prefix sums of the bucket sizes (csg_frame.cuh) — no ordering pass behind the last tile
     const uint32_t cost = overflow ? (uint32_t)min(N, 2 * kCostBuckets - 1) : kept;
     const int bucket = (int)min(cost / 2u, (uint32_t)(kCostBuckets - 1));
     if (lane == 0) {
         const TileDesc td = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
                                      : TileDesc{kept ? q.slots_off32 + (uint32_t)slot * (uint32_t)S : 0u, kept, flags, 0u};
         q.desc[slot] = td;
-        if (q.order) {   // the list entry carries the descriptor: the frame kernel gets the tile and its tree in one load
+        if (q.lists) {   // the list entry carries the descriptor: the frame kernel gets the tile and its tree in one load
             const unsigned int rank = atomicAdd(&q.hist[bucket], 1u);
             q.lists[(size_t)bucket * q.n_slots + rank] = make_uint4(td.offset32, td.n_nodes, td.flags, (uint32_t)tile);
-            __threadfence();
         }
-    }
-    if (!q.order) return;
-    unsigned int done = 0;
-    if (lane == 0) done = atomicAdd(q.done, 1u);
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != (unsigned int)q.n_tiles - 1u) return;
-    // last warp of the grid: concatenate the bucket lists, heaviest bucket first, and reset the counters for the next frame
-    __threadfence();
-    static_assert(kCostBuckets == 64, "two buckets per lane");
-    unsigned int* start = reinterpret_cast<unsigned int*>(&w);   // the warp's own scratch is free now
-    {
-        // k = 63 - bucket: heaviest bucket first.  lane l owns k = l and k = 32 + l; start[k] = first position of bucket k in order[]
-        const unsigned int c0 = __ldcg(&q.hist[63 - lane]), c1 = __ldcg(&q.hist[31 - lane]);
-        unsigned int i0 = c0, i1 = c1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-            if (lane >= o) { i0 += t0; i1 += t1; }
-        }
-        const unsigned int first_half = __shfl_sync(0xffffffffu, i0, 31);
-        start[lane] = i0 - c0;
-        start[32 + lane] = first_half + i1 - c1;
-    }
-    __syncwarp();
-    for (int b = lane; b < kCostBuckets; b += 32) q.hist[b] = 0u;
-    if (lane == 0) *q.done = 0u;
-    // every output position looks up its bucket (largest k with start[k] <= i): independent loads, several in flight per lane
-#pragma unroll 4
-    for (int i = lane; i < q.n_tiles; i += 32) {
-        int k = 0;
-#pragma unroll
-        for (int step = 32; step >= 1; step >>= 1)
-            if (k + step < kCostBuckets && start[k + step] <= (unsigned int)i) k += step;
-        q.order[i] = __ldcg(q.lists + (size_t)(63 - k) * q.n_slots + ((unsigned int)i - start[k]));
     }
 }
 
@@ -423,8 +390,6 @@ struct FlatTileSmem {                  // followed by uint16_t A[n_pad], S[n_pad
     unsigned char done[kSlotMax];      // box and flags are final
     unsigned int wsum[kFlatThreadsMax / 32];
     float plane[5][4];                 // the tile's frustum
-    unsigned int start[kCostBuckets];  // ordering tail
-    unsigned int last;
     unsigned int list_pos;             // this tile's entry in the bucket lists
 };
 
@@ -461,6 +426,7 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
     const int N = q.n_nodes, S = q.slot_nodes;
     cudaTriggerProgrammaticLaunchCompletion();   // the frame kernel may be scheduled now; it waits for this grid before it reads our output
     gate_enter(q.gate);
+    if (blockIdx.x == 0 && tid < kCostBuckets && q.hist_next) q.hist_next[tid] = 0u;   // the bucket counters of the NEXT pruned frame (this frame's: q.hist)
 
     if ((int)blockIdx.x >= q.n_tiles) {
         // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
@@ -578,7 +544,7 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
     const bool overflow = kept > (uint32_t)S;
     // heavy tiles (more nodes) are handed out first by the frame kernel: bucket lists now (the round trips of the atomic and
     // the list entry overlap the emission below), one ordered list at the end
-    if (tid == 0 && q.order) {
+    if (tid == 0 && q.lists) {
         const uint32_t cost = overflow ? (uint32_t)min(N, 2 * kCostBuckets - 1) : kept;
         const int bucket = (int)min(cost / 2u, (uint32_t)(kCostBuckets - 1));
         w.list_pos = (unsigned int)bucket * (unsigned int)q.n_slots + atomicAdd(&q.hist[bucket], 1u);   // filled in below
@@ -680,62 +646,14 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
     }
 
     PROBE(7);
-    // ---- descriptor, and the count of finished tiles (release: this tile's list entry; acquire: everybody else's)
+    // ---- descriptor and list entry (the entry carries the descriptor: the frame kernel gets the tile and its tree in one load)
     if (tid == 0) {
         const TileDesc td = overflow ? TileDesc{0u, (uint32_t)N, q.full_flags, 0u}
                                      : TileDesc{kept ? q.slots_off32 + (uint32_t)slot * (uint32_t)S : 0u, kept, flags, 0u};
         q.desc[slot] = td;
-        unsigned int last = 0u;
-        if (q.order) {
-            // the list entry carries the descriptor: the frame kernel gets the tile and its tree in one load
-            q.lists[w.list_pos] = make_uint4(td.offset32, td.n_nodes, td.flags, (uint32_t)tile);
-            unsigned int before;
-            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(before) : "l"(q.done) : "memory");
-            last = before == (unsigned int)q.n_tiles - 1u ? 1u : 0u;
-        }
-        w.last = last;
+        if (q.lists) q.lists[w.list_pos] = make_uint4(td.offset32, td.n_nodes, td.flags, (uint32_t)tile);
     }
-    __syncthreads();
     PROBE(8);
-    if (!w.last) return;
-    // last CTA of the grid: concatenate the bucket lists, heaviest bucket first, and reset the counters for the next frame
-    static_assert(kCostBuckets == 64, "two buckets per lane");
-    if (tid < 32) {
-        // k = 63 - bucket: heaviest bucket first.  lane l owns k = l and k = 32 + l; start[k] = first position of bucket k in order[]
-        const int lane = tid;
-        const unsigned int c0 = __ldcg(&q.hist[63 - lane]), c1 = __ldcg(&q.hist[31 - lane]);
-        unsigned int i0 = c0, i1 = c1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-            if (lane >= o) { i0 += t0; i1 += t1; }
-        }
-        const unsigned int first_half = __shfl_sync(0xffffffffu, i0, 31);
-        w.start[lane] = i0 - c0;
-        w.start[32 + lane] = first_half + i1 - c1;
-    }
-    __syncthreads();
-    for (int b = tid; b < kCostBuckets; b += T) q.hist[b] = 0u;
-    if (tid == 0) *q.done = 0u;
-    // every output position looks up its bucket (largest k with start[k] <= i); batches of four loads in flight per thread
-    for (int i0 = tid; i0 < q.n_tiles; i0 += 4 * T) {
-        const uint4* src[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned int i = (unsigned int)min(i0 + j * T, q.n_tiles - 1);
-            int k = 0;
-#pragma unroll
-            for (int step = 32; step >= 1; step >>= 1)
-                if (k + step < kCostBuckets && w.start[k + step] <= i) k += step;
-            src[j] = q.lists + (size_t)(63 - k) * q.n_slots + (i - w.start[k]);
-        }
-        uint4 v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = __ldcg(src[j]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (i0 + j * T < q.n_tiles) q.order[i0 + j * T] = v[j];
-    }
     PROBE(9);
 }
 

@@ -100,9 +100,9 @@ struct Shard {  // one GPU's share of the frame
     int* d_parent = nullptr;
     uint2* d_topo = nullptr;             // per node: meta word, end of its subtree (csg_prune_flat_kernel)
     float4* d_leaf_boxes = nullptr;      // per primitive: culling box (world space) + node number, 2 x float4
-    unsigned int* d_hist = nullptr;      // kCostBuckets counters + 1 "done" counter
+    unsigned int* d_hist = nullptr;      // 2 x kCostBuckets counters: the bucket sizes of the last pruned frame, and the (zeroed) set of the next one
+    int hist_cur = 0;                    // which set the tile lists currently belong to
     uint4* d_lists = nullptr;            // kCostBuckets x n_slots tile descriptors
-    uint4* d_order = nullptr;            // n_slots ordered tile descriptors
     int n_slots = 0;
     float4* d_prims = nullptr;
     unsigned int* d_counter = nullptr;
@@ -321,7 +321,8 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
     fp.tile_counter = s.d_counter;
     fp.pool = s.d_pool;
     fp.desc = c->prune ? s.d_desc : nullptr;
-    fp.order = c->prune ? s.d_order : nullptr;
+    fp.lists = c->prune ? s.d_lists : nullptr;   // (hist: set by enqueue_frame once it knows whether this frame prunes)
+    fp.list_stride = s.n_slots;
     fp.full_flags = c->full_flags;
     fp.prims = s.d_prims;
     fp.n_nodes = (int)c->tree.nodes.size();
@@ -450,8 +451,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.leaf_boxes = s.d_leaf_boxes; q.n_leaves = (int)(c->tree.leaf_boxes.size() / 8);
             q.mark_words = c->mark_words; q.marks_first = c->marks_first;
             q.topo = s.d_topo;
-            q.n_slots = s.n_slots; q.hist = s.d_hist; q.done = s.d_hist ? s.d_hist + kCostBuckets : nullptr;
-            q.lists = s.d_lists; q.order = s.d_order;
+            q.n_slots = s.n_slots; q.lists = s.d_lists;   // (hist / hist_next: below, they alternate and must stay out of the view-cache comparison)
             // (heaviest-first hand-out also pays on a frame sharded over 8 GPUs, 2-3 tiles per warp: the slowest of the eight shards
             // takes 63.9 us with it and 67.3 us with the natural order, although shard 0 alone is 3 us faster without the ordering pass)
             q.pool = s.d_pool; q.desc = s.d_desc; q.slot_nodes = c->slot_nodes; q.flat_max = c->flat_leaves; q.flat_tree_max = fp.warp_tree_nodes;
@@ -462,6 +462,14 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             s.last_q = q;
             s.last_q_valid = true;
             q.gate = gate;
+            if (s.d_hist) {
+                // a pruned frame counts into the set of counters the previous pruned frame zeroed, and zeroes the other one
+                const int set = cached ? s.hist_cur : s.hist_cur ^ 1;
+                q.hist = s.d_hist + set * kCostBuckets;
+                q.hist_next = s.d_hist + (set ^ 1) * kCostBuckets;
+                s.hist_cur = set;
+                fp.hist = q.hist;
+            }
             const int stage_ctas = std::max(1, std::min(64, (fp.n_nodes + kPruneThreads - 1) / kPruneThreads));
             // the frame's start mark goes in right in front of its first launch (all host-side preparation is done by now: on an
             // idle GPU whatever the host does between the two calls would show up as device time)
@@ -677,10 +685,9 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
             CUC(cudaMemcpy(s.d_leaf_boxes, c->tree.leaf_boxes.data(), c->tree.leaf_boxes.size() * sizeof(float), cudaMemcpyHostToDevice));
             const char* no_order = std::getenv("CSG_B200_NO_ORDER");   // tuning aid: tiles handed out in their natural order
             if (c->prune && s.n_slots <= 65535 && !(no_order && no_order[0] == '1')) {   // bounds the bucket lists (64 x n_slots x 16 bytes)
-                CUC(cudaMalloc(&s.d_hist, (kCostBuckets + 1) * sizeof(unsigned int)));
-                CUC(cudaMemset(s.d_hist, 0, (kCostBuckets + 1) * sizeof(unsigned int)));
+                CUC(cudaMalloc(&s.d_hist, 2 * kCostBuckets * sizeof(unsigned int)));
+                CUC(cudaMemset(s.d_hist, 0, 2 * kCostBuckets * sizeof(unsigned int)));
                 CUC(cudaMalloc(&s.d_lists, (size_t)kCostBuckets * std::max(s.n_slots, 1) * sizeof(uint4)));
-                CUC(cudaMalloc(&s.d_order, (size_t)std::max(s.n_slots, 1) * sizeof(uint4)));
             }
             if (c->prune_smem > 48 * 1024)
                 CUC(cudaFuncSetAttribute(csg_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->prune_smem));
@@ -944,7 +951,6 @@ void csg_free_context(csg_context* c)
         cudaFree(s.d_leaf_boxes);
         cudaFree(s.d_hist);
         cudaFree(s.d_lists);
-        cudaFree(s.d_order);
         cudaFree(s.d_prims);
         cudaFree(s.d_counter);
         if (s.h_tan) cudaFreeHost(s.h_tan);

@@ -136,6 +136,9 @@ class Raycaster {
     void SetSupersampling(int samplesPerAxis) { if (csg_set_supersampling(ctx_, samplesPerAxis) != CSG_OK) throw std::runtime_error(csg_last_error()); }
     void SetPruning(int mode) { if (csg_set_pruning(ctx_, mode) != CSG_OK) throw std::runtime_error(csg_last_error()); }
     void SetViewCache(bool on) { if (csg_set_view_cache(ctx_, on ? 1 : 0) != CSG_OK) throw std::runtime_error(csg_last_error()); }
+    // the CUDA stream (cudaStream_t) frames are enqueued on — the place of the default stream Raycast shares with the GL map / unmap
+    // (RenderManager.cpp:58-84): work the caller queues there is ordered against the frames on the device
+    void* Stream() { void* s = nullptr; if (csg_stream(ctx_, &s) != CSG_OK) throw std::runtime_error(csg_last_error()); return s; }
     csg_context* context() { return ctx_; }
 
   private:
