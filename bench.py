@@ -640,6 +640,8 @@ def bench_ours(args):
                         "warp_instructions_per_frame": fk["warp_instructions"], "frame_kernel_us_in_profile": fk["us"],
                         "frame_kernel_ms_live": kernel_ms, "frame_kernel_share_of_step": share, "fma_pipe_pct": fk["fma_pipe_pct"], "alu_pipe_pct": fk["alu_pipe_pct"],
                         "issue_active_pct": fk["issue_active_pct"], "local_memory_instructions": (fk.get("local_load_instructions") or 0) + (fk.get("local_store_instructions") or 0),
+                        "sm_instruction_cache_hit_pct": fk.get("sm_instruction_cache_hit_pct"),
+                        "gpc_cache_instruction_requests_pct_of_peak": fk.get("gpc_cache_instruction_requests_pct_of_peak"),
                         "source": "profiles/ncu_summary.json (" + prof.get("tag", "?") + ")",
                         "profile_matches_source": matches, "source_hash": source_hash(), "profile_source_hash": prof.get("source_hash")}
     except Exception:

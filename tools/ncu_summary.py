@@ -34,7 +34,11 @@ keep = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "lau
         "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "sm__cycles_elapsed.max", "lts__t_sectors_op_write.sum",
         "lts__t_bytes.sum", "sm__cycles_active.avg", "sm__cycles_elapsed.avg",
         "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed", "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed",
-        "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores"]
+        "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
+        # instruction fetch: the SMs' instruction caches and what reaches the GPC-level cache (DESIGN 4.2 "Instruction cache")
+        "sm__icc_requests.sum", "sm__icc_request_hit_rate.pct", "gcc__cache_requests_type_instruction.sum",
+        "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
 summ = []
 for r in data:
     d = {}
@@ -75,7 +79,10 @@ if frame:
                            "fp32_flop_per_cycle": (fadd + fmul + 2 * ffma) / cyc if cyc else None, "fp32_flop_per_cycle_peak": 148 * 128 * 2,
                            "local_load_instructions": num(d, "sass__inst_executed_local_loads"),
                            "local_store_instructions": num(d, "sass__inst_executed_local_stores"),
-                           "registers": num(d, "launch__registers_per_thread")}
+                           "registers": num(d, "launch__registers_per_thread"),
+                           "sm_instruction_cache_hit_pct": num(d, "sm__icc_request_hit_rate.pct"),
+                           "gpc_cache_instruction_requests_pct_of_peak": num(d, "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed"),
+                           "no_instruction_stall_per_issue": num(d, "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio")}
 if prune:
     d = prune[-1]
     out["prune_kernel"] = {"us": num(d, "gpu__time_duration.sum"), "warp_instructions": num(d, "smsp__inst_executed.sum"),
