@@ -452,6 +452,27 @@ def test_sample_parallel_supersampling_equals_the_serial_loop(k, csg, monkeypatc
     assert np.array_equal(out["0"][1], out["1"][1])
 
 
+@pytest.mark.parametrize("scene_id", ["synthetic:300", "corpus:testWikipedia", "corpus:testSphereCutByCubesAndCylinder", "corpus:testCheese256"])
+def test_tickets_of_two_warp_tiles_equal_tickets_of_one(scene_id, csg, monkeypatch):
+    """The kPair kernels (one ray per pixel, two neighbouring warp tiles per ticket, tree copied with cp.async) against the one-tile
+    kernels, forced either way through CSG_B200_PAIR: every output mode, frames with partial tiles on both axes, scenes with and
+    without cylinders (both kCyl instantiations)."""
+    if scene_id.startswith("corpus:") and scene_id[7:] not in scenes.corpus_names():
+        pytest.skip("scene corpus not staged")
+    txt = csg.Scene.generate_text(300, seed=5) if scene_id.startswith("synthetic:") else scenes.text_of(scene_id)
+    light = csg.Light()
+    for (w, h), cam in (((203, 117), csg.Camera(pos=(0.0, 0.0, 5.0))), ((640, 360), csg.Camera(pos=(0.3, 0.2, 4.0), pitch=-0.05, yaw=0.1))):
+        out = {}
+        for pair in ("0", "1"):
+            monkeypatch.setenv("CSG_B200_PAIR", pair)
+            ctx = csg.Scene.parse(txt).upload(w, h)
+            hit, prim, t = ctx.render_aov(cam)
+            out[pair] = (ctx.render(cam, light).copy(), ctx.render_f32(cam, light).copy(), hit.copy(), prim.copy(), t.copy())
+            ctx.close()
+        for a, b in zip(out["0"], out["1"]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
 def test_view_cache_reuses_the_trees_of_an_unchanged_view(csg):
     """csg_set_view_cache: same camera, moving light -> the pruning kernel is skipped, the frames are what they would be anyway."""
     txt = scenes.INLINE["nested"]
