@@ -316,8 +316,6 @@ void fill_params(const csg_context* c, const Shard& s, const csg_camera* cam, co
         const bool owns_fb = s.rank == 0 && !c->external_target;
         fp.fill_stride = owns_fb ? 1 : c->shard_count;
         fp.fill_first = owns_fb ? 0 : (c->external_target ? s.rank : (1 << 30));
-        if (const char* e = std::getenv("CSG_B200_FILL_SHARED"))   // experiment: every shard fills its share of the background (peer stores over NVLink)
-            if (e[0] == '1' && c->shard_count > 1) { fp.fill_stride = c->shard_count; fp.fill_first = s.rank; }
     }
     fp.counter_base = s.counter_base;
     fp.tile_counter = s.d_counter;
