@@ -428,6 +428,19 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
     gate_enter(q.gate);
     if (blockIdx.x == 0 && tid < kCostBuckets && q.hist_next) q.hist_next[tid] = 0u;   // the bucket counters of the NEXT pruned frame (this frame's: q.hist)
 
+    if (blockIdx.x < 2u) {
+        // the first two CTAs ask the L2 for everything this kernel and the frame kernel read from the scene (leaf boxes, topology,
+        // node records; primitive records): one request per 128-byte line, answered while the frustum is worked out
+        auto pf = [tid](const void* base, size_t bytes, unsigned int part) {
+            const char* pc = static_cast<const char*>(base);
+            for (size_t o = ((size_t)part * T + tid) * 128u; o < bytes; o += 2u * T * 128u)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pc + o));
+        };
+        pf(q.leaf_boxes, (size_t)q.n_leaves * 32u, blockIdx.x);
+        pf(q.topo, (size_t)N * 8u, blockIdx.x);
+        pf(q.nodes, (size_t)N * 32u, blockIdx.x);
+        if (q.prims) pf(q.prims, (size_t)q.n_prims * 80u, blockIdx.x);
+    }
     if ((int)blockIdx.x >= q.n_tiles) {
         // staging CTAs: origin-relative copy of the whole tree at the head of the pool, for tiles whose tree does not fit a slot
         const int nb = (int)gridDim.x - q.n_tiles;
@@ -582,48 +595,45 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
         }
         __syncthreads();
         PROBE(5);
-        // ---- bottom-up refit in rounds, by one warp (warp barriers only): an operator whose operands are both done computes
-        //      its box and flags; rounds = height of the tile's tree (a handful), shared memory only
-        if (tid < 32) {
-            for (;;) {
-                unsigned int now = 0u;
-                bool pending = false;
-                for (int i = tid, k = 0; i < (int)kept; i += 32, ++k) {
-                    const uint32_t m = w.meta[i], kind = m & 7u;
-                    if (kind >= 3u || w.done[i]) continue;
-                    const int a = i + 1, b = (int)(m >> 8);
-                    if (!(w.done[a] && w.done[b])) { pending = true; continue; }
-                    const float* bl = w.box[a];
-                    const float* br = w.box[b];
-                    float* bo = w.box[i];
-                    if (kind == 0u) {                   // Union: both operands
+        // ---- bottom-up refit in rounds, by the whole CTA: an operator whose operands are both done computes its box and flags,
+        //      and is marked done behind a barrier (nobody reads a record that is being written); rounds = height of the tile's
+        //      tree (a handful), shared memory only
+        for (;;) {
+            unsigned int now = 0u;
+            bool pending = false;
+            for (int i = tid, k = 0; i < (int)kept; i += T, ++k) {
+                const uint32_t m = w.meta[i], kind = m & 7u;
+                if (kind >= 3u || w.done[i]) continue;
+                const int a = i + 1, b = (int)(m >> 8);
+                if (!(w.done[a] && w.done[b])) { pending = true; continue; }
+                const float* bl = w.box[a];
+                const float* br = w.box[b];
+                float* bo = w.box[i];
+                if (kind == 0u) {                   // Union: both operands
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) { bo[c] = fminf(bl[c], br[c]); bo[3 + c] = fmaxf(bl[3 + c], br[3 + c]); }
-                    } else if (kind == 1u) {            // Difference: a subset of the left operand
+                    for (int c = 0; c < 3; ++c) { bo[c] = fminf(bl[c], br[c]); bo[3 + c] = fmaxf(bl[3 + c], br[3 + c]); }
+                } else if (kind == 1u) {            // Difference: a subset of the left operand
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) bo[c] = bl[c];
-                    } else {                            // Intersection: a subset of both; the smaller box
-                        float vl = 1.f, vr = 1.f;
+                    for (int c = 0; c < 6; ++c) bo[c] = bl[c];
+                } else {                            // Intersection: a subset of both; the smaller box
+                    float vl = 1.f, vr = 1.f;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) { vl *= fmaxf(bl[3 + c] - bl[c], 0.f); vr *= fmaxf(br[3 + c] - br[c], 0.f); }
-                        const float* bs = vl <= vr ? bl : br;
+                    for (int c = 0; c < 3; ++c) { vl *= fmaxf(bl[3 + c] - bl[c], 0.f); vr *= fmaxf(br[3 + c] - br[c], 0.f); }
+                    const float* bs = vl <= vr ? bl : br;
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) bo[c] = bs[c];
-                    }
-                    const uint32_t fl = w.flg[a], fr = w.flg[b];
-                    w.flg[i] = (unsigned char)(((kind == 0u) ? (fl & fr & 5u) : 0u) | (fl & fr & 2u));
-                    w.cnt[i] = (unsigned char)min((int)w.cnt[a] + (int)w.cnt[b], 255);
-                    w.lmask[i] = (w.lmask[a] << 1) | (w.lmask[b] << ((2u * w.cnt[a]) & 31u));   // the left subtree holds 2 cnt - 1 records, behind this one
-                    now |= 1u << k;
+                    for (int c = 0; c < 6; ++c) bo[c] = bs[c];
                 }
-                __syncwarp();
-                for (int i = tid, k = 0; i < (int)kept; i += 32, ++k)
-                    if ((now >> k) & 1u) w.done[i] = 1;
-                __syncwarp();
-                if (!__any_sync(0xffffffffu, pending)) break;
+                const uint32_t fl = w.flg[a], fr = w.flg[b];
+                w.flg[i] = (unsigned char)(((kind == 0u) ? (fl & fr & 5u) : 0u) | (fl & fr & 2u));
+                w.cnt[i] = (unsigned char)min((int)w.cnt[a] + (int)w.cnt[b], 255);
+                w.lmask[i] = (w.lmask[a] << 1) | (w.lmask[b] << ((2u * w.cnt[a]) & 31u));   // the left subtree holds 2 cnt - 1 records, behind this one
+                now |= 1u << k;
             }
+            __syncthreads();
+            for (int i = tid, k = 0; i < (int)kept; i += T, ++k)
+                if ((now >> k) & 1u) w.done[i] = 1;
+            if (!__syncthreads_or(pending ? 1 : 0)) break;   // (also the barrier in front of the operator records)
         }
-        __syncthreads();
         PROBE(6);
         // ---- records of the operators
         for (int i = tid; i < (int)kept; i += T) {

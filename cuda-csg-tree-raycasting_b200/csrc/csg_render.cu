@@ -451,6 +451,7 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             q.leaf_boxes = s.d_leaf_boxes; q.n_leaves = (int)(c->tree.leaf_boxes.size() / 8);
             q.mark_words = c->mark_words; q.marks_first = c->marks_first;
             q.topo = s.d_topo;
+            q.prims = s.d_prims; q.n_prims = (int)c->tree.prims.size();
             q.n_slots = s.n_slots; q.lists = s.d_lists;   // (hist / hist_next: below, they alternate and must stay out of the view-cache comparison)
             // (heaviest-first hand-out also pays on a frame sharded over 8 GPUs, 2-3 tiles per warp: the slowest of the eight shards
             // takes 63.9 us with it and 67.3 us with the natural order, although shard 0 alone is 3 us faster without the ordering pass)
