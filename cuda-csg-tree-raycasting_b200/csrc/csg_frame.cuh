@@ -774,14 +774,16 @@ __global__ void __launch_bounds__(kThreads, min_blocks_for(kThreads)) csg_frame_
     // ---- join of a sharded frame (GateParams): a peer's last CTA tells the root that all of this shard's pixels have landed in
     // the root's framebuffer; the root's last CTA waits for every peer before the kernel (and with it the frame) ends
     if (p.gate.role != GATE_NONE) {
-        __threadfence_system();   // this thread's pixel stores (over NVLink on a peer) are performed
         __syncthreads();
         if (tid == 0) {
+            // behind the barrier one fence covers the pixel stores of the whole CTA (over NVLink on a peer): they are performed,
+            // system-wide, before this CTA is counted
+            if (p.gate.role == GATE_PEER) __threadfence_system();
             const unsigned int before = atomicAdd(p.gate.exit_counter, 1u);
             if (before == gridDim.x - 1u) {
                 *p.gate.exit_counter = 0u;   // ready for the next frame
                 SPROBE(4);
-                __threadfence_system();
+                // (release: ordered behind every CTA's count this thread has just observed, and with them behind their fenced stores)
                 if (p.gate.role == GATE_PEER) st_release_sys(&p.gate.words->done[p.gate.rank], p.gate.seq);
                 else
                     for (int r = 1; r < p.gate.n_shards; ++r) wait_seq(&p.gate.words->done[r], p.gate.seq, p.gate.err);

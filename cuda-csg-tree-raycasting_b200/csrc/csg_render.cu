@@ -435,7 +435,10 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             gate.words = s.sync_words;
             gate.exit_counter = s.d_exit;
             gate.err = s.d_err;
+            gate.enter = 1;
+            gate.local_start = s.d_exit + 32;   // (its own 128-byte line)
         }
+        bool gate_entered = false;   // a kernel of this frame in front of the frame kernel has been through the gate
         {   // per-tile pruned trees + the staged copy of the whole tree for this camera
             PruneParams q;
             std::memset(&q, 0, sizeof q);
@@ -491,9 +494,10 @@ int enqueue_frame(csg_context* c, const csg_camera* cam, const float light[3], i
             }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return fail(CSG_ERR_CUDA, std::string("prune kernel launch: ") + cudaGetErrorString(e));
-            if (!cached) c->launches++;
+            if (!cached) { c->launches++; gate_entered = true; }
         }
         fp.gate = gate;
+        if (gate_entered) fp.gate.enter = 0;   // the frame kernel runs behind the pruning kernel (grid dependency), which has opened / passed the gate
         int rc = CSG_OK;
         if (mode == OUT_RGBA8) {
             fp.out = out ? out : (void*)(shard_mode ? s.local_fb : s.target);
@@ -711,8 +715,8 @@ int create_context(const csg_scene* scene, int width, int height, const std::vec
         CUC(cudaHostGetDevicePointer(&s.d_tan, s.h_tan, 0));
         CUC(cudaMalloc(&s.d_counter, sizeof(unsigned int)));
         CUC(cudaMemset(s.d_counter, 0, sizeof(unsigned int)));
-        CUC(cudaMalloc(&s.d_exit, sizeof(unsigned int)));
-        CUC(cudaMemset(s.d_exit, 0, sizeof(unsigned int)));
+        CUC(cudaMalloc(&s.d_exit, 64 * sizeof(unsigned int)));   // [0]: finished CTAs; [32]: this shard's copy of the start word (GateParams::local_start)
+        CUC(cudaMemset(s.d_exit, 0, 64 * sizeof(unsigned int)));
         CUC(cudaHostAlloc(&s.h_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
         *s.h_err = 0;
         CUC(cudaHostGetDevicePointer(&s.d_err, s.h_err, 0));
