@@ -418,7 +418,7 @@ __device__ __forceinline__ void cta_scan_u16(unsigned short* v, int n, int chunk
 }
 
 template <int T>
-__global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant__ PruneParams q)
+__global__ void __launch_bounds__(T, 1024 / T) csg_prune_flat_kernel(const __grid_constant__ PruneParams q)
 {
     extern __shared__ __align__(16) unsigned char psm[];
     const int tid = threadIdx.x;
@@ -533,16 +533,24 @@ __global__ void __launch_bounds__(T) csg_prune_flat_kernel(const __grid_constant
             }
         }
         if (!__syncthreads_or(gone ? 1 : 0)) break;
-        // Sv holds the alive flag of every primitive: clear those below the operators that are gone, rebuild A from the flags
+        // Sv holds the alive flag of every primitive: clear those below the operators that are gone, rebuild A from the flags.
+        // Two parallel passes: the operators that are gone are marked (Sv = 2), then every primitive that is still alive walks up
+        // its ancestors (a dozen cached loads) and drops out when one of them is marked.  (Until the end of round 2 the thread that
+        // found an operator gone cleared its whole subtree by itself: 23 us for a tile that sees Cheese512's spheres but not its
+        // cube — the Difference at the root goes, 1 024 nodes are cleared one by one.)
         for (int n = tid; n < N; n += T) {
             const uint2 tp = __ldg(&q.topo[n]);
             const uint32_t kind = tp.x & 7u;
             if (kind >= 3u) continue;
             const unsigned int an = A[n], ar = A[(tp.x >> 8) - 1u], ae = A[tp.y - 1u];
             const bool hl = ar != an, hr = ae != ar;
-            if (kind == 1u ? (!hl && hr) : (kind == 2u && hl != hr))   // atomics: operators that are gone may be nested
-                for (unsigned int m = (unsigned int)n + 1u; m < tp.y; ++m)
-                    atomicAnd(reinterpret_cast<unsigned int*>(Sv) + (m >> 1), (m & 1u) ? 0x0000ffffu : 0xffff0000u);
+            if (kind == 1u ? (!hl && hr) : (kind == 2u && hl != hr)) Sv[n] = 2;
+        }
+        __syncthreads();
+        for (int n = tid; n < N; n += T) {
+            if ((__ldg(&q.topo[n]).x & 7u) < 3u || !Sv[n]) continue;
+            for (int a = __ldg(&q.parent[n]); a >= 0; a = __ldg(&q.parent[a]))
+                if (Sv[a] == 2) { Sv[n] = 0; break; }
         }
         __syncthreads();
         for (int n = tid; n < N; n += T) A[n] = ((__ldg(&q.topo[n]).x & 7u) >= 3u) ? Sv[n] : (unsigned short)0;
