@@ -234,8 +234,9 @@ def preorder_records(tree):
     return [tuple(x) for x in out]
 
 
-def prune_by_prefix_sums(kind, meta, end, alive):
-    """What csg_prune_flat_kernel does, step for step, in numpy."""
+def prune_by_prefix_sums(kind, meta, end, alive, par=None):
+    """What csg_prune_flat_kernel does, step for step, in numpy.  par = the parent array the kernel walks when it clears the
+    primitives below operators that are gone (None: clear the preorder range of every such operator, the definition)."""
     n = len(kind)
     is_leaf = kind >= 3
     right = (meta >> 8).astype(np.int64)
@@ -253,8 +254,18 @@ def prune_by_prefix_sums(kind, meta, end, alive):
         gone = (~is_leaf) & (((kind == K_DIFF) & ~hl & hr) | ((kind == K_INTER) & (hl != hr)))
         if not gone.any():
             break
-        for i in np.nonzero(gone)[0]:
-            flags[i + 1:end[i]] = 0
+        if par is None:
+            for i in np.nonzero(gone)[0]:
+                flags[i + 1:end[i]] = 0
+        else:
+            # the kernel's two parallel passes: gone operators are marked, every primitive still alive walks up its ancestors
+            for i in np.nonzero(is_leaf & (flags != 0))[0]:
+                a = int(par[i])
+                while a >= 0:
+                    if gone[a]:
+                        flags[i] = 0
+                        break
+                    a = int(par[a])
     S = np.cumsum(surv)
     recs = []
     for i in np.nonzero(surv)[0]:
@@ -278,6 +289,8 @@ def test_prefix_sum_pruning_equals_the_recursive_collapse(scene_id, optimize, cs
         want = preorder_records(collapse_flat(kind, meta, alive))
         got, rounds = prune_by_prefix_sums(kind, meta, end, alive)
         assert got == want
+        got_walk, rounds_walk = prune_by_prefix_sums(kind, meta, end, alive, par)
+        assert (got_walk, rounds_walk) == (got, rounds)   # clearing by the walk up the parents == clearing the preorder ranges
         saw_rounds = max(saw_rounds, rounds)
         # record i+1 is the left operand of operator record i; a record's subtree is contiguous
         for i, (node, ri) in enumerate(got):

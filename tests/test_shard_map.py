@@ -63,3 +63,18 @@ def test_4k_full_frame_matches_the_division_by_multiply_high():
     for count in (1, 2, 4, 8):
         own = hand_out(60, 68, (0, 0, 60, 68), 0, count)
         assert all(own[(mx, my)] == (my * 60 + mx) % count for (mx, my) in own)
+
+
+def test_a_width_coprime_to_the_gpu_count_spreads_every_shard_over_every_column():
+    """Why fill_params widens the traced rectangle of a sharded frame (csg_render.cu): tile j goes to shard j mod N along the
+    rows, so with a width that is a multiple of N a shard owns whole columns of the frame (Cheese512 @ 4K: 24 x 46 tiles on
+    8 GPUs — the shards' loads then differ by what their columns hold), with a coprime width every row is shifted against the
+    one above and every shard has tiles in every column."""
+    own24 = hand_out(60, 68, (18, 11, 24, 46), 0, 8)
+    for rank in range(8):
+        assert {mx for (mx, my), r in own24.items() if r == rank} == {18 + rank, 26 + rank, 34 + rank}
+    own25 = hand_out(60, 68, (18, 11, 25, 46), 0, 8)
+    for rank in range(8):
+        assert {mx for (mx, my), r in own25.items() if r == rank} == set(range(18, 43))
+        counts = [sum(1 for (mx, my), r in own25.items() if r == rank and mx == col) for col in range(18, 43)]
+        assert max(counts) - min(counts) <= 1      # 46 rows of a column dealt out to 8 shards: 5 or 6 each
