@@ -1,5 +1,7 @@
 #!/bin/bash
 # 2-GPU visit: why a peer needs longer than the root for the same share (NVLink pixel stores? the per-thread system fence?)
+# (ab/lib_exp*.so: builds of a scratch copy of csrc/ with an environment switch CSG_EXP_PEER_LOCAL — peers store into local memory, wrong
+# frame, timing only — and -DCSG_EXP_JOIN1 = one system fence per CTA; results: profiles/r02i_peer_experiment*_2gpu.*)
 mkdir -p gpurun_out; : > gpurun_out/peer_exp.jsonl
 N=$(nvidia-smi -L | wc -l)
 P=$PWD/cuda-csg-tree-raycasting_b200

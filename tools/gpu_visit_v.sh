@@ -1,6 +1,7 @@
 #!/bin/bash
 # 2-GPU visit: gate / join changes (first kernel only enters the gate, one poller per peer, relaxed start word, one fence per CTA)
 # against the r02h build; in-process multi-GPU test; torchrun bench with parity_n; per-device timeline
+# (ab/lib_r02h.so: the previous build of the library, kept beside the new one for the A/B; results: profiles/r02i_gate_join_ab_2gpu.jsonl)
 mkdir -p gpurun_out; : > gpurun_out/peer_ab.jsonl
 N=$(nvidia-smi -L | wc -l)
 P=$PWD/cuda-csg-tree-raycasting_b200

@@ -1,6 +1,7 @@
 #!/bin/bash
 # last visit of round 2: records of the final build (tests, bench, ncu launch list + full capture), then the balance of the tile
 # hand-out before / after the traced rectangle is widened to a width coprime to the GPU count
+# (ab/lib_r02i.so: the previous build; results: profiles/r02j_shard_balance.jsonl — this first try was 16 us slower per shard)
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests -q -m gpu 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
 timeout 300 python bench.py 2>gpurun_out/bench.err | tail -1 > gpurun_out/bench.json; cut -c1-300 gpurun_out/bench.json
